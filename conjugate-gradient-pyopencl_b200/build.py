@@ -1,0 +1,62 @@
+"""Build recipe for liboclcg.so (nvcc, sm_100a only) -- the CMakeLists.txt:15-19 of the reference.
+
+    python conjugate-gradient-pyopencl_b200/build.py [--force]
+
+Outputs (all git-ignored, all travel to the GPU box with the snapshot):
+    conjugate-gradient-pyopencl_b200/liboclcg.so   the library the package loads
+    build/liboclcg.so                              where p_h-PY_C-CL.py:38 looks for it
+    liboclcg.so                                    where p_helmholtz.py:29 looks for it
+"""
+import os
+import shutil
+import subprocess
+import sys
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(PKG)
+CSRC = os.path.join(PKG, "csrc")
+LIB = os.path.join(PKG, "liboclcg.so")
+SOURCES = ["cgb200.cu"]
+NVCC_FLAGS = [
+    "-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-shared",
+    "--cudart", "static",
+]
+
+
+def _nvcc():
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found: liboclcg.so cannot be built (there is no CPU fallback)")
+
+
+def _stale():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
+    deps += [os.path.join(ROOT, "include", f) for f in os.listdir(os.path.join(ROOT, "include"))]
+    deps.append(os.path.abspath(__file__))
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    """Compile (if stale) and place the copies the reference drivers expect.  Returns the path."""
+    if force or _stale():
+        cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+              ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+        # the image exports CC/CXX pointing at a wrapper without OpenMP specs; nvcc wants plain g++
+        env = dict(os.environ)
+        env.pop("CC", None)
+        env.pop("CXX", None)
+        subprocess.check_call(cmd, cwd=CSRC, env=env)
+    for dst in (os.path.join(ROOT, "build", "liboclcg.so"), os.path.join(ROOT, "liboclcg.so")):
+        os.makedirs(os.path.dirname(dst), exist_ok=True)
+        if not os.path.exists(dst) or os.path.getmtime(dst) < os.path.getmtime(LIB):
+            shutil.copy2(LIB, dst)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,880 @@
+// cgb200.cu -- host orchestration and the C ABI of liboclcg.so.
+//
+// Replaces the host side of the reference, clcg.c:111-466: device/buffer set-up,
+// the initialisation (q = A x0, r = b - q, d = r, delta = r.r) and the CG loop.
+// Where the reference re-creates a context, JIT-compiles five kernels and uploads
+// the matrix on every call, a `cgb200_handle` keeps the CSR matrix, the work
+// vectors, the scalar state and the captured CUDA graphs resident on one B200.
+//
+// The product path has no CPU fallback: without a CUDA device every entry point
+// fails with CGB200_ERR_CUDA.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/cgb200.h"
+#include "../../include/clcg.h"
+#include "kernels.cuh"
+
+using namespace cgb;
+
+// ---------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU(call)                                                                          \
+    do {                                                                                  \
+        cudaError_t e_ = (call);                                                          \
+        if (e_ != cudaSuccess)                                                            \
+            return fail(e_ == cudaErrorMemoryAllocation ? CGB200_ERR_NOMEM : CGB200_ERR_CUDA, \
+                        "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+#define TRY(call)              \
+    do {                       \
+        int r_ = (call);       \
+        if (r_ < 0) return r_; \
+    } while (0)
+
+// ---------------------------------------------------------------------------
+// the handle
+// ---------------------------------------------------------------------------
+struct cgb200_ctx {
+    int device = 0, dtype = 0, n = 0;
+    long long nnz = 0;
+    size_t vsize = 0;
+    void *d_vals = nullptr;
+    int *d_rowptr = nullptr, *d_cols = nullptr;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int sm_count = 0;
+    int max_row = 0;
+    double mean_row = 0;
+    // options
+    int opt_lpr = 0, graph_chunk = 16, use_graph = 1, blocks_per_sm = 0;
+    // workspace (for ws_k right-hand sides)
+    int ws_k = 0;
+    void *x = nullptr, *r = nullptr, *d = nullptr, *q = nullptr, *stage = nullptr;
+    void *scal_mem = nullptr;   // device block the CgScalars arrays are carved from
+    void *partial = nullptr;
+    int grid_cap = 0;
+    double *d_hist = nullptr;
+    size_t hist_doubles = 0;
+    int *h_flag = nullptr;      // pinned
+    // graphs: (k, chunk) -> exec ; dropped whenever buffers or options change
+    cudaGraphExec_t graph = nullptr;
+    int graph_k = 0, graph_chunk_built = 0;
+    double graph_tol = -1;
+    int graph_hist_cap = -1;
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    double last_ms[4] = {0, 0, 0, 0};
+    long long launches = 0, graph_launches = 0;
+    std::map<const void *, int> occ;   // kernel -> resident blocks per SM
+    int spmv_grid_last = 0;
+};
+
+static size_t dtype_size(int dt) {
+    switch (dt) {
+    case CGB200_F32: return 4;
+    case CGB200_F64: return 8;
+    case CGB200_C64: return 8;
+    case CGB200_C128: return 16;
+    }
+    return 0;
+}
+
+static void drop_graph(cgb200_ctx *c) {
+    if (c->graph) cudaGraphExecDestroy(c->graph);
+    c->graph = nullptr;
+    c->graph_k = 0;
+}
+
+static void free_workspace(cgb200_ctx *c) {
+    drop_graph(c);
+    void **bufs[] = {&c->x, &c->r, &c->d, &c->q, &c->stage, &c->scal_mem, &c->partial};
+    for (void **b : bufs) {
+        if (*b) cudaFree(*b);
+        *b = nullptr;
+    }
+    c->ws_k = 0;
+}
+
+// persistent grid for `kernel` with `block` threads and `smem` bytes, capped by `work_blocks`
+template <typename K>
+static int persistent_grid(cgb200_ctx *c, K kernel, int block, size_t smem, long long work_blocks) {
+    const void *key = (const void *)kernel;
+    auto it = c->occ.find(key);
+    int per_sm;
+    if (it == c->occ.end()) {
+        per_sm = 1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, smem) != cudaSuccess || per_sm < 1) {
+            cudaGetLastError();
+            per_sm = 1;
+        }
+        c->occ[key] = per_sm;
+    } else {
+        per_sm = it->second;
+    }
+    if (c->blocks_per_sm > 0) per_sm = std::min(per_sm, c->blocks_per_sm);
+    long long g = (long long)c->sm_count * per_sm;
+    g = std::min<long long>(g, c->grid_cap);
+    g = std::min(g, std::max<long long>(work_blocks, 1));
+    return (int)g;
+}
+
+// ---------------------------------------------------------------------------
+// typed engine
+// ---------------------------------------------------------------------------
+template <typename T> struct Engine {
+    static constexpr int VW = VecW<T>::value;
+
+    // pack width used for k right-hand sides
+    static int pack_width(int k) { return (k == 1 || k % VW == 0) ? VW : 1; }
+    static int kv_of(int k) { return k == 1 ? 1 : k / pack_width(k); }
+    // largest batch of columns one launch handles (lanes per row <= 32)
+    static int max_batch() { return 32 * VW; }
+    // how many of `remaining` columns the next launch takes: at most 32 packs, and a
+    // batch wider than 32 must be a whole number of 128-bit packs
+    static int next_batch(int remaining) {
+        int kb = std::min(remaining, max_batch());
+        if (kb > 32 && kb % VW != 0) kb -= kb % VW;
+        return kb;
+    }
+    static bool batch_ok(int k) { return k <= max_batch() && (k <= 32 || k % VW == 0); }
+
+    static CgScalars<T> scalars(cgb200_ctx *c, int k, double tol, int hist_cap) {
+        CgScalars<T> s;
+        unsigned char *p = (unsigned char *)c->scal_mem;
+        const size_t kk = (size_t)c->ws_k;
+        auto take = [&p](size_t bytes) {
+            unsigned char *q = p;
+            p += (bytes + 15) & ~(size_t)15;
+            return q;
+        };
+        s.dq = (T *)take(kk * sizeof(T));
+        s.delta_new = (T *)take(kk * sizeof(T));
+        s.delta_old = (T *)take(kk * sizeof(T));
+        s.delta0 = (double *)take(kk * sizeof(double));
+        s.state = (int *)take(kk * sizeof(int));
+        s.iters = (int *)take(kk * sizeof(int));
+        s.n_active = (int *)take(sizeof(int));
+        s.it = (int *)take(sizeof(int));
+        s.ticket = (unsigned *)take(4 * sizeof(unsigned));
+        s.partial = (T *)c->partial;
+        s.hist = hist_cap > 0 ? c->d_hist : nullptr;
+        s.hist_cap = hist_cap;
+        s.tol = tol;
+        (void)k;
+        return s;
+    }
+    static size_t scalars_bytes(int k) {
+        return (size_t)k * (3 * sizeof(T) + sizeof(double) + 2 * sizeof(int)) + 16 * 10 + 64;
+    }
+
+    static int ensure_workspace(cgb200_ctx *c, int k) {
+        if (c->ws_k >= k && c->x) return 0;
+        free_workspace(c);
+        const size_t bytes = (size_t)c->n * k * sizeof(T) + 64;
+        CU(cudaMalloc(&c->x, bytes));
+        CU(cudaMalloc(&c->r, bytes));
+        CU(cudaMalloc(&c->d, bytes));
+        CU(cudaMalloc(&c->q, bytes));
+        if (k > 1) CU(cudaMalloc(&c->stage, bytes));
+        CU(cudaMalloc(&c->scal_mem, scalars_bytes(k)));
+        CU(cudaMemset(c->scal_mem, 0, scalars_bytes(k)));
+        CU(cudaMalloc(&c->partial, (size_t)c->grid_cap * k * sizeof(T)));
+        c->ws_k = k;
+        return 0;
+    }
+
+    // ---- SpMV / SpMM launch ------------------------------------------------
+    template <int LPR, bool DOT>
+    static int launch_spmv1(cgb200_ctx *c, const T *x, T *y, const CgScalars<T> &sc) {
+        auto kern = spmv1_kernel<T, LPR, DOT>;
+        const int block = 256;
+        const size_t smem = block * sizeof(T);
+        const long long work = ((long long)c->n + (block / LPR) - 1) / (block / LPR);
+        const int grid = persistent_grid(c, kern, block, smem, work);
+        c->spmv_grid_last = grid;
+        kern<<<grid, block, smem, c->stream>>>(c->n, (const T *)c->d_vals, c->d_rowptr, c->d_cols, x, y, sc);
+        c->launches++;
+        return 0;
+    }
+    template <bool DOT>
+    static int spmv1(cgb200_ctx *c, const T *x, T *y, const CgScalars<T> &sc) {
+        int lpr = c->opt_lpr;
+        if (lpr <= 0) {
+            // smallest power of two that covers the mean row, so that most rows take one pass
+            lpr = 2;
+            while (lpr < 32 && lpr < c->mean_row) lpr *= 2;
+        }
+        switch (lpr) {
+        case 1:
+        case 2: return launch_spmv1<2, DOT>(c, x, y, sc);
+        case 4: return launch_spmv1<4, DOT>(c, x, y, sc);
+        case 8: return launch_spmv1<8, DOT>(c, x, y, sc);
+        case 16: return launch_spmv1<16, DOT>(c, x, y, sc);
+        default: return launch_spmv1<32, DOT>(c, x, y, sc);
+        }
+    }
+    template <int V, int G, bool DOT>
+    static int launch_spmm(cgb200_ctx *c, int k, const T *x, T *y, const CgScalars<T> &sc) {
+        auto kern = spmm_kernel<T, V, G, DOT>;
+        const int block = 256;
+        const size_t smem = (size_t)block * V * sizeof(T);
+        const long long work = ((long long)c->n + (block / G) - 1) / (block / G);
+        const int grid = persistent_grid(c, kern, block, smem, work);
+        c->spmv_grid_last = grid;
+        kern<<<grid, block, smem, c->stream>>>(c->n, k, (const T *)c->d_vals, c->d_rowptr, c->d_cols, x, y, sc);
+        c->launches++;
+        return 0;
+    }
+    template <int V, bool DOT>
+    static int spmm_v(cgb200_ctx *c, int k, const T *x, T *y, const CgScalars<T> &sc) {
+        const int kv = k / V;
+        if (kv <= 1) return launch_spmm<V, 1, DOT>(c, k, x, y, sc);
+        if (kv <= 2) return launch_spmm<V, 2, DOT>(c, k, x, y, sc);
+        if (kv <= 4) return launch_spmm<V, 4, DOT>(c, k, x, y, sc);
+        if (kv <= 8) return launch_spmm<V, 8, DOT>(c, k, x, y, sc);
+        if (kv <= 16) return launch_spmm<V, 16, DOT>(c, k, x, y, sc);
+        return launch_spmm<V, 32, DOT>(c, k, x, y, sc);
+    }
+    template <bool DOT>
+    static int spmv(cgb200_ctx *c, int k, const T *x, T *y, const CgScalars<T> &sc) {
+        if (k == 1) return spmv1<DOT>(c, x, y, sc);
+        if (pack_width(k) == 1) return spmm_v<1, DOT>(c, k, x, y, sc);
+        return spmm_v<VW, DOT>(c, k, x, y, sc);
+    }
+
+    // ---- vector kernels ----------------------------------------------------
+    struct VecGeom {
+        int V, kv, block;
+        size_t npacks, nelem;
+    };
+    static VecGeom geom(cgb200_ctx *c, int k) {
+        VecGeom g;
+        g.V = pack_width(k);
+        g.kv = kv_of(k);
+        g.block = g.kv;
+        while (g.block * 2 <= 256) g.block *= 2;
+        g.nelem = (size_t)c->n * k;
+        g.npacks = g.nelem / g.V;
+        return g;
+    }
+    template <int V>
+    static int launch_init(cgb200_ctx *c, int k, const VecGeom &g, const T *b, const T *q, T *r, T *d, const CgScalars<T> &sc) {
+        auto kern = init_kernel<T, V>;
+        const size_t smem = (size_t)g.block * V * sizeof(T);
+        const int grid = persistent_grid(c, kern, g.block, smem, (long long)((g.npacks + g.block - 1) / g.block));
+        kern<<<grid, g.block, smem, c->stream>>>(g.npacks, g.nelem, k, g.kv, b, q, r, d, sc);
+        c->launches++;
+        return 0;
+    }
+    template <int V>
+    static int launch_update_xr(cgb200_ctx *c, int k, const VecGeom &g, const CgScalars<T> &sc) {
+        auto kern = update_xr_kernel<T, V>;
+        const size_t smem = (size_t)g.block * V * sizeof(T);
+        const int grid = persistent_grid(c, kern, g.block, smem, (long long)((g.npacks + g.block - 1) / g.block));
+        kern<<<grid, g.block, smem, c->stream>>>(g.npacks, g.nelem, k, g.kv, (const T *)c->d, (const T *)c->q, (T *)c->x, (T *)c->r, sc);
+        c->launches++;
+        return 0;
+    }
+    template <int V>
+    static int launch_update_d(cgb200_ctx *c, int k, const VecGeom &g, const CgScalars<T> &sc) {
+        auto kern = update_d_kernel<T, V>;
+        const int grid = persistent_grid(c, kern, g.block, 0, (long long)((g.npacks + g.block - 1) / g.block));
+        kern<<<grid, g.block, 0, c->stream>>>(g.npacks, g.nelem, k, g.kv, (const T *)c->r, (T *)c->d, sc);
+        c->launches++;
+        return 0;
+    }
+
+    static int iteration(cgb200_ctx *c, int k, const VecGeom &g, const CgScalars<T> &sc) {
+        TRY(spmv<true>(c, k, (const T *)c->d, (T *)c->q, sc));           // q = A d, d.q
+        if (g.V == 1) {
+            TRY(launch_update_xr<1>(c, k, g, sc));                      // x, r, delta
+            TRY(launch_update_d<1>(c, k, g, sc));                       // d
+        } else {
+            TRY(launch_update_xr<VW>(c, k, g, sc));
+            TRY(launch_update_d<VW>(c, k, g, sc));
+        }
+        return 0;
+    }
+
+    static int transpose(cgb200_ctx *c, const T *src, T *dst, int rows, long long cols) {
+        dim3 block(32, 8);
+        dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32));
+        transpose_kernel<T><<<grid, block, 0, c->stream>>>(src, dst, rows, cols);
+        c->launches++;
+        return 0;
+    }
+
+    // ---- y = A x -------------------------------------------------------------
+    static int spmv_api(cgb200_ctx *c, const void *x, void *y, int k, int layout) {
+        if (layout == CGB200_LAYOUT_ROWMAJOR && !batch_ok(k))
+            return fail(CGB200_ERR_UNSUPPORTED, "row-major spmv: k=%d does not fit one batch (max %d)", k, max_batch());
+        if (layout == CGB200_LAYOUT_CLCG && k > 1) {
+            // independent columns: process in batches through the workspace
+            for (int c0 = 0, kb = 0; c0 < k; c0 += kb) {
+                kb = next_batch(k - c0);
+                TRY(ensure_workspace(c, kb));
+                const size_t bytes = (size_t)c->n * kb * sizeof(T);
+                const T *xs = (const T *)x + (size_t)c0 * c->n;
+                T *ys = (T *)y + (size_t)c0 * c->n;
+                if (kb == 1) {
+                    CU(cudaMemcpyAsync(c->d, xs, bytes, cudaMemcpyDefault, c->stream));
+                    TRY(spmv<false>(c, 1, (const T *)c->d, (T *)c->q, scalars(c, 1, 0, 0)));
+                    CU(cudaMemcpyAsync(ys, c->q, bytes, cudaMemcpyDefault, c->stream));
+                } else {
+                    CU(cudaMemcpyAsync(c->stage, xs, bytes, cudaMemcpyDefault, c->stream));
+                    TRY(transpose(c, (const T *)c->stage, (T *)c->d, kb, c->n));
+                    TRY(spmv<false>(c, kb, (const T *)c->d, (T *)c->q, scalars(c, kb, 0, 0)));
+                    TRY(transpose(c, (const T *)c->q, (T *)c->stage, c->n, kb));
+                    CU(cudaMemcpyAsync(ys, c->stage, bytes, cudaMemcpyDefault, c->stream));
+                }
+            }
+            CU(cudaGetLastError());
+            return 0;
+        }
+        // k == 1, or row-major: device pointers are used in place, host pointers are staged
+        cudaPointerAttributes ax, ay;
+        CU(cudaPointerGetAttributes(&ax, x));
+        CU(cudaPointerGetAttributes(&ay, y));
+        const bool xdev = ax.type == cudaMemoryTypeDevice || ax.type == cudaMemoryTypeManaged;
+        const bool ydev = ay.type == cudaMemoryTypeDevice || ay.type == cudaMemoryTypeManaged;
+        const size_t bytes = (size_t)c->n * k * sizeof(T);
+        TRY(ensure_workspace(c, k));
+        const T *xd = (const T *)x;
+        T *yd = (T *)y;
+        if (!xdev) {
+            CU(cudaMemcpyAsync(c->d, x, bytes, cudaMemcpyDefault, c->stream));
+            xd = (const T *)c->d;
+        }
+        if (!ydev) yd = (T *)c->q;
+        TRY(spmv<false>(c, k, xd, yd, scalars(c, k, 0, 0)));
+        if (!ydev) CU(cudaMemcpyAsync(y, c->q, bytes, cudaMemcpyDefault, c->stream));
+        CU(cudaGetLastError());
+        if (!xdev || !ydev) CU(cudaStreamSynchronize(c->stream));
+        return 0;
+    }
+
+    // ---- one batch of k <= max_batch() right-hand sides ------------------------
+    static int solve_batch(cgb200_ctx *c, const T *b, T *x, int k, int maxit, double tol, int *iters,
+                           double *relres, double *hist, int hist_stride_k, int hist_col0, int layout,
+                           int *flags, double ms[4]) {
+        TRY(ensure_workspace(c, k));
+        const size_t bytes = (size_t)c->n * k * sizeof(T);
+        const int ncomp = Sc<T>::cplx ? 2 : 1;
+        int hist_cap = 0;
+        if (hist) {
+            hist_cap = maxit + 1;
+            const size_t need = (size_t)hist_cap * k * ncomp;
+            if (need > c->hist_doubles) {
+                if (c->d_hist) cudaFree(c->d_hist);
+                c->d_hist = nullptr;
+                c->hist_doubles = 0;
+                drop_graph(c);
+                CU(cudaMalloc(&c->d_hist, need * sizeof(double)));
+                c->hist_doubles = need;
+            }
+            CU(cudaMemsetAsync(c->d_hist, 0, need * sizeof(double), c->stream));
+        }
+        const CgScalars<T> sc = scalars(c, k, tol, hist_cap);
+        const VecGeom g = geom(c, k);
+
+        CU(cudaEventRecord(c->ev[0], c->stream));
+        // inputs: b -> d (temporarily), x0 -> x
+        if (k == 1 || layout == CGB200_LAYOUT_ROWMAJOR) {
+            CU(cudaMemcpyAsync(c->d, b, bytes, cudaMemcpyDefault, c->stream));
+            CU(cudaMemcpyAsync(c->x, x, bytes, cudaMemcpyDefault, c->stream));
+        } else {
+            CU(cudaMemcpyAsync(c->stage, b, bytes, cudaMemcpyDefault, c->stream));
+            TRY(transpose(c, (const T *)c->stage, (T *)c->d, k, c->n));
+            CU(cudaMemcpyAsync(c->stage, x, bytes, cudaMemcpyDefault, c->stream));
+            TRY(transpose(c, (const T *)c->stage, (T *)c->x, k, c->n));
+        }
+        CU(cudaEventRecord(c->ev[1], c->stream));
+
+        // q = A x0 ; r = b - q ; d = r ; delta = r.r          clcg.c:253-292
+        TRY(spmv<false>(c, k, (const T *)c->x, (T *)c->q, sc));
+        if (g.V == 1) TRY(launch_init<1>(c, k, g, (const T *)c->d, (const T *)c->q, (T *)c->r, (T *)c->d, sc));
+        else TRY(launch_init<VW>(c, k, g, (const T *)c->d, (const T *)c->q, (T *)c->r, (T *)c->d, sc));
+        CU(cudaEventRecord(c->ev[2], c->stream));
+
+        // the loop, clcg.c:296-419
+        int done = 0;
+        const int chunk = std::max(1, c->graph_chunk);
+        if (c->use_graph && maxit >= chunk) {
+            if (!c->graph || c->graph_k != k || c->graph_chunk_built != chunk || c->graph_tol != tol ||
+                c->graph_hist_cap != hist_cap) {
+                drop_graph(c);
+                cudaGraph_t gr = nullptr;
+                const long long before = c->launches;
+                CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+                int rc = 0;
+                for (int i = 0; i < chunk && rc == 0; i++) rc = iteration(c, k, g, sc);
+                cudaError_t ce = cudaStreamEndCapture(c->stream, &gr);
+                c->launches = before;
+                if (rc < 0) return rc;
+                if (ce != cudaSuccess) return fail(CGB200_ERR_CUDA, "graph capture: %s", cudaGetErrorString(ce));
+                ce = cudaGraphInstantiate(&c->graph, gr, 0);
+                cudaGraphDestroy(gr);
+                if (ce != cudaSuccess) return fail(CGB200_ERR_CUDA, "graph instantiate: %s", cudaGetErrorString(ce));
+                c->graph_k = k;
+                c->graph_chunk_built = chunk;
+                c->graph_tol = tol;
+                c->graph_hist_cap = hist_cap;
+            }
+            while (done + chunk <= maxit) {
+                CU(cudaGraphLaunch(c->graph, c->stream));
+                c->graph_launches++;
+                c->launches += 3LL * chunk;
+                done += chunk;
+                if (tol > 0) {
+                    CU(cudaMemcpyAsync(c->h_flag, sc.n_active, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+                    CU(cudaStreamSynchronize(c->stream));
+                    if (*c->h_flag == 0) { done = maxit; break; }
+                }
+            }
+        }
+        for (; done < maxit; done++) {
+            TRY(iteration(c, k, g, sc));
+            if (tol > 0 && (done % chunk) == chunk - 1) {
+                CU(cudaMemcpyAsync(c->h_flag, sc.n_active, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+                CU(cudaStreamSynchronize(c->stream));
+                if (*c->h_flag == 0) break;
+            }
+        }
+        CU(cudaEventRecord(c->ev[3], c->stream));
+
+        // result                                                   clcg.c:426
+        if (k == 1 || layout == CGB200_LAYOUT_ROWMAJOR) {
+            CU(cudaMemcpyAsync(x, c->x, bytes, cudaMemcpyDefault, c->stream));
+        } else {
+            TRY(transpose(c, (const T *)c->x, (T *)c->stage, c->n, k));
+            CU(cudaMemcpyAsync(x, c->stage, bytes, cudaMemcpyDefault, c->stream));
+        }
+        CU(cudaEventRecord(c->ev[4], c->stream));
+
+        // scalar results
+        std::vector<T> dn(k);
+        std::vector<double> d0(k);
+        std::vector<int> st(k), its(k);
+        CU(cudaMemcpyAsync(dn.data(), sc.delta_new, k * sizeof(T), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(d0.data(), sc.delta0, k * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(st.data(), sc.state, k * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(its.data(), sc.iters, k * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        std::vector<double> hh;
+        if (hist) {
+            hh.resize((size_t)hist_cap * k * ncomp);
+            CU(cudaMemcpyAsync(hh.data(), c->d_hist, hh.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        }
+        CU(cudaStreamSynchronize(c->stream));
+        CU(cudaGetLastError());
+        for (int i = 0; i < 4; i++) {
+            float f = 0;
+            CU(cudaEventElapsedTime(&f, c->ev[i], c->ev[i + 1]));
+            ms[i] += f;
+        }
+        for (int col = 0; col < k; col++) {
+            if (st[col] == ST_ACTIVE) {
+                its[col] = maxit;
+                if (tol > 0) *flags |= CGB200_FLAG_MAXIT;
+            }
+            if (st[col] == ST_BREAKDOWN) *flags |= CGB200_FLAG_BREAKDOWN;
+            if (iters) iters[col] = its[col];
+            if (relres) relres[col] = d0[col] > 0 ? sqrt(Sc<T>::abs(dn[col]) / d0[col]) : 0.0;
+        }
+        if (hist) {
+            // device history is [it][k][ncomp]; a frozen column repeats its last value
+            for (int it = 0; it < hist_cap; it++)
+                for (int col = 0; col < k; col++) {
+                    const int src_it = std::min(it, std::max(its[col], 0));
+                    for (int m = 0; m < ncomp; m++)
+                        hist[((size_t)it * hist_stride_k + hist_col0 + col) * ncomp + m] =
+                            hh[((size_t)src_it * k + col) * ncomp + m];
+                }
+        }
+        return 0;
+    }
+
+    static int solve_api(cgb200_ctx *c, const void *b, void *x, int k, int maxit, double tol, int *iters,
+                         double *relres, double *hist, int layout) {
+        int flags = 0;
+        double ms[4] = {0, 0, 0, 0};
+        if (layout == CGB200_LAYOUT_ROWMAJOR) {
+            if (!batch_ok(k))
+                return fail(CGB200_ERR_UNSUPPORTED, "row-major solve: k=%d does not fit one batch (max %d)", k, max_batch());
+            TRY(solve_batch(c, (const T *)b, (T *)x, k, maxit, tol, iters, relres, hist, k, 0, layout, &flags, ms));
+        } else {
+            // the k systems are independent (clcg.c runs k CGs that share A): batch the columns
+            for (int c0 = 0, kb = 0; c0 < k; c0 += kb) {
+                kb = next_batch(k - c0);
+                TRY(solve_batch(c, (const T *)b + (size_t)c0 * c->n, (T *)x + (size_t)c0 * c->n, kb, maxit, tol,
+                                iters ? iters + c0 : nullptr, relres ? relres + c0 : nullptr, hist, k, c0, layout,
+                                &flags, ms));
+            }
+        }
+        for (int i = 0; i < 4; i++) c->last_ms[i] = ms[i];
+        return flags;
+    }
+};
+
+#define DISPATCH(c, expr)                                                    \
+    [&]() -> int {                                                           \
+        switch ((c)->dtype) {                                                \
+        case CGB200_F32: { using E = Engine<float>; return expr; }           \
+        case CGB200_F64: { using E = Engine<double>; return expr; }          \
+        case CGB200_C64: { using E = Engine<float2>; return expr; }          \
+        case CGB200_C128: { using E = Engine<double2>; return expr; }        \
+        }                                                                    \
+        return fail(CGB200_ERR_ARG, "bad dtype %d", (c)->dtype);             \
+    }()
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) cudaSetDevice(dev);
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+// ---------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------
+extern "C" {
+
+const char *cgb200_last_error(void) { return g_err; }
+const char *cgb200_version(void) { return "cgb200 0.1 (sm_100a)"; }
+
+int cgb200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int cgb200_create(cgb200_handle *out, int n, long long nnz, const void *aValues, const int *aPointers,
+                  const int *aCols, int dtype, int device) {
+    if (!out) return fail(CGB200_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    if (n <= 0 || nnz < 0 || !aPointers || (nnz > 0 && (!aValues || !aCols)))
+        return fail(CGB200_ERR_ARG, "bad matrix arguments (n=%d nnz=%lld)", n, nnz);
+    if (nnz > 0x7fffffffLL) return fail(CGB200_ERR_UNSUPPORTED, "nnz > 2^31-1 (int32 row offsets, as the reference)");
+    const size_t vs = dtype_size(dtype);
+    if (!vs) return fail(CGB200_ERR_ARG, "bad dtype %d", dtype);
+    int ndev = 0;
+    CU(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(CGB200_ERR_ARG, "device %d of %d", device, ndev);
+    DeviceGuard guard(device);
+
+    cgb200_ctx *c = new cgb200_ctx();
+    c->device = device;
+    c->dtype = dtype;
+    c->n = n;
+    c->nnz = nnz;
+    c->vsize = vs;
+    auto bail = [&](int rc) {
+        cgb200_destroy(c);
+        return rc;
+    };
+#define CUB(call)                                                                                 \
+    do {                                                                                          \
+        cudaError_t e_ = (call);                                                                  \
+        if (e_ != cudaSuccess)                                                                    \
+            return bail(fail(e_ == cudaErrorMemoryAllocation ? CGB200_ERR_NOMEM : CGB200_ERR_CUDA, \
+                             "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_))); \
+    } while (0)
+    cudaDeviceProp prop;
+    CUB(cudaGetDeviceProperties(&prop, device));
+    c->sm_count = prop.multiProcessorCount;
+    c->grid_cap = c->sm_count * 16;
+    CUB(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    c->own_stream = true;
+    for (auto &e : c->ev) CUB(cudaEventCreate(&e));
+    CUB(cudaMallocHost(&c->h_flag, sizeof(int)));
+    // padded by 16 entries so 128-bit stream loads may run past the end
+    CUB(cudaMalloc(&c->d_vals, ((size_t)nnz + 16) * vs));
+    CUB(cudaMalloc(&c->d_cols, ((size_t)nnz + 16) * sizeof(int)));
+    CUB(cudaMalloc(&c->d_rowptr, ((size_t)n + 1 + 16) * sizeof(int)));
+    CUB(cudaMemsetAsync((char *)c->d_vals + (size_t)nnz * vs, 0, 16 * vs, c->stream));
+    CUB(cudaMemsetAsync(c->d_cols + nnz, 0, 16 * sizeof(int), c->stream));
+    CUB(cudaMemcpyAsync(c->d_vals, aValues, (size_t)nnz * vs, cudaMemcpyDefault, c->stream));
+    CUB(cudaMemcpyAsync(c->d_cols, aCols, (size_t)nnz * sizeof(int), cudaMemcpyDefault, c->stream));
+    CUB(cudaMemcpyAsync(c->d_rowptr, aPointers, ((size_t)n + 1) * sizeof(int), cudaMemcpyDefault, c->stream));
+    // row-length statistics choose the SpMV schedule
+    std::vector<int> rp((size_t)n + 1);
+    CUB(cudaMemcpyAsync(rp.data(), c->d_rowptr, ((size_t)n + 1) * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUB(cudaStreamSynchronize(c->stream));
+#undef CUB
+    if (rp[0] != 0 || rp[n] != (int)nnz)
+        return bail(fail(CGB200_ERR_ARG, "aPointers[0]=%d aPointers[n]=%d but nnz=%lld", rp[0], rp[n], nnz));
+    int mx = 0;
+    for (int i = 0; i < n; i++) {
+        const int len = rp[i + 1] - rp[i];
+        if (len < 0) return bail(fail(CGB200_ERR_ARG, "aPointers not monotone at row %d", i));
+        mx = std::max(mx, len);
+    }
+    c->max_row = mx;
+    c->mean_row = (double)nnz / n;
+    if (const char *e = getenv("CGB200_LANES_PER_ROW")) c->opt_lpr = atoi(e);
+    if (const char *e = getenv("CGB200_GRAPH_CHUNK")) c->graph_chunk = std::max(1, atoi(e));
+    if (const char *e = getenv("CGB200_USE_GRAPH")) c->use_graph = atoi(e);
+    if (const char *e = getenv("CGB200_BLOCKS_PER_SM")) c->blocks_per_sm = atoi(e);
+    *out = c;
+    return CGB200_OK;
+}
+
+int cgb200_destroy(cgb200_handle c) {
+    if (!c) return CGB200_OK;
+    DeviceGuard guard(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    free_workspace(c);
+    if (c->d_hist) cudaFree(c->d_hist);
+    if (c->d_vals) cudaFree(c->d_vals);
+    if (c->d_cols) cudaFree(c->d_cols);
+    if (c->d_rowptr) cudaFree(c->d_rowptr);
+    if (c->h_flag) cudaFreeHost(c->h_flag);
+    for (auto &e : c->ev)
+        if (e) cudaEventDestroy(e);
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    cudaGetLastError();
+    return CGB200_OK;
+}
+
+int cgb200_set_stream(cgb200_handle c, void *cuda_stream) {
+    if (!c) return fail(CGB200_ERR_ARG, "NULL handle");
+    DeviceGuard guard(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    drop_graph(c);
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    c->own_stream = false;
+    c->stream = (cudaStream_t)cuda_stream;
+    if (!cuda_stream) {
+        CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        c->own_stream = true;
+    }
+    return CGB200_OK;
+}
+
+static int *option_slot(cgb200_handle c, const char *key) {
+    if (!strcmp(key, "lanes_per_row")) return &c->opt_lpr;
+    if (!strcmp(key, "graph_chunk")) return &c->graph_chunk;
+    if (!strcmp(key, "use_graph")) return &c->use_graph;
+    if (!strcmp(key, "blocks_per_sm")) return &c->blocks_per_sm;
+    return nullptr;
+}
+
+int cgb200_set_option(cgb200_handle c, const char *key, long long value) {
+    if (!c || !key) return fail(CGB200_ERR_ARG, "NULL argument");
+    int *slot = option_slot(c, key);
+    if (!slot) return fail(CGB200_ERR_ARG, "unknown option '%s'", key);
+    if (!strcmp(key, "lanes_per_row") && value != 0 && value != 1 && value != 2 && value != 4 && value != 8 &&
+        value != 16 && value != 32)
+        return fail(CGB200_ERR_ARG, "lanes_per_row must be 0 or a power of two <= 32");
+    if (!strcmp(key, "graph_chunk") && value < 1) return fail(CGB200_ERR_ARG, "graph_chunk must be >= 1");
+    *slot = (int)value;
+    drop_graph(c);
+    return CGB200_OK;
+}
+
+int cgb200_get_option(cgb200_handle c, const char *key, long long *value) {
+    if (!c || !key || !value) return fail(CGB200_ERR_ARG, "NULL argument");
+    int *slot = option_slot(c, key);
+    if (!slot) return fail(CGB200_ERR_ARG, "unknown option '%s'", key);
+    *value = *slot;
+    return CGB200_OK;
+}
+
+int cgb200_spmv(cgb200_handle c, const void *x, void *y, int k, int layout) {
+    if (!c || !x || !y || k < 1) return fail(CGB200_ERR_ARG, "bad spmv arguments");
+    if (layout != CGB200_LAYOUT_CLCG && layout != CGB200_LAYOUT_ROWMAJOR) return fail(CGB200_ERR_ARG, "bad layout");
+    DeviceGuard guard(c->device);
+    return DISPATCH(c, E::spmv_api(c, x, y, k, layout));
+}
+
+int cgb200_solve(cgb200_handle c, const void *b, void *x, int k, int max_iterations, double tol, int *iterations,
+                 double *relres, double *delta_hist, int layout) {
+    if (!c || !b || !x || k < 1 || max_iterations < 0 || !(tol >= 0))
+        return fail(CGB200_ERR_ARG, "bad solve arguments");
+    if (layout != CGB200_LAYOUT_CLCG && layout != CGB200_LAYOUT_ROWMAJOR) return fail(CGB200_ERR_ARG, "bad layout");
+    DeviceGuard guard(c->device);
+    return DISPATCH(c, E::solve_api(c, b, x, k, max_iterations, tol, iterations, relres, delta_hist, layout));
+}
+
+int cgb200_last_timing(cgb200_handle c, double ms[4]) {
+    if (!c || !ms) return fail(CGB200_ERR_ARG, "NULL argument");
+    for (int i = 0; i < 4; i++) ms[i] = c->last_ms[i];
+    return CGB200_OK;
+}
+
+int cgb200_info(cgb200_handle c, long long out[10]) {
+    if (!c || !out) return fail(CGB200_ERR_ARG, "NULL argument");
+    int lpr = c->opt_lpr;
+    if (lpr <= 0) {
+        lpr = 2;
+        while (lpr < 32 && lpr < c->mean_row) lpr *= 2;
+    }
+    out[0] = c->n;
+    out[1] = c->nnz;
+    out[2] = c->dtype;
+    out[3] = lpr;
+    out[4] = c->spmv_grid_last;
+    out[5] = c->sm_count;
+    out[6] = c->launches;
+    out[7] = c->graph_launches;
+    out[8] = c->max_row;
+    out[9] = c->device;
+    return CGB200_OK;
+}
+
+// ---------------------------------------------------------------------------
+// cg() / cgd(): the reference's entry point.  clcg.h:3-5, clcg.c:111-466.
+// The matrix of the previous call is kept resident per device and reused when the
+// next call passes the same content (as_prec solves with the same P[0] on every
+// outer iteration, p_h-PY_C-CL.py:1924-1953).
+// ---------------------------------------------------------------------------
+struct CacheSlot {
+    std::mutex mu;
+    cgb200_handle h = nullptr;
+    uint64_t hash = 0;
+    int n = 0, dtype = -1;
+    long long nnz = 0;
+};
+static CacheSlot g_cache[64];
+
+static uint64_t hash_span(const unsigned char *p, size_t bytes, uint64_t seed) {
+    uint64_t h[4] = {seed ^ 0x9E3779B97F4A7C15ull, seed ^ 0xC2B2AE3D27D4EB4Full, seed ^ 0x165667B19E3779F9ull,
+                     seed ^ 0x27D4EB2F165667C5ull};
+    size_t i = 0;
+    for (; i + 32 <= bytes; i += 32) {
+        uint64_t w[4];
+        memcpy(w, p + i, 32);
+        for (int l = 0; l < 4; l++) {
+            h[l] = (h[l] ^ w[l]) * 0x100000001B3ull;
+            h[l] = (h[l] << 27) | (h[l] >> 37);
+        }
+    }
+    uint64_t tail = 0;
+    for (; i < bytes; i++) tail = tail * 131 + p[i];
+    uint64_t r = h[0];
+    for (int l = 1; l < 4; l++) r = (r ^ h[l]) * 0x9E3779B97F4A7C15ull + (r >> 29);
+    return (r ^ tail) * 0xD6E8FEB86659FD93ull;
+}
+
+static uint64_t hash_bytes(const void *ptr, size_t bytes, uint64_t seed) {
+    const unsigned char *p = (const unsigned char *)ptr;
+    const size_t min_chunk = 4u << 20;
+    int nt = (int)std::min<size_t>(8, bytes / min_chunk);
+    if (nt <= 1) return hash_span(p, bytes, seed);
+    std::vector<uint64_t> parts(nt);
+    std::vector<std::thread> th;
+    const size_t chunk = ((bytes / nt) + 31) & ~(size_t)31;
+    for (int i = 0; i < nt; i++) {
+        const size_t lo = std::min(bytes, (size_t)i * chunk), hi = (i == nt - 1) ? bytes : std::min(bytes, lo + chunk);
+        th.emplace_back([&, i, lo, hi] { parts[i] = hash_span(p + lo, hi - lo, seed + i); });
+    }
+    for (auto &t : th) t.join();
+    uint64_t r = seed;
+    for (int i = 0; i < nt; i++) r = (r ^ parts[i]) * 0x9E3779B97F4A7C15ull + (r >> 31);
+    return r;
+}
+
+static int legacy_device() {
+    if (const char *e = getenv("CGB200_DEVICE")) return atoi(e);
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess) {
+        cudaGetLastError();
+        d = 0;
+    }
+    return d;
+}
+
+static int legacy_cg(int dev, int dtype, int size, int nonZeros, const void *aValues, const void *b,
+                     const int *aPointers, const int *aCols, void *x, int nRHS, int nIterations) {
+    if (size <= 0 || nonZeros < 0 || !aValues || !b || !aPointers || !aCols || !x || nRHS < 1 || nIterations < 0)
+        return fail(CGB200_ERR_ARG, "bad cg() arguments");
+    if (dev < 0) dev = legacy_device();
+    if (dev < 0 || dev >= 64) return fail(CGB200_ERR_ARG, "device %d", dev);
+    const char *ce = getenv("CGB200_CACHE");
+    const bool use_cache = !(ce && atoi(ce) == 0);
+    if (!use_cache) {
+        cgb200_handle h = nullptr;
+        TRY(cgb200_create(&h, size, nonZeros, aValues, aPointers, aCols, dtype, dev));
+        int rc = cgb200_solve(h, b, x, nRHS, nIterations, 0.0, nullptr, nullptr, nullptr, CGB200_LAYOUT_CLCG);
+        cgb200_destroy(h);
+        return rc;
+    }
+    CacheSlot &s = g_cache[dev];
+    std::lock_guard<std::mutex> lock(s.mu);
+    const size_t vs = dtype_size(dtype);
+    uint64_t hsh = hash_bytes(aValues, (size_t)nonZeros * vs, 1);
+    hsh = hash_bytes(aCols, (size_t)nonZeros * sizeof(int), hsh);
+    hsh = hash_bytes(aPointers, ((size_t)size + 1) * sizeof(int), hsh);
+    if (!(s.h && s.n == size && s.nnz == nonZeros && s.dtype == dtype && s.hash == hsh)) {
+        if (s.h) cgb200_destroy(s.h);
+        s.h = nullptr;
+        TRY(cgb200_create(&s.h, size, nonZeros, aValues, aPointers, aCols, dtype, dev));
+        s.n = size;
+        s.nnz = nonZeros;
+        s.dtype = dtype;
+        s.hash = hsh;
+    }
+    return cgb200_solve(s.h, b, x, nRHS, nIterations, 0.0, nullptr, nullptr, nullptr, CGB200_LAYOUT_CLCG);
+}
+
+int cgb200_clear_cache(void) {
+    for (auto &s : g_cache) {
+        std::lock_guard<std::mutex> lock(s.mu);
+        if (s.h) cgb200_destroy(s.h);
+        s.h = nullptr;
+        s.dtype = -1;
+    }
+    return CGB200_OK;
+}
+
+int cgb200_cg(int device, int dtype, int size, int nonZeros, const void *aValues, const void *b,
+              const int *aPointers, const int *aCols, void *x, int nRHS, int nIterations) {
+    if (!dtype_size(dtype)) return fail(CGB200_ERR_ARG, "bad dtype %d", dtype);
+    return legacy_cg(device, dtype, size, nonZeros, aValues, b, aPointers, aCols, x, nRHS, nIterations);
+}
+
+float *cg(int size, int nonZeros, const float *aValues, const float *b, const int *aPointers, const int *aCols,
+          float *x, int nRHS, int nIterations, int isComplex) {
+    const int rc = legacy_cg(-1, isComplex ? CGB200_C64 : CGB200_F32, size, nonZeros, aValues, b, aPointers, aCols, x,
+                             nRHS, nIterations);
+    return rc < 0 ? nullptr : x;
+}
+
+double *cgd(int size, int nonZeros, const double *aValues, const double *b, const int *aPointers, const int *aCols,
+            double *x, int nRHS, int nIterations, int isComplex) {
+    const int rc = legacy_cg(-1, isComplex ? CGB200_C128 : CGB200_F64, size, nonZeros, aValues, b, aPointers, aCols, x,
+                             nRHS, nIterations);
+    return rc < 0 ? nullptr : x;
+}
+
+}  // extern "C"

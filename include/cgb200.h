@@ -1,0 +1,125 @@
+/*
+ * include/cgb200.h -- extended C ABI of liboclcg.so (the B200 CG engine).
+ *
+ * The reference's only entry point is cg() (include/clcg.h).  It re-creates its
+ * OpenCL context, re-compiles its kernels and re-uploads the matrix on every call
+ * (clcg.c:142-214), has no double precision (main.c:49), no convergence test and
+ * no error reporting (clcg.c:52-56).  The functions below expose the same path
+ * piecewise so that a caller can keep the matrix resident, solve in double
+ * precision, stop on a tolerance and read timings.  Each one names the part of the
+ * reference it stands for.
+ *
+ * Conventions
+ *   - plain C types only; every pointer argument may be a HOST or a DEVICE pointer
+ *     (the CUDA runtime tells them apart), so the same call serves a ctypes user with
+ *     numpy arrays and a caller whose data already lives in HBM;
+ *   - vectors use the reference's layout: nRHS blocks of n values, RHS r at offset
+ *     r*n (axpy.cl:12, p_h-PY_C-CL.py:1929-1930), unless a `layout` argument says
+ *     CGB200_LAYOUT_ROWMAJOR ([n][k], the engine's internal SpMM layout);
+ *   - return value: 0 ok, < 0 failure (cgb200_last_error() has the text),
+ *     > 0 numerical flags of cgb200_solve();
+ *   - no function calls exit() or prints.
+ */
+#ifndef CGB200_H
+#define CGB200_H
+
+#ifndef CGB200_API
+#define CGB200_API __attribute__((visibility("default")))
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* value types: what `isComplex` (clcg.c:154-158) selects, times two precisions */
+#define CGB200_F32 0   /* float                 -- cg(..., isComplex=0) */
+#define CGB200_F64 1   /* double                -- cgd(..., isComplex=0) */
+#define CGB200_C64 2   /* float  (re, im) pairs -- cg(..., isComplex=1), cfloat of cmplx.h:4 */
+#define CGB200_C128 3  /* double (re, im) pairs -- cgd(..., isComplex=1) */
+
+#define CGB200_LAYOUT_CLCG 0      /* [k][n]: RHS r at r*n, the cg() ABI */
+#define CGB200_LAYOUT_ROWMAJOR 1  /* [n][k]: the k values of a row are contiguous */
+
+#define CGB200_OK 0
+#define CGB200_ERR_ARG (-1)
+#define CGB200_ERR_CUDA (-2)
+#define CGB200_ERR_NOMEM (-3)
+#define CGB200_ERR_NCCL (-4)
+#define CGB200_ERR_UNSUPPORTED (-5)
+/* flags OR-ed into a positive return of cgb200_solve() */
+#define CGB200_FLAG_MAXIT 1      /* tol > 0 and some RHS did not reach it */
+#define CGB200_FLAG_BREAKDOWN 2  /* d.q or delta became 0 / non-finite for some RHS; that RHS was frozen */
+
+typedef struct cgb200_ctx *cgb200_handle;
+
+/* The prologue of cg() (clcg.c:137-214): device selection, buffers, matrix upload --
+ * done once.  Copies the CSR arrays (host or device pointers) into HBM on `device`,
+ * inspects the row-length distribution and picks the SpMV schedule. */
+CGB200_API int cgb200_create(cgb200_handle *out, int n, long long nnz, const void *aValues,
+                  const int *aPointers, const int *aCols, int dtype, int device);
+
+/* clcg.c:432-459 (release everything). */
+CGB200_API int cgb200_destroy(cgb200_handle h);
+
+/* All work of `h` is enqueued on one CUDA stream (clcg.c:184 creates one in-order
+ * queue).  By default the handle owns a stream; pass a cudaStream_t to share one. */
+CGB200_API int cgb200_set_stream(cgb200_handle h, void *cuda_stream);
+
+/* Tuning knobs (the reference's are compile-time macros, clcg.c:37-43).
+ *   "lanes_per_row"  0 auto | 1,2,4,8,16,32   SpMV lanes cooperating on one row
+ *   "graph_chunk"    CG iterations captured per CUDA graph launch (default 16)
+ *   "use_graph"      0/1
+ *   "blocks_per_sm"  0 auto | n               persistent-grid size multiplier
+ */
+CGB200_API int cgb200_set_option(cgb200_handle h, const char *key, long long value);
+CGB200_API int cgb200_get_option(cgb200_handle h, const char *key, long long *value);
+
+/* y = A x for k vectors: the `spmv` kernel alone (kernel/real/spmv.cl:5-50,
+ * kernel/complex/spmv.cl:7-53).  Asynchronous when x and y are device pointers. */
+CGB200_API int cgb200_spmv(cgb200_handle h, const void *x, void *y, int k, int layout);
+
+/* The body of cg(): clcg.c:253-292 (q=Ax0, r=b-q, d=r, delta=r.r) and the loop
+ * :296-419, for k right-hand sides.
+ *   tol == 0   exactly max_iterations iterations (the reference's behaviour);
+ *   tol  > 0   RHS c stops after the first iteration with sqrt(|delta|/|delta_0|) < tol,
+ *              the recursive residual the reference already forms (clcg.c:384-391).
+ * Optional outputs (host pointers or NULL):
+ *   iterations[k]   iterations performed per RHS
+ *   relres[k]       sqrt(|delta_final| / |delta_0|) per RHS
+ *   delta_hist      (max_iterations+1) * k * (1|2) doubles: delta_new after the
+ *                   initialisation and after every iteration (re, im for complex)
+ * Blocks until x is complete. */
+CGB200_API int cgb200_solve(cgb200_handle h, const void *b, void *x, int k, int max_iterations,
+                 double tol, int *iterations, double *relres, double *delta_hist, int layout);
+
+/* Milliseconds of the last cgb200_solve() on this handle, from CUDA events on its
+ * stream: [0] inputs to HBM (+ layout change), [1] initialisation, [2] iterations,
+ * [3] result back (+ layout change). */
+CGB200_API int cgb200_last_timing(cgb200_handle h, double ms[4]);
+
+/* Facts about a handle, for benches and tests:
+ * [0] n [1] nnz [2] dtype [3] lanes_per_row [4] persistent grid of the SpMV kernel
+ * [5] SM count [6] kernels launched so far [7] graph launches so far
+ * [8] max row length [9] device ordinal */
+CGB200_API int cgb200_info(cgb200_handle h, long long out[10]);
+
+/* cg()/cgd() with the value type and the device spelled out (device < 0: the calling
+ * thread's current CUDA device, or $CGB200_DEVICE).  This is what the pyopencl twin
+ * of the reference, cl.py:44-200 `CG` / :203-360 `conjugate_gradient_multi_gpu`
+ * (one context per device), maps onto.  Exactly nIterations iterations; x in/out. */
+CGB200_API int cgb200_cg(int device, int dtype, int size, int nonZeros, const void *aValues,
+                         const void *b, const int *aPointers, const int *aCols, void *x,
+                         int nRHS, int nIterations);
+
+/* Drop the matrix that cg()/cgd() keep resident between calls (keyed by content). */
+CGB200_API int cgb200_clear_cache(void);
+
+CGB200_API const char *cgb200_last_error(void);
+CGB200_API int cgb200_device_count(void);
+CGB200_API const char *cgb200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* CGB200_H */

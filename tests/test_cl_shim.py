@@ -1,0 +1,57 @@
+"""Host logic of the `cl` drop-in module (no GPU needed): both call forms of the reference
+drivers parse to the same C call; devices / contexts / kernels are the expected tokens."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture()
+def pcl(monkeypatch):
+    # the reference drivers do `import cl as pcl` with the module directory on sys.path
+    monkeypatch.syspath_prepend(os.path.join(ROOT, "conjugate-gradient-pyopencl_b200"))
+    sys.modules.pop("cl", None)
+    import cl
+    yield cl
+    sys.modules.pop("cl", None)
+
+
+def test_module_surface_matches_reference(pcl):
+    for name in ("initialize_cl_environment", "initialize_cl_environment_with_device", "get_gpu_devices",
+                 "load_and_build_kernels", "create_kernels", "CG", "conjugate_gradient_multi_gpu",
+                 "IS_COMPLEX", "WAVE_SIZE", "LOCAL_SIZE"):
+        assert hasattr(pcl, name), name
+    assert pcl.LOCAL_SIZE == 256 and pcl.WAVE_SIZE == 32
+    k = pcl.load_and_build_kernels(None, 4)
+    assert set(k) == {"axpy", "aypx", "spmv", "sub", "vdot"}        # cl.py:36-42
+    assert set(pcl.create_kernels(1)) == set(k)
+
+
+def test_both_call_forms_reach_the_same_c_call(pcl, monkeypatch):
+    calls = []
+    monkeypatch.setattr(pcl, "_solve", lambda dev, *a: calls.append((dev, a)) or a[6])
+    ctx, queue = pcl.initialize_cl_environment_with_device(pcl.Device(3))
+    kern = pcl.load_and_build_kernels(ctx, 2)
+    a = np.ones(3, np.csingle); b = np.ones(4, np.csingle); p = np.zeros(3, np.intc); c = np.zeros(3, np.intc)
+    x = np.zeros(4, np.csingle)
+    assert pcl.CG(ctx, queue, kern, 2, 3, a, b, p, c, x, 2, 7) is x                 # p_h-PY_C-CL.py:1933
+    assert pcl.CG(2, 3, a, b, p, c, x, 2, 7) is x                                   # p_helmholtz.py:1839
+    assert pcl.CG(2, 3, a, b, p, c, x, 2, 7, pcl.Device(1)) is x                    # commented form, :1934
+    assert pcl.conjugate_gradient_multi_gpu(ctx, queue, kern, 2, 3, a, b, p, c, x, 2, 7, pcl.Device(5)) is x
+    assert [d for d, _ in calls] == [3, 0, 1, 5]
+    assert all(args[0] == 2 and args[1] == 3 and args[7] == 2 and args[8] == 7 for _, args in calls)
+    with pytest.raises(TypeError):
+        pcl.CG(1, 2, 3)
+
+
+def test_input_validation(pcl):
+    a = np.ones(3, np.csingle); p = np.array([0, 1, 3], np.intc); c = np.zeros(3, np.intc)
+    with pytest.raises(TypeError):       # x of the wrong dtype cannot be filled in place
+        pcl.CG(2, 3, a, np.ones(2, np.csingle), p, c, np.zeros(2, np.complex128), 1, 1)
+    with pytest.raises(ValueError):      # b shorter than n_rhs * size
+        pcl.CG(2, 3, a, np.ones(2, np.csingle), p, c, np.zeros(4, np.csingle), 2, 1)
+    with pytest.raises(TypeError):
+        pcl.CG(2, 3, a.astype(np.int32), np.ones(2), p, c, np.zeros(2), 1, 1)

@@ -1,0 +1,389 @@
+"""Parity of the CUDA path (through the C ABI) with the CPU oracle -- runs on the B200 box.
+
+Tolerances (BASELINE.json north_star): 1e-10 relative in double precision, 1e-5 in single,
+iterations to convergence within +-1 of the reference recurrence in the same precision.
+Bit-exactness is not expected: the device sums in a different order and uses FMAs.
+"""
+import ctypes
+import json
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+pytestmark = pytest.mark.gpu
+
+DT = {"f32": np.float32, "f64": np.float64, "c64": np.complex64, "c128": np.complex128}
+TOL = {"f32": 1e-5, "c64": 1e-5, "f64": 1e-10, "c128": 1e-10}
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def rel(a, b):
+    """Relative 2-norm difference; every value is also appended to gpurun_out/parity_errors.log."""
+    e = float(np.linalg.norm(np.asarray(a) - np.asarray(b)) / max(np.linalg.norm(b), 1e-300))
+    try:
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", "parity_errors.log"), "a") as f:
+            f.write(f"{os.environ.get('PYTEST_CURRENT_TEST', '?')} {e:.3e}\n")
+    except OSError:
+        pass
+    return e
+
+
+def rand(rng, n, dt):
+    v = rng.standard_normal(n)
+    if np.dtype(dt).kind == "c":
+        v = v + 1j * rng.standard_normal(n)
+    return v.astype(dt)
+
+
+def system(kind, N, dt):
+    """A small CG-friendly system in dtype dt: (A, b)."""
+    import cg_b200.problems as P
+    cplx = np.dtype(dt).kind == "c"
+    if kind == "helm":
+        if cplx:
+            A = P.helmholtz_fe(N)
+            b = P.rhs_a(N, 12.0)
+        else:          # real twin: variable-coefficient SPD operator on the same grid
+            rng = np.random.default_rng(N)
+            A = (P.poisson2d(N) + sp.diags(0.05 + rng.random(N * N))).tocsr()
+            b = rng.standard_normal(N * N)
+    else:
+        A = P.poisson2d(N)
+        b = np.ones(A.shape[0])
+        if cplx:       # complex-symmetric twin of the Laplacian
+            A = (A + 0.3j * sp.eye(A.shape[0])).tocsr()
+            b = b * (1.0 + 0.5j)
+    A = A.astype(dt)
+    A.sort_indices()
+    return A, b.astype(dt)
+
+
+# ---------------------------------------------------------------------------------------
+# spmv / spmm kernels
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dname", ["f32", "f64", "c64", "c128"])
+@pytest.mark.parametrize("k", [1, 2, 3, 4, 8, 9, 32])
+def test_spmv_matches_oracle(gpu, cpu_ref, dname, k):
+    dt = DT[dname]
+    A, _ = system("helm", 40, dt)
+    n = A.shape[0]
+    rng = np.random.default_rng(k)
+    X = rand(rng, n * k, dt)
+    with gpu.Matrix.from_scipy(A) as M:
+        Y = M.spmv(X, k=k)
+    ref = cpu_ref.spmv(A.data, A.indptr, A.indices, X, k=k)
+    exact = np.concatenate([A.astype(np.complex128 if np.dtype(dt).kind == "c" else np.float64)
+                            @ X[r * n:(r + 1) * n] for r in range(k)])
+    assert rel(Y, ref) < (1e-6 if dname in ("f32", "c64") else 1e-14)
+    assert rel(Y, exact) < (1e-6 if dname in ("f32", "c64") else 1e-14)
+
+
+@pytest.mark.parametrize("dname", ["f64", "c64"])
+def test_spmv_wide_rhs_batches(gpu, dname):
+    # more columns than one launch takes (32 packs), and an odd remainder
+    dt = DT[dname]
+    A, _ = system("poisson", 24, dt)
+    n = A.shape[0]
+    k = 32 * (16 // np.dtype(dt).itemsize) + 5
+    X = rand(np.random.default_rng(1), n * k, dt)
+    with gpu.Matrix.from_scipy(A) as M:
+        Y = M.spmv(X, k=k)
+    ref = (A @ X.reshape(k, n).T).T.ravel()
+    assert rel(Y, ref) < (1e-5 if dname == "c64" else 1e-13)
+
+
+@pytest.mark.parametrize("lanes", [2, 4, 8, 16, 32])
+def test_spmv_every_lane_count_and_irregular_rows(gpu, lanes):
+    # empty rows, rows longer than lanes*32, unsorted columns inside a row, n % 8 != 0
+    rng = np.random.default_rng(lanes)
+    n = 1237
+    lens = rng.integers(0, 12, n)
+    lens[5] = 0
+    lens[17] = 700
+    lens[n - 1] = 1100
+    rows = np.repeat(np.arange(n), lens)
+    cols = np.concatenate([rng.choice(n, l, replace=False) for l in lens]).astype(np.intc)
+    vals = rng.standard_normal(rows.size)
+    indptr = np.zeros(n + 1, np.intc)
+    np.cumsum(lens, out=indptr[1:])
+    A = sp.csr_matrix((vals, cols, indptr), shape=(n, n))     # NOT sorted: "any order inside a row"
+    x = rng.standard_normal(n)
+    with gpu.Matrix(vals, indptr, cols) as M:
+        M.set_option("lanes_per_row", lanes)
+        y = M.spmv(x)
+        assert M.info()["lanes_per_row"] == lanes
+    assert rel(y, A @ x) < 1e-13
+
+
+def test_spmv_device_pointers_and_stream(gpu):
+    import torch
+    A, _ = system("helm", 64, np.complex128)
+    n = A.shape[0]
+    x = torch.randn(n, dtype=torch.complex128, device="cuda")
+    y = torch.empty_like(x)
+    s = torch.cuda.Stream()
+    with gpu.Matrix.from_scipy(A) as M:
+        M.set_stream(s.cuda_stream)
+        with torch.cuda.stream(s):
+            M.spmv(x, y)
+        s.synchronize()
+        M.set_stream(0)
+    assert rel(y.cpu().numpy(), A @ x.cpu().numpy()) < 1e-14
+
+
+# ---------------------------------------------------------------------------------------
+# CG, fixed iteration count (the reference's semantics)
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dname", ["f32", "f64", "c64", "c128"])
+@pytest.mark.parametrize("kind,N,iters", [("poisson", 48, 60), ("helm", 48, 80)])
+def test_cg_fixed_iterations_matches_oracle(gpu, cpu_ref, dname, kind, N, iters):
+    dt = DT[dname]
+    A, b = system(kind, N, dt)
+    with gpu.Matrix.from_scipy(A) as M:
+        x, info = M.solve(b, max_iterations=iters, history=True)
+    ref, _, hist = cpu_ref.cg(A.data, A.indptr, A.indices, b, iters=iters, want_hist=True)
+    assert info.flags == 0 and info.iterations[0] == iters
+    assert rel(x, ref) < TOL[dname], (rel(x, ref), dname)
+    # the recursive residual history follows the oracle's
+    hg, ho = info.delta_hist[:, 0], hist[:, 0]
+    assert np.all(np.abs(hg - ho) <= (1e-3 if dname in ("f32", "c64") else 1e-8) * np.abs(ho))
+
+
+@pytest.mark.parametrize("dname", ["f32", "f64", "c64", "c128"])
+@pytest.mark.parametrize("k", [2, 3, 5, 8, 32])
+def test_cg_multi_rhs_matches_oracle(gpu, cpu_ref, dname, k):
+    dt = DT[dname]
+    A, b = system("helm", 32, dt)
+    n = A.shape[0]
+    rng = np.random.default_rng(10 + k)
+    B = np.concatenate([b * (r + 1) if r % 2 == 0 else rand(rng, n, dt) for r in range(k)])
+    X0 = rand(rng, n * k, dt) * dt(0.1)          # non-zero initial guess: x is in/out (clcg.c:210)
+    with gpu.Matrix.from_scipy(A) as M:
+        x, info = M.solve(B, x=X0.copy(), k=k, max_iterations=40)
+    ref, _, _ = cpu_ref.cg(A.data, A.indptr, A.indices, B, x0=X0, k=k, iters=40)
+    assert rel(x, ref) < TOL[dname]
+    # column independence: column 1 alone gives the same answer
+    with gpu.Matrix.from_scipy(A) as M:
+        x1, _ = M.solve(B[n:2 * n].copy(), x=X0[n:2 * n].copy(), max_iterations=40)
+    assert rel(x[n:2 * n], x1) < TOL[dname]
+
+
+def test_cg_more_rhs_than_one_batch(gpu, cpu_ref):
+    A, b = system("poisson", 20, np.complex128)
+    n = A.shape[0]
+    k = 37                                        # c128: 32 per launch -> batches of 32 + 5
+    B = rand(np.random.default_rng(5), n * k, np.complex128)
+    with gpu.Matrix.from_scipy(A) as M:
+        x, info = M.solve(B, k=k, max_iterations=25, tol=0.0)
+    ref, _, _ = cpu_ref.cg(A.data, A.indptr, A.indices, B, k=k, iters=25)
+    assert rel(x, ref) < 1e-10 and np.all(info.iterations == 25)
+
+
+def test_cg_zero_iterations_returns_initial_guess(gpu):
+    A, b = system("poisson", 16, np.float64)
+    x0 = np.arange(A.shape[0], dtype=np.float64)
+    with gpu.Matrix.from_scipy(A) as M:
+        x, info = M.solve(b, x=x0.copy(), max_iterations=0)
+    assert np.array_equal(x, x0)
+
+
+@pytest.mark.parametrize("n", [1, 5, 37, 255, 257, 300])
+def test_cg_small_and_ragged_sizes(gpu, cpu_ref, n):
+    # sizes the reference warns about (n < 256, clcg.c:123) or mishandles (n % 8 != 0, spmv.cl:18-19)
+    rng = np.random.default_rng(n)
+    Mx = sp.random(n, n, density=min(1.0, 40.0 / n), random_state=1, format="csr")
+    A = (Mx + Mx.T + sp.eye(n) * (n + 1.0)).tocsr()
+    A.sort_indices()
+    b = rng.standard_normal(n)
+    its = min(n, 30)
+    with gpu.Matrix.from_scipy(A) as M:
+        x, info = M.solve(b, max_iterations=its)
+    ref, _, _ = cpu_ref.cg(A.data, A.indptr, A.indices, b, iters=its, tol=0.0)
+    good = np.isfinite(ref).all()
+    if good:
+        assert rel(x, ref) < 1e-10
+    assert np.isfinite(x).all()                   # converged columns freeze instead of producing NaN
+
+
+def test_golden_fixtures_from_reference_numpy_cg(gpu, golden_dir):
+    """x after 10/50/200 iterations of helmFE_var.CG (the reference itself, complex128)."""
+    g = np.load(os.path.join(golden_dir, "helm32_c128.npz"))
+    with gpu.Matrix(g["data"], g["indptr"], g["indices"]) as M:
+        for it in (10, 50, 200):
+            x, _ = M.solve(g["b"], max_iterations=it)
+            assert rel(x, g[f"x{it}"]) < 1e-10, it
+    g = np.load(os.path.join(golden_dir, "poisson32_f64.npz"))
+    with gpu.Matrix(g["data"], g["indptr"], g["indices"]) as M:
+        for it in (10, 40, 120):
+            x, _ = M.solve(g["b"], max_iterations=it)
+            assert rel(x, g[f"x{it}"]) < 1e-10, it
+
+
+# ---------------------------------------------------------------------------------------
+# iterations to convergence (+-1) -- SURVEY.md 8(c) known answers
+# ---------------------------------------------------------------------------------------
+def test_iterations_to_convergence_double(gpu, cpu_ref, golden_dir):
+    import cg_b200.problems as P
+    ka = json.load(open(os.path.join(golden_dir, "known_answers.json")))
+    A = P.poisson2d(256)
+    b = np.ones(A.shape[0])
+    with gpu.Matrix.from_scipy(A) as M:
+        for tol, want in ka["poisson256_f64"]["iters"].items():
+            x, info = M.solve(b, max_iterations=2000, tol=float(tol))
+            assert abs(int(info.iterations[0]) - want) <= 1, (tol, info.iterations, want)
+            assert info.flags == 0 and info.relres[0] < float(tol)
+            ref, _, _ = cpu_ref.cg(A.data, A.indptr, A.indices, b, iters=2000, tol=float(tol))
+            assert rel(x, ref) < 1e-10
+    A = P.helmholtz_fe(128)
+    b = P.rhs_a(128, 12.0)
+    with gpu.Matrix.from_scipy(A) as M:
+        for tol, want in ka["helm128_c128"]["iters"].items():
+            x, info = M.solve(b, max_iterations=3000, tol=float(tol))
+            assert abs(int(info.iterations[0]) - want) <= 1, (tol, info.iterations, want)
+            ref, its, _ = cpu_ref.cg(A.data, A.indptr, A.indices, b, iters=3000, tol=float(tol))
+            if int(info.iterations[0]) == int(its[0]):
+                assert rel(x, ref) < 1e-10
+        assert np.linalg.norm(A @ x - b) / np.linalg.norm(b) < 1e-9
+
+
+def test_iterations_to_convergence_single(gpu, cpu_ref):
+    # single precision is only well-posed above the stagnation floor: tol >= 1e-4
+    import cg_b200.problems as P
+    A = P.helmholtz_fe(128)
+    a32, b32 = A.data.astype(np.complex64), P.rhs_a(128, 12.0).astype(np.complex64)
+    with gpu.Matrix(a32, A.indptr, A.indices) as M:
+        for tol in (1e-3, 1e-4):
+            x, info = M.solve(b32, max_iterations=3000, tol=tol)
+            ref, its, _ = cpu_ref.cg(a32, A.indptr, A.indices, b32, iters=3000, tol=tol)
+            assert abs(int(info.iterations[0]) - int(its[0])) <= 1, (tol, info.iterations, its)
+            assert rel(x, ref) < 5e-5
+    A = P.poisson2d(256).astype(np.float32)
+    b = np.ones(A.shape[0], np.float32)
+    with gpu.Matrix.from_scipy(A) as M:
+        x, info = M.solve(b, max_iterations=2000, tol=1e-4)
+        ref, its, _ = cpu_ref.cg(A.data, A.indptr, A.indices, b, iters=2000, tol=1e-4)
+        assert abs(int(info.iterations[0]) - int(its[0])) <= 1
+        assert rel(x, ref) < 5e-5
+
+
+def test_tolerance_mode_freezes_columns_individually(gpu, cpu_ref):
+    A, b = system("helm", 48, np.complex128)
+    n = A.shape[0]
+    rng = np.random.default_rng(2)
+    B = np.concatenate([b, rand(rng, n, np.complex128), b * 0])       # third RHS is zero: converged at once
+    with gpu.Matrix.from_scipy(A) as M:
+        x, info = M.solve(B, k=3, max_iterations=2000, tol=1e-9, history=True)
+    ref, its, _ = cpu_ref.cg(A.data, A.indptr, A.indices, B, k=3, iters=2000, tol=1e-9)
+    assert np.all(np.abs(info.iterations - its) <= 1), (info.iterations, its)
+    assert info.iterations[2] == 0 and np.all(x[2 * n:] == 0)
+    assert info.iterations[0] != info.iterations[1]
+    assert rel(x[:2 * n], ref[:2 * n]) < 1e-8
+    assert info.flags == 0
+
+
+def test_breakdown_guard_instead_of_nan(gpu):
+    # run far past convergence in single precision: the reference produces NaN
+    A, b = system("helm", 32, np.complex64)
+    with gpu.Matrix.from_scipy(A) as M:
+        x, info = M.solve(b, max_iterations=4000)
+    assert np.isfinite(x).all()
+    A64, b64 = system("helm", 32, np.complex128)
+    exact = sp.linalg.spsolve(A64.tocsc(), b64)
+    assert rel(x, exact) < 1e-3
+
+
+# ---------------------------------------------------------------------------------------
+# the reference's own entry points: cg(), cgd(), the `cl` module
+# ---------------------------------------------------------------------------------------
+def test_legacy_cg_symbol_with_reference_argtypes(gpu, cpu_ref):
+    from numpy.ctypeslib import ndpointer
+    L = ctypes.CDLL(os.path.join(ROOT, "build", "liboclcg.so"))
+    L.cg.argtypes = [ctypes.c_int, ctypes.c_int, ndpointer(dtype=np.csingle, ndim=1, flags="C"),
+                     ndpointer(dtype=np.csingle, ndim=1, flags="C"), ndpointer(dtype=np.intc, ndim=1, flags="C"),
+                     ndpointer(dtype=np.intc, ndim=1, flags="C"), ndpointer(dtype=np.csingle, ndim=1, flags="C"),
+                     ctypes.c_int, ctypes.c_int, ctypes.c_int]          # p_h-PY_C-CL.py:1948-1950
+    A, b = system("helm", 40, np.complex64)
+    n, k = A.shape[0], 4
+    size = n
+    b_values = np.zeros(size * k, dtype=np.csingle)
+    for p in range(k):
+        b_values[p * size:(p + 1) * size] = b * (p + 1)                # as_prec's block layout, :1925-1930
+    x = np.ascontiguousarray(np.zeros(size * k), dtype=np.csingle)
+    a_values = np.array(A.data, dtype=np.csingle)
+    row_ptr = np.array(A.indptr, dtype=np.intc)
+    col_idx = np.array(A.indices, dtype=np.intc)
+    L.cg(size, A.nnz, a_values, b_values, row_ptr, col_idx, x, k, 64, 1)
+    ref, _, _ = cpu_ref.cg(a_values, row_ptr, col_idx, b_values, k=k, iters=64)
+    assert rel(x, ref) < 1e-5
+    # second call, same matrix: served from the resident copy; different values: re-uploaded
+    x2 = np.zeros_like(x)
+    L.cg(size, A.nnz, a_values, b_values, row_ptr, col_idx, x2, k, 64, 1)
+    assert np.array_equal(x, x2)
+    a2 = (a_values * np.csingle(1.5)).astype(np.csingle)
+    x3 = np.zeros_like(x)
+    L.cg(size, A.nnz, a2, b_values, row_ptr, col_idx, x3, k, 64, 1)
+    ref3, _, _ = cpu_ref.cg(a2, row_ptr, col_idx, b_values, k=k, iters=64)
+    assert rel(x3, ref3) < 1e-5 and rel(x3, x) > 1e-2
+
+
+@pytest.mark.parametrize("dname", ["f32", "f64", "c64", "c128"])
+def test_cg_and_cgd_wrappers(gpu, cpu_ref, dname):
+    dt = DT[dname]
+    A, b = system("poisson", 40, dt)
+    x = np.zeros(A.shape[0], dt)
+    out = gpu.cg(A.shape[0], A.nnz, A.data, b, A.indptr, A.indices, x, 1, 50)
+    assert out is x
+    ref, _, _ = cpu_ref.cg(A.data, A.indptr, A.indices, b, iters=50)
+    assert rel(x, ref) < TOL[dname]
+
+
+def test_cl_module_drop_in(gpu, cpu_ref, monkeypatch):
+    import sys
+    monkeypatch.syspath_prepend(os.path.join(ROOT, "conjugate-gradient-pyopencl_b200"))
+    sys.modules.pop("cl", None)
+    import cl as pcl
+    devices = pcl.get_gpu_devices()
+    assert len(devices) >= 1
+    ctx, queue = pcl.initialize_cl_environment()
+    A, b = system("helm", 36, np.complex64)
+    n, n_my = A.shape[0], 3
+    kernels = pcl.load_and_build_kernels(ctx, n_my)
+    b_values = np.concatenate([b * (p + 1) for p in range(n_my)]).astype(np.csingle)
+    x = np.ascontiguousarray(np.zeros(n * n_my), dtype=np.csingle)
+    out = pcl.CG(ctx, queue, kernels, n, A.nnz, A.data, b_values, A.indptr, A.indices, x, n_my, 48)
+    ref, _, _ = cpu_ref.cg(A.data, A.indptr, A.indices, b_values, k=n_my, iters=48)
+    assert out is x and rel(x, ref) < 1e-5
+    x1 = np.zeros(n, dtype=np.csingle)
+    pcl.conjugate_gradient_multi_gpu(ctx, queue, kernels, n, A.nnz, A.data, b_values[:n].copy(), A.indptr,
+                                     A.indices, x1, 1, 48, devices[0])
+    assert rel(x1, ref[:n]) < 1e-5
+    x9 = np.zeros(n, dtype=np.csingle)
+    pcl.CG(n, A.nnz, A.data, b_values[:n].copy(), A.indptr, A.indices, x9, 1, 48)     # p_helmholtz.py form
+    assert np.array_equal(x9, x1)
+    sys.modules.pop("cl", None)
+
+
+def test_solve_with_device_tensors(gpu, cpu_ref):
+    import torch
+    A, b = system("helm", 48, np.complex128)
+    bt = torch.from_numpy(b).cuda()
+    xt = torch.zeros_like(bt)
+    with gpu.Matrix.from_scipy(A) as M:
+        _, info = M.solve(bt, x=xt, max_iterations=70)
+    ref, _, _ = cpu_ref.cg(A.data, A.indptr, A.indices, b, iters=70)
+    assert rel(xt.cpu().numpy(), ref) < 1e-10
+
+
+def test_graph_and_plain_launch_paths_agree(gpu):
+    A, b = system("helm", 40, np.complex128)
+    with gpu.Matrix.from_scipy(A) as M:
+        M.set_option("use_graph", 0)
+        x0, _ = M.solve(b, max_iterations=50)
+        M.set_option("use_graph", 1)
+        M.set_option("graph_chunk", 7)
+        x1, i1 = M.solve(b, max_iterations=50)
+        assert M.info()["graph_launches"] == 7
+    assert np.array_equal(x0, x1)                 # deterministic: same kernels, same order

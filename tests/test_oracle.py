@@ -1,0 +1,122 @@
+"""Pins the two CPU oracles (test infrastructure) before anything is compared with them.
+
+  - oracle/np_cg.py  against fixtures produced by the reference's own numpy CG
+    (helmFE_var.py:507-544) -- bit-identical;
+  - oracle/cpu_ref.c (restatement of clcg.c:253-419 + kernels) against the same fixtures
+    and against the known answers of SURVEY.md 8(c) (tests/golden/known_answers.json).
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import np_cg
+
+
+def _load(golden_dir, name):
+    g = np.load(os.path.join(golden_dir, name))
+    n = g["indptr"].size - 1
+    A = sp.csr_matrix((g["data"], g["indices"], g["indptr"]), shape=(n, n))
+    return g, A
+
+
+@pytest.mark.parametrize("name,its,cplx", [("helm32_c128.npz", (10, 50, 200), True),
+                                           ("poisson32_f64.npz", (10, 40, 120), False)])
+def test_np_cg_bit_identical_to_reference_fixture(golden_dir, name, its, cplx):
+    g, A = _load(golden_dir, name)
+    for it in its:
+        x0 = np.zeros(A.shape[0], dtype=complex if cplx else float)
+        x = np_cg.cg(A, g["b"], x=x0, maxit=it)
+        assert np.array_equal(x, g[f"x{it}"])
+
+
+@pytest.mark.reference
+def test_np_cg_bit_identical_to_imported_reference():
+    import sys
+    sys.path.insert(0, "/root/reference")
+    import helmFE_var as H
+    N = 24
+    A = H.helmFE_var(N, 12.0, np.ones((N - 1, N - 1)), 0.15, N, N)
+    b = H.rhs(N, 12.0).flatten()
+    for it in (1, 7, 60):
+        assert np.array_equal(H.CG(A, b, x=np.zeros(N * N, dtype=complex), maxit=it),
+                              np_cg.cg(A, b, x=np.zeros(N * N, dtype=complex), maxit=it))
+
+
+@pytest.mark.parametrize("name,its", [("helm32_c128.npz", (10, 50, 200)), ("poisson32_f64.npz", (10, 40, 120))])
+def test_c_oracle_matches_reference_fixture_double(cpu_ref, golden_dir, name, its):
+    g, A = _load(golden_dir, name)
+    for it in its:
+        x, n_it, _ = cpu_ref.cg(g["data"], g["indptr"], g["indices"], g["b"], iters=it)
+        ref = g[f"x{it}"]
+        # different summation order (GPU-style trees) => agreement to rounding, not bitwise
+        assert np.linalg.norm(x - ref) <= 1e-12 * np.linalg.norm(ref)
+        assert n_it[0] == it
+
+
+def test_c_oracle_single_precision_tracks_double(cpu_ref, golden_dir):
+    g, A = _load(golden_dir, "helm32_c128.npz")
+    x, _, _ = cpu_ref.cg(g["data"].astype(np.complex64), g["indptr"], g["indices"],
+                         g["b"].astype(np.complex64), iters=50)
+    ref = g["x50"]
+    assert np.linalg.norm(x - ref) <= 2e-4 * np.linalg.norm(ref)
+
+
+def test_c_oracle_known_answers(cpu_ref, golden_dir):
+    import cg_b200.problems as P
+    ka = json.load(open(os.path.join(golden_dir, "known_answers.json")))
+    A = P.poisson2d(256)
+    assert (A.shape[0], A.nnz) == (ka["poisson256_f64"]["n"], ka["poisson256_f64"]["nnz"])
+    b = np.ones(A.shape[0])
+    for tol, want in ka["poisson256_f64"]["iters"].items():
+        _, its, _ = cpu_ref.cg(A.data, A.indptr, A.indices, b, iters=2000, tol=float(tol))
+        assert its[0] == want
+    A = P.helmholtz_fe(128)
+    assert (A.shape[0], A.nnz) == (ka["helm128_c128"]["n"], ka["helm128_c128"]["nnz"])
+    b = P.rhs_a(128, 12.0)
+    for tol, want in ka["helm128_c128"]["iters"].items():
+        x, its, _ = cpu_ref.cg(A.data, A.indptr, A.indices, b, iters=3000, tol=float(tol))
+        assert its[0] == want
+    assert np.linalg.norm(A @ x - b) / np.linalg.norm(b) < 1e-9
+    # single precision, SURVEY.md 8(c): 271 / 328 iterations at 1e-4 / 1e-5
+    a32, b32 = A.data.astype(np.complex64), b.astype(np.complex64)
+    for tol, want in ((1e-4, 271), (1e-5, 328)):
+        _, its, _ = cpu_ref.cg(a32, A.indptr, A.indices, b32, iters=3000, tol=tol)
+        assert abs(int(its[0]) - want) <= 1
+
+
+def test_c_oracle_delta_history_and_np_cg_agree(cpu_ref, golden_dir):
+    g, A = _load(golden_dir, "helm32_c128.npz")
+    hist = []
+    np_cg.cg(A, g["b"], x=np.zeros(A.shape[0], dtype=complex), maxit=60, history=hist)
+    _, _, h = cpu_ref.cg(g["data"], g["indptr"], g["indices"], g["b"], iters=60, want_hist=True)
+    hist = np.array(hist)
+    assert h.shape == (61, 1)
+    assert np.all(np.abs(h[:, 0] - hist) <= 1e-10 * np.abs(hist))
+
+
+def test_c_oracle_multi_rhs_columns_are_independent(cpu_ref, golden_dir):
+    g, A = _load(golden_dir, "poisson32_f64.npz")
+    n = A.shape[0]
+    rng = np.random.default_rng(3)
+    B = rng.standard_normal((3, n))
+    X, _, _ = cpu_ref.cg(g["data"], g["indptr"], g["indices"], B.ravel(), k=3, iters=30)
+    for r in range(3):
+        x1, _, _ = cpu_ref.cg(g["data"], g["indptr"], g["indices"], B[r], iters=30)
+        assert np.array_equal(X[r * n:(r + 1) * n], x1)
+
+
+def test_c_oracle_edge_shapes(cpu_ref):
+    # n < 256 and n % 8 != 0 (the reference's "NOT SUPPORTED" / out-of-bounds cases), rows longer than a wave
+    rng = np.random.default_rng(0)
+    for n in (1, 5, 37, 255, 257, 300):
+        M = sp.random(n, n, density=min(1.0, 40.0 / n), random_state=1, format="csr")
+        A = (M + M.T + sp.eye(n) * (n + 1.0)).tocsr()
+        A.sort_indices()
+        b = rng.standard_normal(n)
+        x, _, _ = cpu_ref.cg(A.data, A.indptr, A.indices, b, iters=min(n, 40) + 5, tol=1e-13)
+        assert np.linalg.norm(A @ x - b) <= 1e-10 * np.linalg.norm(b)
+        y = cpu_ref.spmv(A.data, A.indptr, A.indices, b)
+        assert np.allclose(y, A @ b, rtol=1e-13, atol=1e-13)
