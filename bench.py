@@ -1,0 +1,366 @@
+#!/usr/bin/env python3
+"""bench.py -- CG iterations/s of the B200 engine on the BASELINE.json configs.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2] [--dtype c128]
+    python bench.py --impl reference ...        # the CPU oracle port on the host cores
+
+A *step* is one call of the hot path as the reference's caller makes it: one
+`cg(size, nnz, A, b, ptr, cols, x, k, nIterations=256, isComplex)` (CGMaxIT = 256 is the
+driver default, p_h-PY_C-CL.py:3553), i.e. 256 CG iterations on one batch of k right-hand sides.
+
+  value   iterations/s with the matrix, b and x already resident in HBM (device pointers through
+          cgb200_solve), CUDA events on the launching stream, max over ranks.
+  e2e     the same metric through the exported `cg`/`cgd` symbol with pinned HOST buffers:
+          every step uploads the CSR matrix, b and x0 and reads x back (resident-matrix cache off).
+  roofline  the dominant kernel (SpMV fused with d.q) timed alone with CUDA events, algorithmic
+          bytes B_spmv = nnz(v+4) + 4(n+1) + 2knv against MEASURED_PEAKS.json.
+  cpu_baseline  the oracle port (oracle/cpu_ref.c, OpenMP, all host cores) on a bounded sample.
+
+N > 1 (torchrun, one rank per GPU): the reference's own multi-GPU mode -- right-hand sides split
+across GPUs, matrix replicated, no collective (p_h-PY_C-CL-multi-GPU.py:2123-2181).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ITERS_PER_STEP = 256
+WORKLOADS = {
+    "c1": dict(desc="C1 2-D 5-point Poisson 256x256", dtype="f64", k=1),
+    "c2": dict(desc="C2 complex-symmetric Helmholtz FE 1024x1024 (helmFE_var, omega=12, rho=0.15)", dtype="c128", k=1),
+    "c3": dict(desc="C3 3-D 7-point Laplacian 128^3, 32 right-hand sides", dtype="f64", k=32),
+    "c4": dict(desc="C4 3-D 7-point Laplacian 300^3", dtype="f64", k=1),
+    "c5": dict(desc="C5 power-law SPD, 5M rows, 50M nnz", dtype="f64", k=1),
+}
+
+
+def make_problem(name, dtype, k):
+    """(A scipy CSR, B flat [k][n]) of BASELINE.json config `name` (SURVEY.md 8(d) inputs)."""
+    import cg_b200.problems as P
+    np_t = P.DTYPES[dtype][0]
+    cplx = P.DTYPES[dtype][3]
+    if name == "c1":
+        A = P.poisson2d(256)
+        b = np.ones(A.shape[0])
+    elif name == "c2":
+        A = P.helmholtz_fe(1024)
+        b = P.rhs_a(1024, 12.0)
+    elif name == "c3":
+        A = P.laplace3d(128)
+        b = None
+    elif name == "c4":
+        A = P.laplace3d(300)
+        b = np.ones(A.shape[0])
+    elif name == "c5":
+        A = P.powerlaw_spd()
+        b = A @ np.ones(A.shape[0])
+    else:
+        raise SystemExit(f"unknown workload {name}")
+    n = A.shape[0]
+    if not cplx and np.iscomplexobj(A.data):
+        raise SystemExit(f"workload {name} is complex; pick --dtype c64 or c128")
+    if b is None or k > 1:
+        cols = []
+        for r in range(k):
+            if b is not None and r == 0:
+                cols.append(b)
+            else:
+                v = np.random.default_rng(1000 + r).uniform(-1.0, 1.0, n)
+                cols.append(v + 0j if cplx else v)
+        B = np.concatenate(cols)
+    else:
+        B = b
+    A = A.astype(np_t)
+    return A, np.ascontiguousarray(B, dtype=np_t)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            pass
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        rows = [l.strip().split(", ") for l in open(self.f.name) if l.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons, power = [], [], set(), []
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for r in rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2])); power.append(float(r[3]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, r[5:9]):
+                if v.strip().lower().startswith("active"):
+                    reasons.add(nm)
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons),
+                       samples=len(sm), power_w_max=max(power))
+        return out
+
+
+def measured_peak():
+    try:
+        pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(pk["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
+    except Exception:
+        return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md); MEASURED_PEAKS.json absent"
+
+
+def calibrate(cpu_ref, A, B, k):
+    """Seconds per CG iteration of the oracle on this host (after one warm call)."""
+    cpu_ref.cg(A.data, A.indptr, A.indices, B, k=k, iters=1)
+    t0 = time.perf_counter()
+    cpu_ref.cg(A.data, A.indptr, A.indices, B, k=k, iters=7)
+    return max((time.perf_counter() - t0) / 8.0, 1e-7)          # 7 iterations + the initialisation
+
+
+def cpu_sample(A, B, k, target_s, max_iters):
+    """Time the oracle port on the host cores for about target_s seconds of CG iterations."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import cpu_ref
+    cpu_ref.build()
+    per_it = calibrate(cpu_ref, A, B, k)
+    iters = int(max(4, min(max_iters, target_s / per_it)))
+    t0 = time.perf_counter()
+    cpu_ref.cg(A.data, A.indptr, A.indices, B, k=k, iters=iters)
+    dt = time.perf_counter() - t0
+    return iters, dt, cpu_ref.threads()
+
+
+def run_reference(args, wl, dtype, k, rank, world):
+    """--impl reference: the reference's CPU implementation of the path = the oracle port (the OpenCL
+    original cannot run in this image: no ICD); rank 0 only."""
+    if rank != 0:
+        return
+    A, B = make_problem(args.workload, dtype, k)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import cpu_ref
+    cpu_ref.build()
+    per_it = calibrate(cpu_ref, A, B, k)
+    # a step is a bounded sample: as many of the 256 iterations as fit ~2 s of host time
+    budget = 120.0 / max(1, args.steps + args.warmup)
+    iters = int(max(2, min(ITERS_PER_STEP, min(2.0, budget) / per_it)))
+    for _ in range(args.warmup):
+        cpu_ref.cg(A.data, A.indptr, A.indices, B, k=k, iters=iters)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_ref.cg(A.data, A.indptr, A.indices, B, k=k, iters=iters)
+    dt = time.perf_counter() - t0
+    value = args.steps * iters * k / dt
+    line = {
+        "impl": "reference", "metric": "CG iters/sec", "value": value, "unit": "iterations/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": dtype, "data": "synthetic",
+        "config": config_of(args, wl, A, k, dtype, world),
+        "cpu_baseline": {"value": value, "unit": "iterations/s", "cores": cpu_ref.threads(), "kind": "port",
+                         "sample": f"{iters} of the {ITERS_PER_STEP} iterations of a step, x {args.steps} steps, "
+                                   f"oracle/cpu_ref.c (OpenMP) on {os.cpu_count()} host cpus"},
+        "e2e": {"value": value, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def config_of(args, wl, A, k, dtype, world):
+    return {"workload": f"{wl['desc']}; n={A.shape[0]}, nnz={A.nnz}, k={k} per GPU, dtype {dtype}; "
+                        f"step = one cg() call of {ITERS_PER_STEP} iterations from x0=0",
+            "name": args.workload, "n": int(A.shape[0]), "nnz": int(A.nnz), "k": int(k),
+            "iters_per_step": ITERS_PER_STEP,
+            "parallelism": "single GPU" if world == 1 else f"rhs-split x{world} (matrix replicated, no collective)",
+            "l2": "no L2 flush: matrix + vectors per iteration exceed the 126 MB L2"
+                  if A.nnz * (A.dtype.itemsize + 4) > 126e6 else
+                  "working set fits the 126 MB L2 (latency-bound config); no flush between iterations"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--dtype", default=None, choices=["f32", "f64", "c64", "c128"])
+    ap.add_argument("--k", type=int, default=None)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    wl = WORKLOADS[args.workload]
+    dtype = args.dtype or wl["dtype"]
+    k = args.k or wl["k"]
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, wl, dtype, k, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import cg_b200
+    import cg_b200.problems as P
+    if not torch.cuda.is_available() or cg_b200.device_count() < 1:
+        raise SystemExit("bench.py: no CUDA device; the engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    A, B = make_problem(args.workload, dtype, k)
+    if world > 1 and k == 1:
+        # rhs-split: every rank gets its own right-hand side (rank 0 keeps the config's b)
+        if rank > 0:
+            v = np.random.default_rng(1000 + rank).uniform(-1.0, 1.0, A.shape[0])
+            B = np.ascontiguousarray(v + 0j if P.DTYPES[dtype][3] else v, dtype=A.dtype)
+    n, nnz = A.shape[0], A.nnz
+    v_bytes = P.DTYPES[dtype][2]
+    b_spmv, b_iter = P.algorithmic_bytes(n, nnz, k, dtype)
+
+    stream = torch.cuda.Stream()
+    tdt = {"f32": torch.float32, "f64": torch.float64, "c64": torch.complex64, "c128": torch.complex128}[dtype]
+    M = cg_b200.Matrix.from_scipy(A, device=local_rank)
+    M.set_stream(stream.cuda_stream)
+    with torch.cuda.stream(stream):
+        b_dev = torch.from_numpy(B).to("cuda", non_blocking=False)
+        x_dev = torch.zeros(n * k, dtype=tdt, device="cuda")
+
+    def step():
+        x_dev.zero_()
+        M.solve(b_dev, x=x_dev, k=k, max_iterations=ITERS_PER_STEP, tol=0.0)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.cuda.stream(stream):
+        for _ in range(args.warmup):
+            step()
+        launches0 = M.info()["launches"]
+        barrier()
+        sampler = ClockSampler(local_rank)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.steps):
+            step()
+        e1.record(stream)
+        barrier()
+        clocks = sampler.stop()
+        ms = e0.elapsed_time(e1)
+        launches = M.info()["launches"] - launches0
+        timing = M.solve(b_dev, x=x_dev, k=k, max_iterations=ITERS_PER_STEP)[1].timing_ms
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    ms_per_step = ms / args.steps
+    value = world * k * ITERS_PER_STEP / (ms_per_step / 1e3)    # right-hand-side iterations per second, whole job
+
+    # ---- per-kernel rooflines (rank 0), CUDA events around back-to-back launches of one kernel
+    peak, peak_src = measured_peak()
+    kernels = {}
+    if rank == 0:
+        reps = 50 if b_iter > 50e6 else 400
+        bytes_of = {"spmv_dot": b_spmv, "update_xr": 6 * k * n * v_bytes, "update_d": 3 * k * n * v_bytes}
+        for name, nbytes in bytes_of.items():
+            kms = M.time_kernel(name, k=k, reps=reps)
+            kernels[name] = {"ms": kms, "algorithmic_bytes": nbytes, "gbs": nbytes / kms / 1e6,
+                             "frac": nbytes / kms / 1e6 / peak}
+        M.solve(b_dev, x=x_dev, k=k, max_iterations=2)          # restore a sane state
+    it_ms = timing["iterations"] / ITERS_PER_STEP
+
+    # ---- e2e through the exported cg / cgd symbol, pinned host buffers, matrix re-uploaded each step
+    e2e = None
+    if not args.no_e2e:
+        os.environ["CGB200_CACHE"] = "0"
+        os.environ["CGB200_DEVICE"] = str(local_rank)
+        pin = lambda a: torch.from_numpy(a).pin_memory().numpy()
+        vals_h, ptr_h, cols_h = pin(A.data), pin(A.indptr.astype(np.intc)), pin(A.indices.astype(np.intc))
+        b_h, x_h = pin(B), pin(np.zeros_like(B))
+        def e2e_step():
+            x_h[...] = 0
+            t0 = time.perf_counter()
+            cg_b200.cg(n, nnz, vals_h, b_h, ptr_h, cols_h, x_h, k, ITERS_PER_STEP)
+            return time.perf_counter() - t0
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        tt = sum(e2e_step() for _ in range(args.steps))
+        t = torch.tensor([tt], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        tt = float(t.item())
+        h2d = nnz * (v_bytes + 4) + 4 * (n + 1) + 2 * k * n * v_bytes
+        e2e = {"value": world * k * ITERS_PER_STEP * args.steps / tt, "unit": "iterations/s",
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(k * n * v_bytes),
+               "ms_per_step": 1e3 * tt / args.steps,
+               "how": "cg()/cgd() C symbol on pinned host numpy arrays; CSR matrix, b, x0 uploaded and x read back "
+                      "inside every timed call (CGB200_CACHE=0); wall clock around the blocking call"}
+        # the as_prec pattern: same matrix on every call -> resident copy reused (content hash), only b/x move
+        os.environ["CGB200_CACHE"] = "1"
+        e2e_step()
+        tt2 = sum(e2e_step() for _ in range(args.steps))
+        e2e["resident_matrix_value"] = world * k * ITERS_PER_STEP * args.steps / tt2
+        cg_b200._lib.lib().cgb200_clear_cache()
+
+    if rank == 0:
+        cpu = None
+        if not args.no_cpu_baseline:
+            iters, dt, threads = cpu_sample(A, B, k, 12.0, ITERS_PER_STEP)
+            cpu = {"value": iters * k / dt, "unit": "iterations/s", "cores": threads, "kind": "port",
+                   "sample": f"{iters} CG iterations of the same system on the host "
+                             f"(oracle/cpu_ref.c, OpenMP, {threads} threads of {os.cpu_count()} cpus), {dt:.1f} s"}
+        dom = max(kernels, key=lambda nm: kernels[nm]["ms"])
+        line = {
+            "metric": "CG iters/sec", "value": value, "unit": "iterations/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": dtype, "data": "synthetic",
+            "config": config_of(args, wl, A, k, dtype, world),
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["gbs"], "peak": peak, "unit": "GB/s",
+                         "frac": kernels[dom]["frac"], "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": kernels[dom]["algorithmic_bytes"],
+                         "ms_per_launch": kernels[dom]["ms"]},
+            "kernels": kernels,
+            "iteration": {"ms": it_ms, "algorithmic_bytes": b_iter, "gbs": b_iter / it_ms / 1e6,
+                          "frac": b_iter / it_ms / 1e6 / peak, "spmv_pct_of_nominal_8TBs": None},
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "solve_phases_ms": timing,
+        }
+        line["iteration"]["spmv_pct_of_nominal_8TBs"] = 100.0 * kernels["spmv_dot"]["gbs"] / 8000.0
+        print(json.dumps(line), flush=True)
+    M.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

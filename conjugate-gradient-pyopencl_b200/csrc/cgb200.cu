@@ -516,6 +516,43 @@ template <typename T> struct Engine {
         return 0;
     }
 
+    // ---- one kernel of the CG loop, launched `reps` times back to back, timed with CUDA
+    // events on the handle's stream (for the roofline lines of bench.py).  Must follow a solve
+    // with the same k (the work vectors then hold sane values).  Leaves the state unusable
+    // until the next solve re-initialises it.
+    static int time_kernel(cgb200_ctx *c, int which, int k, int reps, double *ms_avg) {
+        if (!c->x || c->ws_k < k) return fail(CGB200_ERR_ARG, "time_kernel: run a solve with k=%d first", k);
+        if (!batch_ok(k)) return fail(CGB200_ERR_UNSUPPORTED, "time_kernel: k=%d exceeds one batch", k);
+        const CgScalars<T> sc = scalars(c, k, 0.0, 0);
+        const VecGeom g = geom(c, k);
+        // keep every column ACTIVE and the updates neutral: alpha = 0 (dq = 0), beta = 0 (delta_new = 0)
+        CU(cudaMemsetAsync(sc.state, 0, k * sizeof(int), c->stream));
+        int one = k;
+        CU(cudaMemcpyAsync(sc.n_active, &one, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        if (which == 1) CU(cudaMemsetAsync(sc.dq, 0, k * sizeof(T), c->stream));
+        if (which == 2) CU(cudaMemsetAsync(sc.delta_new, 0, k * sizeof(T), c->stream));
+        auto launch = [&]() -> int {
+            switch (which) {
+            case 0: return spmv<true>(c, k, (const T *)c->d, (T *)c->q, sc);
+            case 1: return g.V == 1 ? launch_update_xr<1>(c, k, g, sc) : launch_update_xr<VW>(c, k, g, sc);
+            case 2: return g.V == 1 ? launch_update_d<1>(c, k, g, sc) : launch_update_d<VW>(c, k, g, sc);
+            case 3: return spmv<false>(c, k, (const T *)c->d, (T *)c->q, sc);
+            }
+            return fail(CGB200_ERR_ARG, "time_kernel: which=%d", which);
+        };
+        for (int i = 0; i < 3; i++) TRY(launch());
+        CU(cudaEventRecord(c->ev[0], c->stream));
+        for (int i = 0; i < reps; i++) TRY(launch());
+        CU(cudaEventRecord(c->ev[1], c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        CU(cudaGetLastError());
+        float f = 0;
+        CU(cudaEventElapsedTime(&f, c->ev[0], c->ev[1]));
+        *ms_avg = (double)f / reps;
+        return 0;
+    }
+
     static int solve_api(cgb200_ctx *c, const void *b, void *x, int k, int maxit, double tol, int *iters,
                          double *relres, double *hist, int layout) {
         int flags = 0;
@@ -724,6 +761,12 @@ int cgb200_solve(cgb200_handle c, const void *b, void *x, int k, int max_iterati
     if (layout != CGB200_LAYOUT_CLCG && layout != CGB200_LAYOUT_ROWMAJOR) return fail(CGB200_ERR_ARG, "bad layout");
     DeviceGuard guard(c->device);
     return DISPATCH(c, E::solve_api(c, b, x, k, max_iterations, tol, iterations, relres, delta_hist, layout));
+}
+
+int cgb200_time_kernel(cgb200_handle c, int which, int k, int reps, double *ms_avg) {
+    if (!c || !ms_avg || reps < 1 || k < 1) return fail(CGB200_ERR_ARG, "bad time_kernel arguments");
+    DeviceGuard guard(c->device);
+    return DISPATCH(c, E::time_kernel(c, which, k, reps, ms_avg));
 }
 
 int cgb200_last_timing(cgb200_handle c, double ms[4]) {

@@ -111,6 +111,14 @@ class Matrix:
                 "max_row", "device")
         return dict(zip(keys, list(out)))
 
+    KERNELS = {"spmv_dot": 0, "update_xr": 1, "update_d": 2, "spmv": 3}
+
+    def time_kernel(self, which, k=1, reps=50):
+        """Mean milliseconds of one kernel of the CG loop over `reps` back-to-back launches (CUDA events)."""
+        ms = ctypes.c_double()
+        check(lib().cgb200_time_kernel(self._h, self.KERNELS[which], int(k), int(reps), ctypes.byref(ms)))
+        return ms.value
+
     # -- operations ---------------------------------------------------------------
     def spmv(self, x, y=None, k=1, layout=_lib.LAYOUT_CLCG):
         """y = A x.  numpy in -> numpy out (blocking); device tensors in -> asynchronous, y required."""

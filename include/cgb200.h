@@ -97,6 +97,13 @@ CGB200_API int cgb200_solve(cgb200_handle h, const void *b, void *x, int k, int 
  * [3] result back (+ layout change). */
 CGB200_API int cgb200_last_timing(cgb200_handle h, double ms[4]);
 
+/* Measurement hook: launches ONE kernel of the CG loop `reps` times back to back on the
+ * handle's stream (after 3 warm-up launches) between two CUDA events and returns the mean
+ * duration.  which: 0 spmv fused with d.q (spmv.cl + vdot.cl), 1 x/r update fused with r.r
+ * (axpy.cl x2 + vdot.cl), 2 direction update (aypx.cl), 3 plain spmv.  Call it after a
+ * cgb200_solve() with the same k; the next solve re-initialises the state it disturbs. */
+CGB200_API int cgb200_time_kernel(cgb200_handle h, int which, int k, int reps, double *ms_avg);
+
 /* Facts about a handle, for benches and tests:
  * [0] n [1] nnz [2] dtype [3] lanes_per_row [4] persistent grid of the SpMV kernel
  * [5] SM count [6] kernels launched so far [7] graph launches so far
