@@ -212,6 +212,7 @@ def main():
     ap.add_argument("--k", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--opt", action="append", default=[], help="engine option key=value (cgb200_set_option)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     wl = WORKLOADS[args.workload]
@@ -249,6 +250,9 @@ def main():
     tdt = {"f32": torch.float32, "f64": torch.float64, "c64": torch.complex64, "c128": torch.complex128}[dtype]
     M = cg_b200.Matrix.from_scipy(A, device=local_rank)
     M.set_stream(stream.cuda_stream)
+    for kv in args.opt:
+        key, val = kv.split("=")
+        M.set_option(key, int(val))
     with torch.cuda.stream(stream):
         b_dev = torch.from_numpy(B).to("cuda", non_blocking=False)
         x_dev = torch.zeros(n * k, dtype=tdt, device="cuda")
@@ -262,12 +266,12 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)          # nvidia-smi needs ~0.5 s to start: the warm-up steps cover it
     with torch.cuda.stream(stream):
         for _ in range(args.warmup):
             step()
         launches0 = M.info()["launches"]
         barrier()
-        sampler = ClockSampler(local_rank)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         for _ in range(args.steps):
@@ -352,7 +356,7 @@ def main():
             "kernels": kernels,
             "iteration": {"ms": it_ms, "algorithmic_bytes": b_iter, "gbs": b_iter / it_ms / 1e6,
                           "frac": b_iter / it_ms / 1e6 / peak, "spmv_pct_of_nominal_8TBs": None},
-            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "options": args.opt, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "solve_phases_ms": timing,
         }
         line["iteration"]["spmv_pct_of_nominal_8TBs"] = 100.0 * kernels["spmv_dot"]["gbs"] / 8000.0

@@ -69,8 +69,11 @@ struct cgb200_ctx {
     int sm_count = 0;
     int max_row = 0;
     double mean_row = 0;
+    // CSR-stream schedule (k = 1): tiles of whole rows / chunks of long rows
+    void *d_tiles = nullptr, *d_long = nullptr, *d_chunk_sum = nullptr;
+    int ntiles = 0, nlong = 0, nslots = 0;
     // options
-    int opt_lpr = 0, graph_chunk = 16, use_graph = 1, blocks_per_sm = 0;
+    int opt_lpr = 0, graph_chunk = 16, use_graph = 1, blocks_per_sm = 0, spmv_variant = 0;
     // workspace (for ws_k right-hand sides)
     int ws_k = 0;
     void *x = nullptr, *r = nullptr, *d = nullptr, *q = nullptr, *stage = nullptr;
@@ -87,7 +90,7 @@ struct cgb200_ctx {
     int graph_hist_cap = -1;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     double last_ms[4] = {0, 0, 0, 0};
-    long long launches = 0, graph_launches = 0;
+    long long launches = 0, graph_launches = 0, graph_nodes = 0;
     std::map<const void *, int> occ;   // kernel -> resident blocks per SM
     int spmv_grid_last = 0;
 };
@@ -236,6 +239,85 @@ template <typename T> struct Engine {
         default: return launch_spmv1<32, DOT>(c, x, y, sc);
         }
     }
+    // ---- CSR-stream schedule -------------------------------------------------
+    static int build_tiles(cgb200_ctx *c, const std::vector<int> &rp) {
+        using C = StreamCfg<T>;
+        const int cap = C::CAP, rowcap = C::RMAX;
+        std::vector<SpmvTile> tiles;
+        std::vector<LongRow> longs;
+        int slots = 0;
+        tiles.reserve((size_t)(c->nnz / cap) + 16);
+        for (int r = 0; r < c->n;) {
+            const int len = rp[r + 1] - rp[r];
+            if (len > cap) {
+                const int nch = (len + cap - 1) / cap;
+                longs.push_back(LongRow{r, slots, nch});
+                for (int ch = 0; ch < nch; ch++)
+                    tiles.push_back(SpmvTile{r, -(slots + ch + 1), rp[r] + ch * cap, std::min(rp[r + 1], rp[r] + (ch + 1) * cap)});
+                slots += nch;
+                r++;
+                continue;
+            }
+            int e = r, cnt = 0;
+            while (e < c->n && e - r < rowcap) {
+                const int l = rp[e + 1] - rp[e];
+                if (l > cap || cnt + l > cap) break;
+                cnt += l;
+                e++;
+            }
+            tiles.push_back(SpmvTile{r, e, rp[r], rp[e]});
+            r = e;
+        }
+        c->ntiles = (int)tiles.size();
+        c->nlong = (int)longs.size();
+        c->nslots = slots;
+        CU(cudaMalloc(&c->d_tiles, std::max<size_t>(1, tiles.size()) * sizeof(SpmvTile)));
+        CU(cudaMemcpy(c->d_tiles, tiles.data(), tiles.size() * sizeof(SpmvTile), cudaMemcpyHostToDevice));
+        if (!longs.empty()) {
+            CU(cudaMalloc(&c->d_long, longs.size() * sizeof(LongRow)));
+            CU(cudaMemcpy(c->d_long, longs.data(), longs.size() * sizeof(LongRow), cudaMemcpyHostToDevice));
+            CU(cudaMalloc(&c->d_chunk_sum, (size_t)slots * sizeof(T)));
+        }
+        return 0;
+    }
+    template <bool DOT>
+    static int spmv_stream(cgb200_ctx *c, const T *x, T *y, const CgScalars<T> &sc) {
+        using C = StreamCfg<T>;
+        auto kern = spmv_stream_kernel<T, DOT>;
+        const size_t smem = (size_t)(C::TILE + C::THREADS) * sizeof(T);
+        const int grid = persistent_grid(c, kern, C::THREADS, smem, c->ntiles);
+        c->spmv_grid_last = grid;
+        kern<<<grid, C::THREADS, smem, c->stream>>>(c->ntiles, (const SpmvTile *)c->d_tiles, (const T *)c->d_vals,
+                                                    c->d_rowptr, c->d_cols, x, y, (T *)c->d_chunk_sum, sc);
+        c->launches++;
+        if (c->nlong > 0) {
+            combine_long_rows_kernel<T><<<(c->nlong + 127) / 128, 128, 0, c->stream>>>(
+                c->nlong, (const LongRow *)c->d_long, (const T *)c->d_chunk_sum, y);
+            c->launches++;
+        }
+        return 0;
+    }
+    template <int S, bool DOT>
+    static int spmv_tma(cgb200_ctx *c, const T *x, T *y, const CgScalars<T> &sc) {
+        using C = StreamCfg<T>;
+        using K = TmaCfg<T, S>;
+        auto kern = spmv_tma_kernel<T, S, DOT>;
+        const size_t smem = K::SMEM_BYTES;
+        const void *key = (const void *)kern;
+        if (c->occ.find(key) == c->occ.end())
+            CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int grid = persistent_grid(c, kern, C::THREADS, smem, c->ntiles);
+        c->spmv_grid_last = grid;
+        kern<<<grid, C::THREADS, smem, c->stream>>>(c->ntiles, (const SpmvTile *)c->d_tiles, (const T *)c->d_vals,
+                                                    c->d_rowptr, c->d_cols, x, y, (T *)c->d_chunk_sum, sc);
+        c->launches++;
+        if (c->nlong > 0) {
+            combine_long_rows_kernel<T><<<(c->nlong + 127) / 128, 128, 0, c->stream>>>(
+                c->nlong, (const LongRow *)c->d_long, (const T *)c->d_chunk_sum, y);
+            c->launches++;
+        }
+        return 0;
+    }
     template <int V, int G, bool DOT>
     static int launch_spmm(cgb200_ctx *c, int k, const T *x, T *y, const CgScalars<T> &sc) {
         auto kern = spmm_kernel<T, V, G, DOT>;
@@ -260,7 +342,15 @@ template <typename T> struct Engine {
     }
     template <bool DOT>
     static int spmv(cgb200_ctx *c, int k, const T *x, T *y, const CgScalars<T> &sc) {
-        if (k == 1) return spmv1<DOT>(c, x, y, sc);
+        if (k == 1) {
+            switch (c->d_tiles ? c->spmv_variant : 1) {
+            case 1: return spmv1<DOT>(c, x, y, sc);
+            case 2: return spmv_stream<DOT>(c, x, y, sc);
+            case 4: return spmv_tma<3, DOT>(c, x, y, sc);
+            case 5: return spmv_tma<4, DOT>(c, x, y, sc);
+            default: return spmv_tma<2, DOT>(c, x, y, sc);      // 0 (auto), 3
+            }
+        }
         if (pack_width(k) == 1) return spmm_v<1, DOT>(c, k, x, y, sc);
         return spmm_v<VW, DOT>(c, k, x, y, sc);
     }
@@ -321,7 +411,7 @@ template <typename T> struct Engine {
 
     static int transpose(cgb200_ctx *c, const T *src, T *dst, int rows, long long cols) {
         dim3 block(32, 8);
-        dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32));
+        dim3 grid((unsigned)(((cols + 31) / 32) * ((rows + 31) / 32)));
         transpose_kernel<T><<<grid, block, 0, c->stream>>>(src, dst, rows, cols);
         c->launches++;
         return 0;
@@ -432,6 +522,7 @@ template <typename T> struct Engine {
                 int rc = 0;
                 for (int i = 0; i < chunk && rc == 0; i++) rc = iteration(c, k, g, sc);
                 cudaError_t ce = cudaStreamEndCapture(c->stream, &gr);
+                c->graph_nodes = c->launches - before;
                 c->launches = before;
                 if (rc < 0) return rc;
                 if (ce != cudaSuccess) return fail(CGB200_ERR_CUDA, "graph capture: %s", cudaGetErrorString(ce));
@@ -446,7 +537,7 @@ template <typename T> struct Engine {
             while (done + chunk <= maxit) {
                 CU(cudaGraphLaunch(c->graph, c->stream));
                 c->graph_launches++;
-                c->launches += 3LL * chunk;
+                c->launches += c->graph_nodes;
                 done += chunk;
                 if (tol > 0) {
                     CU(cudaMemcpyAsync(c->h_flag, sc.n_active, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
@@ -677,10 +768,15 @@ int cgb200_create(cgb200_handle *out, int n, long long nnz, const void *aValues,
     }
     c->max_row = mx;
     c->mean_row = (double)nnz / n;
+    {
+        int rc = DISPATCH(c, E::build_tiles(c, rp));
+        if (rc < 0) return bail(rc);
+    }
     if (const char *e = getenv("CGB200_LANES_PER_ROW")) c->opt_lpr = atoi(e);
     if (const char *e = getenv("CGB200_GRAPH_CHUNK")) c->graph_chunk = std::max(1, atoi(e));
     if (const char *e = getenv("CGB200_USE_GRAPH")) c->use_graph = atoi(e);
     if (const char *e = getenv("CGB200_BLOCKS_PER_SM")) c->blocks_per_sm = atoi(e);
+    if (const char *e = getenv("CGB200_SPMV_VARIANT")) c->spmv_variant = atoi(e);
     *out = c;
     return CGB200_OK;
 }
@@ -691,6 +787,9 @@ int cgb200_destroy(cgb200_handle c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     free_workspace(c);
     if (c->d_hist) cudaFree(c->d_hist);
+    if (c->d_tiles) cudaFree(c->d_tiles);
+    if (c->d_long) cudaFree(c->d_long);
+    if (c->d_chunk_sum) cudaFree(c->d_chunk_sum);
     if (c->d_vals) cudaFree(c->d_vals);
     if (c->d_cols) cudaFree(c->d_cols);
     if (c->d_rowptr) cudaFree(c->d_rowptr);
@@ -723,6 +822,7 @@ static int *option_slot(cgb200_handle c, const char *key) {
     if (!strcmp(key, "graph_chunk")) return &c->graph_chunk;
     if (!strcmp(key, "use_graph")) return &c->use_graph;
     if (!strcmp(key, "blocks_per_sm")) return &c->blocks_per_sm;
+    if (!strcmp(key, "spmv_variant")) return &c->spmv_variant;
     return nullptr;
 }
 

@@ -47,6 +47,22 @@ template <typename T> struct CgScalars {
 // Matrix streams (values, column indices) are read exactly once per SpMV: mark them
 // streaming so they do not displace the gathered vector from L1/L2.
 template <typename T> __device__ __forceinline__ T ld_stream(const T *p) { return __ldcs(p); }
+// 4-, 8- or 16-byte streaming load of any trivially copyable bundle.
+template <typename P> __device__ __forceinline__ P ld_stream_bytes(const P *p) {
+    P out;
+    if constexpr (sizeof(P) == 16) {
+        const uint4 v = __ldcs(reinterpret_cast<const uint4 *>(p));
+        memcpy(&out, &v, 16);
+    } else if constexpr (sizeof(P) == 8) {
+        const uint2 v = __ldcs(reinterpret_cast<const uint2 *>(p));
+        memcpy(&out, &v, 8);
+    } else {
+        static_assert(sizeof(P) == 4, "ld_stream_bytes: 4, 8 or 16 bytes");
+        const unsigned v = __ldcs(reinterpret_cast<const unsigned *>(p));
+        memcpy(&out, &v, 4);
+    }
+    return out;
+}
 // Cross-block data (partials) must come from L2, never from a stale L1 line.
 template <typename T> __device__ __forceinline__ T ld_cg(const T *p) { return __ldcg(p); }
 
@@ -130,7 +146,7 @@ spmv1_kernel(int n, const T *__restrict__ vals, const int *__restrict__ rowptr,
     if (DOT) {
         if (*sc.n_active == 0) return;
     }
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     T *smem = reinterpret_cast<T *>(smem_raw);
     const int t = threadIdx.x;
     const int lane = t % LPR;
@@ -178,6 +194,354 @@ spmv1_kernel(int n, const T *__restrict__ vals, const int *__restrict__ rowptr,
 }
 
 // ---------------------------------------------------------------------------
+// SpMV, one right-hand side, "CSR-stream": the schedule for short or irregular rows.
+//
+// The non-zeros are cut, at matrix set-up, into tiles of at most TILE entries that hold
+// whole rows (a row longer than a tile is cut into chunks).  A block
+//   1. streams the tile's values and column indices with fully coalesced 128-bit loads
+//      (every lane busy whatever the row lengths are), gathers x[col] and leaves the
+//      products in shared memory;
+//   2. sums each row's products out of shared memory -- one thread per row when rows
+//      are short, a power-of-two group of lanes per row when the tile holds few rows.
+// Load balance is per non-zero, not per row, so power-law matrices cost the same per
+// entry as stencils.  A long row's chunk sums go to `chunk_sum` and are added up by
+// combine_long_rows_kernel; the fused d.q term of such a row uses linearity,
+// d_i * (partial row sum), so it needs no second pass.
+// ---------------------------------------------------------------------------
+struct SpmvTile {
+    int r0;   // first row
+    int r1;   // one past the last row; < 0: chunk of long row r0, result slot -(r1 + 1)
+    int p0;   // first non-zero
+    int p1;   // one past the last non-zero
+};
+
+template <typename T> struct StreamCfg {
+    static constexpr int VPT = VecW<T>::value;                 // values per 128-bit load
+    static constexpr int U = (sizeof(T) == 16) ? 4 : (sizeof(T) == 4 ? 2 : 4);   // loads in flight per thread
+    static constexpr int THREADS = 256;
+    static constexpr int TILE = THREADS * VPT * U;             // products held in shared memory
+    static constexpr int CAP = TILE - 4;                       // non-zeros per tile (16-byte aligned windows may start 3 entries early)
+    static constexpr int RMAX = 512;                           // rows per tile (their row offsets are staged in shared memory)
+};
+
+template <int VPT> struct ColPack;
+template <> struct ColPack<1> { int c[1]; };
+template <> struct alignas(8) ColPack<2> { int c[2]; };
+template <> struct alignas(16) ColPack<4> { int c[4]; };
+
+template <typename T, bool DOT>
+__global__ void __launch_bounds__(256)
+spmv_stream_kernel(int ntiles, const SpmvTile *__restrict__ tiles, const T *__restrict__ vals,
+                   const int *__restrict__ rowptr, const int *__restrict__ cols,
+                   const T *__restrict__ x, T *__restrict__ y, T *__restrict__ chunk_sum,
+                   CgScalars<T> sc) {
+    using C = StreamCfg<T>;
+    constexpr int VPT = C::VPT, U = C::U, NT = C::THREADS;
+    using VP = Pack<T, VPT>;
+    using CP = ColPack<VPT>;
+    if (DOT) {
+        if (*sc.n_active == 0) return;
+    }
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    T *prod = reinterpret_cast<T *>(smem_raw);                 // [TILE]
+    T *red = prod + C::TILE;                                   // [NT] block-reduction scratch
+    const int t = threadIdx.x;
+    T dot[1] = {Sc<T>::zero()};
+
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const SpmvTile tl = tiles[tile];
+        const int base = tl.p0 - (tl.p0 % VPT);
+        // ---- 1. stream A, gather x, products to shared memory
+        VP av[U];
+        CP cv[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int j0 = base + (t + u * NT) * VPT;
+            if (j0 < tl.p1) {
+                av[u] = ld_stream_bytes(reinterpret_cast<const VP *>(vals + j0));
+                cv[u] = ld_stream_bytes(reinterpret_cast<const CP *>(cols + j0));
+            }
+        }
+        T xv[U][VPT];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int j0 = base + (t + u * NT) * VPT;
+#pragma unroll
+            for (int e = 0; e < VPT; e++) {
+                const int j = j0 + e;
+                if (j >= tl.p0 && j < tl.p1) xv[u][e] = __ldg(x + cv[u].c[e]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int j0 = base + (t + u * NT) * VPT;
+#pragma unroll
+            for (int e = 0; e < VPT; e++) {
+                const int j = j0 + e;
+                if (j >= tl.p0 && j < tl.p1) prod[j - base] = Sc<T>::mul(av[u].v[e], xv[u][e]);
+            }
+        }
+        __syncthreads();
+
+        if (tl.r1 >= 0) {
+            // ---- 2. row sums
+            const int rows = tl.r1 - tl.r0;
+            int lpr = 1;
+            while (lpr < 32 && rows * lpr * 2 <= NT) lpr *= 2;
+            const int g = t / lpr, lane = t % lpr, groups = NT / lpr;
+            for (int rr0 = 0; rr0 < rows; rr0 += groups) {
+                const int rr = rr0 + g;
+                const bool valid = rr < rows;
+                T sum = Sc<T>::zero();
+                if (valid) {
+                    const int lo = __ldg(rowptr + tl.r0 + rr) - base;
+                    const int hi = __ldg(rowptr + tl.r0 + rr + 1) - base;
+                    for (int j = lo + lane; j < hi; j += lpr) sum = Sc<T>::add(sum, prod[j]);
+                }
+                for (int off = lpr >> 1; off > 0; off >>= 1) {
+                    if constexpr (Sc<T>::cplx) {
+                        sum.x += __shfl_xor_sync(0xffffffffu, sum.x, off);
+                        sum.y += __shfl_xor_sync(0xffffffffu, sum.y, off);
+                    } else {
+                        sum += __shfl_xor_sync(0xffffffffu, sum, off);
+                    }
+                }
+                if (valid && lane == 0) {
+                    const int row = tl.r0 + rr;
+                    y[row] = sum;
+                    if (DOT) dot[0] = Sc<T>::fma(__ldg(x + row), sum, dot[0]);
+                }
+            }
+        } else {
+            // ---- 2'. chunk of a long row: one sum for the whole tile
+            T part[1] = {Sc<T>::zero()};
+            for (int j = tl.p0 - base + t; j < tl.p1 - base; j += NT) part[0] = Sc<T>::add(part[0], prod[j]);
+            block_col_reduce<T, 1>(part, 1, red);
+            if (t == 0) {
+                chunk_sum[-(tl.r1 + 1)] = red[0];
+                if (DOT) dot[0] = Sc<T>::fma(__ldg(x + tl.r0), red[0], dot[0]);
+            }
+        }
+        __syncthreads();   // prod is rewritten by the next tile
+    }
+
+    if (DOT) {
+        block_col_reduce<T, 1>(dot, 1, red);
+        if (publish_and_arrive<T, 1>(red, 1, 1, sc.partial, sc.ticket + TK_SPMV)) {
+            grid_col_reduce<T, 1>(sc.partial, 1, 1, 1, red);
+            if (t == 0) {
+                sc.dq[0] = red[0];
+                sc.ticket[TK_SPMV] = 0;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// SpMV, one right-hand side, CSR-stream fed by the TMA engine.
+//
+// Same tiles and the same two phases as spmv_stream_kernel, but the matrix stream never
+// passes through registers: one elected thread issues 1-D bulk async copies
+// (cp.async.bulk global -> shared, completion counted in bytes on an mbarrier) for the
+// tile's values, column indices and row offsets into an S-stage ring, S tiles ahead of
+// the one being consumed.  DRAM latency of the A stream is therefore always covered by
+// S * ~20 KB in flight per block, independent of occupancy, and the 256 threads spend
+// their issue slots on the x gather and the row sums only.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long *bar, unsigned parity) {
+    unsigned ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+// A lost completion would otherwise hang the GPU: trap instead after ~seconds.
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+    unsigned spins = 0;
+    while (!mbar_try_wait(bar, parity))
+        if (++spins > (1u << 22)) __trap();
+}
+
+template <typename T, int S> struct TmaCfg {
+    using C = StreamCfg<T>;
+    static constexpr int TILE = C::TILE;
+    static constexpr size_t VALS_BYTES = (size_t)TILE * sizeof(T);
+    static constexpr size_t COLS_BYTES = (size_t)TILE * sizeof(int);
+    static constexpr size_t ROWS_BYTES = (size_t)(C::RMAX + 8) * sizeof(int);
+    static constexpr size_t STAGE_BYTES = VALS_BYTES + COLS_BYTES + ROWS_BYTES;
+    static constexpr size_t BAR_BYTES = 128;
+    static constexpr size_t PROD_BYTES = (size_t)TILE * sizeof(T);
+    static constexpr size_t RED_BYTES = (size_t)C::THREADS * sizeof(T);
+    static constexpr size_t SMEM_BYTES = BAR_BYTES + PROD_BYTES + RED_BYTES + S * STAGE_BYTES;
+    static_assert(STAGE_BYTES % 16 == 0 && PROD_BYTES % 16 == 0 && RED_BYTES % 16 == 0, "16-byte aligned stages");
+};
+
+template <typename T, int S, bool DOT>
+__global__ void __launch_bounds__(256)
+spmv_tma_kernel(int ntiles, const SpmvTile *__restrict__ tiles, const T *__restrict__ vals,
+                const int *__restrict__ rowptr, const int *__restrict__ cols, const T *__restrict__ x,
+                T *__restrict__ y, T *__restrict__ chunk_sum, CgScalars<T> sc) {
+    using C = StreamCfg<T>;
+    using K = TmaCfg<T, S>;
+    constexpr int VPT = C::VPT, NT = C::THREADS, NPT = C::TILE / NT;
+    if (DOT) {
+        if (*sc.n_active == 0) return;
+    }
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem_raw);
+    T *prod = reinterpret_cast<T *>(smem_raw + K::BAR_BYTES);
+    T *red = reinterpret_cast<T *>(smem_raw + K::BAR_BYTES + K::PROD_BYTES);
+    unsigned char *stage0 = smem_raw + K::BAR_BYTES + K::PROD_BYTES + K::RED_BYTES;
+    const int t = threadIdx.x;
+    const int count = ((int)blockIdx.x < ntiles) ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    T dot[1] = {Sc<T>::zero()};
+
+    if (t == 0) {
+        for (int s = 0; s < S; s++) mbar_init(&bars[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    auto issue = [&](int i) {   // thread 0: start the copies of this block's i-th tile
+        const SpmvTile tl = tiles[blockIdx.x + (size_t)i * gridDim.x];
+        unsigned char *st = stage0 + (size_t)(i % S) * K::STAGE_BYTES;
+        unsigned long long *bar = &bars[i % S];
+        const int vb = tl.p0 - (tl.p0 % VPT), cb = tl.p0 & ~3;
+        const unsigned vbytes = (unsigned)(((tl.p1 - vb + VPT - 1) / VPT) * VPT * sizeof(T));
+        const unsigned cbytes = (unsigned)(((tl.p1 - cb + 3) / 4) * 16);
+        unsigned rbytes = 0;
+        int rb = 0;
+        if (tl.r1 >= 0) {
+            rb = tl.r0 & ~3;
+            rbytes = (unsigned)(((tl.r1 + 1 - rb + 3) / 4) * 16);
+        }
+        const bool has_nnz = tl.p1 > tl.p0;
+        mbar_arrive_expect_tx(bar, (has_nnz ? vbytes + cbytes : 0u) + rbytes);
+        if (has_nnz) {
+            bulk_g2s(st, vals + vb, vbytes, bar);
+            bulk_g2s(st + K::VALS_BYTES, cols + cb, cbytes, bar);
+        }
+        if (rbytes) bulk_g2s(st + K::VALS_BYTES + K::COLS_BYTES, rowptr + rb, rbytes, bar);
+    };
+
+    if (t == 0)
+        for (int i = 0; i < S && i < count; i++) issue(i);
+
+    SpmvTile tl_next = {0, 0, 0, 0};
+    if (count > 0) tl_next = tiles[blockIdx.x];
+    for (int i = 0; i < count; i++) {
+        const SpmvTile tl = tl_next;
+        if (i + 1 < count) tl_next = tiles[blockIdx.x + (size_t)(i + 1) * gridDim.x];
+        const int s = i % S;
+        const unsigned char *st = stage0 + (size_t)s * K::STAGE_BYTES;
+        const T *vals_s = reinterpret_cast<const T *>(st);
+        const int *cols_s = reinterpret_cast<const int *>(st + K::VALS_BYTES);
+        const int *rp_s = reinterpret_cast<const int *>(st + K::VALS_BYTES + K::COLS_BYTES);
+        const int vb = tl.p0 - (tl.p0 % VPT), cb = tl.p0 & ~3;
+        mbar_wait(&bars[s], (unsigned)((i / S) & 1));
+
+        // ---- 1. products: columns from the stage, gather x, multiply, into `prod`
+        int cc[NPT];
+#pragma unroll
+        for (int u = 0; u < NPT; u++) {
+            const int j = tl.p0 + t + u * NT;
+            cc[u] = (j < tl.p1) ? cols_s[j - cb] : -1;
+        }
+        T xv[NPT];
+#pragma unroll
+        for (int u = 0; u < NPT; u++)
+            if (cc[u] >= 0) xv[u] = __ldg(x + cc[u]);
+#pragma unroll
+        for (int u = 0; u < NPT; u++) {
+            const int j = tl.p0 + t + u * NT;
+            if (cc[u] >= 0) prod[j - tl.p0] = Sc<T>::mul(vals_s[j - vb], xv[u]);
+        }
+        __syncthreads();
+
+        if (tl.r1 >= 0) {
+            // ---- 2. row sums
+            const int rows = tl.r1 - tl.r0;
+            const int rb = tl.r0 & ~3;
+            int lpr = 1;
+            while (lpr < 32 && rows * lpr * 2 <= NT) lpr *= 2;
+            const int g = t / lpr, lane = t % lpr, groups = NT / lpr;
+            for (int rr0 = 0; rr0 < rows; rr0 += groups) {
+                const int rr = rr0 + g;
+                const bool valid = rr < rows;
+                T sum = Sc<T>::zero();
+                T xr = Sc<T>::zero();
+                if (valid) {
+                    if (DOT && lane == 0) xr = __ldg(x + tl.r0 + rr);
+                    const int lo = rp_s[tl.r0 + rr - rb] - tl.p0;
+                    const int hi = rp_s[tl.r0 + rr + 1 - rb] - tl.p0;
+                    for (int j = lo + lane; j < hi; j += lpr) sum = Sc<T>::add(sum, prod[j]);
+                }
+                for (int off = lpr >> 1; off > 0; off >>= 1) {
+                    if constexpr (Sc<T>::cplx) {
+                        sum.x += __shfl_xor_sync(0xffffffffu, sum.x, off);
+                        sum.y += __shfl_xor_sync(0xffffffffu, sum.y, off);
+                    } else {
+                        sum += __shfl_xor_sync(0xffffffffu, sum, off);
+                    }
+                }
+                if (valid && lane == 0) {
+                    y[tl.r0 + rr] = sum;
+                    if (DOT) dot[0] = Sc<T>::fma(xr, sum, dot[0]);
+                }
+            }
+        } else {
+            // ---- 2'. chunk of a long row: one sum for the whole tile
+            T part[1] = {Sc<T>::zero()};
+            for (int j = t; j < tl.p1 - tl.p0; j += NT) part[0] = Sc<T>::add(part[0], prod[j]);
+            block_col_reduce<T, 1>(part, 1, red);
+            if (t == 0) {
+                chunk_sum[-(tl.r1 + 1)] = red[0];
+                if (DOT) dot[0] = Sc<T>::fma(__ldg(x + tl.r0), red[0], dot[0]);
+            }
+        }
+        __syncthreads();   // the stage and `prod` are free again
+        if (t == 0 && i + S < count) issue(i + S);
+    }
+
+    if (DOT) {
+        block_col_reduce<T, 1>(dot, 1, red);
+        if (publish_and_arrive<T, 1>(red, 1, 1, sc.partial, sc.ticket + TK_SPMV)) {
+            grid_col_reduce<T, 1>(sc.partial, 1, 1, 1, red);
+            if (t == 0) {
+                sc.dq[0] = red[0];
+                sc.ticket[TK_SPMV] = 0;
+            }
+        }
+    }
+}
+
+// y[row] = sum of the chunk sums of a long row (fixed order).  One thread per long row.
+struct LongRow {
+    int row, slot0, nslots;
+};
+template <typename T>
+__global__ void combine_long_rows_kernel(int nlong, const LongRow *__restrict__ rows,
+                                         const T *__restrict__ chunk_sum, T *__restrict__ y) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nlong) return;
+    const LongRow lr = rows[i];
+    T s = Sc<T>::zero();
+    for (int c = 0; c < lr.nslots; c++) s = Sc<T>::add(s, chunk_sum[lr.slot0 + c]);
+    y[lr.row] = s;
+}
+
+// ---------------------------------------------------------------------------
 // SpMM, k right-hand sides in row-major [n][k]: G lanes per row, lane cp owns the
 // V-wide column pack cp (one 128-bit gather per non-zero per lane when
 // V*sizeof(T) = 16).  kv = k / V <= G; G is a power of two <= 32.
@@ -190,7 +554,7 @@ spmm_kernel(int n, int k, const T *__restrict__ vals, const int *__restrict__ ro
     if (DOT) {
         if (*sc.n_active == 0) return;
     }
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     T *smem = reinterpret_cast<T *>(smem_raw);
     using P = Pack<T, V>;
     const int t = threadIdx.x;
@@ -259,7 +623,7 @@ template <typename T, int V>
 __global__ void __launch_bounds__(256)
 init_kernel(size_t npacks, size_t nelem, int k, int kv, const T *b /* may alias d */,
             const T *__restrict__ q, T *__restrict__ r, T *d, CgScalars<T> sc) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     T *smem = reinterpret_cast<T *>(smem_raw);
     using P = Pack<T, V>;
     const int t = threadIdx.x;
@@ -332,7 +696,7 @@ __global__ void __launch_bounds__(256)
 update_xr_kernel(size_t npacks, size_t nelem, int k, int kv, const T *__restrict__ d,
                  const T *__restrict__ q, T *__restrict__ x, T *__restrict__ r, CgScalars<T> sc) {
     if (*sc.n_active == 0) return;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     T *smem = reinterpret_cast<T *>(smem_raw);
     using P = Pack<T, V>;
     const int t = threadIdx.x;
@@ -452,17 +816,19 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 transpose_kernel(const T *__restrict__ src, T *__restrict__ dst, int rows, long long cols) {
     __shared__ T tile[32][33];
-    const long long c0 = (long long)blockIdx.x * 32;
-    const int r0 = blockIdx.y * 32;
+    // 1-D grid over 32x32 tiles (either dimension may be the long one: [k][n] -> [n][k] and back)
+    const long long tiles_c = (cols + 31) / 32;
+    const long long c0 = ((long long)blockIdx.x % tiles_c) * 32;
+    const long long r0 = ((long long)blockIdx.x / tiles_c) * 32;
     for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-        const int rr = r0 + i;
+        const long long rr = r0 + i;
         const long long cc = c0 + threadIdx.x;
         if (rr < rows && cc < cols) tile[i][threadIdx.x] = src[(size_t)rr * cols + cc];
     }
     __syncthreads();
     for (int i = threadIdx.y; i < 32; i += blockDim.y) {
         const long long cc = c0 + i;
-        const int rr = r0 + threadIdx.x;
+        const long long rr = r0 + threadIdx.x;
         if (rr < rows && cc < cols) dst[(size_t)cc * rows + rr] = tile[threadIdx.x][i];
     }
 }

