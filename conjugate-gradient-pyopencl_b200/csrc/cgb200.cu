@@ -242,7 +242,8 @@ template <typename T> struct Engine {
     // ---- CSR-stream schedule -------------------------------------------------
     static int build_tiles(cgb200_ctx *c, const std::vector<int> &rp) {
         using C = StreamCfg<T>;
-        const int cap = C::CAP, rowcap = C::RMAX;
+        const int cap = std::min<int>(C::CAP, RowTileCfg::CAP), rowcap = std::min<int>(C::RMAX, RowTileCfg::NT);
+        (void)sizeof(C);
         std::vector<SpmvTile> tiles;
         std::vector<LongRow> longs;
         int slots = 0;
@@ -318,6 +319,26 @@ template <typename T> struct Engine {
         }
         return 0;
     }
+    template <int S, bool DOT>
+    static int spmv_tma_rows(cgb200_ctx *c, const T *x, T *y, const CgScalars<T> &sc) {
+        using K = RowTmaCfg<T, S>;
+        auto kern = spmv_tma_rows_kernel<T, S, DOT>;
+        const size_t smem = K::SMEM_BYTES;
+        const void *key = (const void *)kern;
+        if (c->occ.find(key) == c->occ.end())
+            CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int grid = persistent_grid(c, kern, RowTileCfg::NT, smem, c->ntiles);
+        c->spmv_grid_last = grid;
+        kern<<<grid, RowTileCfg::NT, smem, c->stream>>>(c->ntiles, (const SpmvTile *)c->d_tiles, (const T *)c->d_vals,
+                                                        c->d_rowptr, c->d_cols, x, y, (T *)c->d_chunk_sum, sc);
+        c->launches++;
+        if (c->nlong > 0) {
+            combine_long_rows_kernel<T><<<(c->nlong + 127) / 128, 128, 0, c->stream>>>(
+                c->nlong, (const LongRow *)c->d_long, (const T *)c->d_chunk_sum, y);
+            c->launches++;
+        }
+        return 0;
+    }
     template <int V, int G, bool DOT>
     static int launch_spmm(cgb200_ctx *c, int k, const T *x, T *y, const CgScalars<T> &sc) {
         auto kern = spmm_kernel<T, V, G, DOT>;
@@ -348,6 +369,10 @@ template <typename T> struct Engine {
             case 2: return spmv_stream<DOT>(c, x, y, sc);
             case 4: return spmv_tma<3, DOT>(c, x, y, sc);
             case 5: return spmv_tma<4, DOT>(c, x, y, sc);
+            case 6: return spmv_tma_rows<2, DOT>(c, x, y, sc);
+            case 7: return spmv_tma_rows<3, DOT>(c, x, y, sc);
+            case 8: return spmv_tma_rows<4, DOT>(c, x, y, sc);
+            case 9: return spmv_tma_rows<6, DOT>(c, x, y, sc);
             default: return spmv_tma<2, DOT>(c, x, y, sc);      // 0 (auto), 3
             }
         }

@@ -526,6 +526,159 @@ spmv_tma_kernel(int ntiles, const SpmvTile *__restrict__ tiles, const T *__restr
     }
 }
 
+// ---------------------------------------------------------------------------
+// SpMV, one right-hand side, "row-direct" CSR-stream fed by TMA.
+//
+// Like spmv_tma_kernel the tile's values / column indices / row offsets arrive in shared
+// memory by bulk async copies, S tiles ahead.  Unlike it there is no product buffer and
+// no second phase: a tile holds at most RT::NT rows, every row is owned by a group of
+// lpr lanes (1 for short rows, up to 32 when the tile holds few long rows) that walks the
+// row straight out of the staged arrays, gathers x and accumulates in registers.  One
+// block-wide barrier per tile (to recycle the stage), all shared memory spent on stages,
+// i.e. on bytes in flight.
+// ---------------------------------------------------------------------------
+struct RowTileCfg {
+    static constexpr int NT = 128;        // threads per block = max rows per tile
+    static constexpr int TILE = 1024;     // staged non-zeros per tile
+    static constexpr int CAP = TILE - 4;  // non-zeros per tile (aligned windows may start 3 entries early)
+};
+
+template <typename T, int S> struct RowTmaCfg {
+    static constexpr size_t VALS_BYTES = (size_t)RowTileCfg::TILE * sizeof(T);
+    static constexpr size_t COLS_BYTES = (size_t)RowTileCfg::TILE * sizeof(int);
+    static constexpr size_t ROWS_BYTES = (size_t)(RowTileCfg::NT + 8) * sizeof(int);
+    static constexpr size_t STAGE_BYTES = VALS_BYTES + COLS_BYTES + ROWS_BYTES;
+    static constexpr size_t BAR_BYTES = 128;
+    static constexpr size_t RED_BYTES = (size_t)RowTileCfg::NT * sizeof(T);
+    static constexpr size_t SMEM_BYTES = BAR_BYTES + RED_BYTES + S * STAGE_BYTES;
+    static_assert(STAGE_BYTES % 16 == 0 && RED_BYTES % 16 == 0, "16-byte aligned stages");
+};
+
+template <typename T, int S, bool DOT>
+__global__ void __launch_bounds__(RowTileCfg::NT)
+spmv_tma_rows_kernel(int ntiles, const SpmvTile *__restrict__ tiles, const T *__restrict__ vals,
+                     const int *__restrict__ rowptr, const int *__restrict__ cols, const T *__restrict__ x,
+                     T *__restrict__ y, T *__restrict__ chunk_sum, CgScalars<T> sc) {
+    using K = RowTmaCfg<T, S>;
+    constexpr int VPT = VecW<T>::value, NT = RowTileCfg::NT;
+    if (DOT) {
+        if (*sc.n_active == 0) return;
+    }
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem_raw);
+    T *red = reinterpret_cast<T *>(smem_raw + K::BAR_BYTES);
+    unsigned char *stage0 = smem_raw + K::BAR_BYTES + K::RED_BYTES;
+    const int t = threadIdx.x;
+    const int count = ((int)blockIdx.x < ntiles) ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    T dot[1] = {Sc<T>::zero()};
+
+    if (t == 0) {
+        for (int s = 0; s < S; s++) mbar_init(&bars[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    auto issue = [&](const SpmvTile &tl, int i) {   // thread 0: start the copies of this block's i-th tile
+        unsigned char *st = stage0 + (size_t)(i % S) * K::STAGE_BYTES;
+        unsigned long long *bar = &bars[i % S];
+        const int vb = tl.p0 - (tl.p0 % VPT), cb = tl.p0 & ~3;
+        const unsigned vbytes = (unsigned)(((tl.p1 - vb + VPT - 1) / VPT) * VPT * sizeof(T));
+        const unsigned cbytes = (unsigned)(((tl.p1 - cb + 3) / 4) * 16);
+        unsigned rbytes = 0;
+        int rb = 0;
+        if (tl.r1 >= 0) {
+            rb = tl.r0 & ~3;
+            rbytes = (unsigned)(((tl.r1 + 1 - rb + 3) / 4) * 16);
+        }
+        const bool has_nnz = tl.p1 > tl.p0;
+        mbar_arrive_expect_tx(bar, (has_nnz ? vbytes + cbytes : 0u) + rbytes);
+        if (has_nnz) {
+            bulk_g2s(st, vals + vb, vbytes, bar);
+            bulk_g2s(st + K::VALS_BYTES, cols + cb, cbytes, bar);
+        }
+        if (rbytes) bulk_g2s(st + K::VALS_BYTES + K::COLS_BYTES, rowptr + rb, rbytes, bar);
+    };
+    auto tile_of = [&](int i) { return tiles[blockIdx.x + (size_t)i * gridDim.x]; };
+
+    // thread 0 keeps the descriptor of the next tile to issue in a register, fetched one tile early
+    SpmvTile tl_issue = {0, 0, 0, 0};
+    if (t == 0) {
+        for (int i = 0; i < S && i < count; i++) issue(tile_of(i), i);
+        if (S < count) tl_issue = tile_of(S);
+    }
+    SpmvTile tl_next = {0, 0, 0, 0};
+    if (count > 0) tl_next = tile_of(0);
+
+    for (int i = 0; i < count; i++) {
+        const SpmvTile tl = tl_next;
+        if (i + 1 < count) tl_next = tile_of(i + 1);
+        const int s = i % S;
+        const unsigned char *st = stage0 + (size_t)s * K::STAGE_BYTES;
+        const T *vals_s = reinterpret_cast<const T *>(st);
+        const int *cols_s = reinterpret_cast<const int *>(st + K::VALS_BYTES);
+        const int *rp_s = reinterpret_cast<const int *>(st + K::VALS_BYTES + K::COLS_BYTES);
+        const int vb = tl.p0 - (tl.p0 % VPT), cb = tl.p0 & ~3;
+        mbar_wait(&bars[s], (unsigned)((i / S) & 1));
+
+        if (tl.r1 >= 0) {
+            const int rows = tl.r1 - tl.r0;          // <= NT
+            const int rb = tl.r0 & ~3;
+            int lpr = 1;
+            while (lpr < 32 && rows * lpr * 2 <= NT) lpr *= 2;
+            const int rr = t / lpr, lane = t % lpr;
+            const bool valid = rr < rows;
+            T sum = Sc<T>::zero();
+            T xr = Sc<T>::zero();
+            if (valid) {
+                if (DOT && lane == 0) xr = __ldg(x + tl.r0 + rr);
+                const int lo = rp_s[tl.r0 + rr - rb], hi = rp_s[tl.r0 + rr + 1 - rb];
+#pragma unroll 8
+                for (int j = lo + lane; j < hi; j += lpr)
+                    sum = Sc<T>::fma(vals_s[j - vb], __ldg(x + cols_s[j - cb]), sum);
+            }
+            for (int off = lpr >> 1; off > 0; off >>= 1) {
+                if constexpr (Sc<T>::cplx) {
+                    sum.x += __shfl_xor_sync(0xffffffffu, sum.x, off);
+                    sum.y += __shfl_xor_sync(0xffffffffu, sum.y, off);
+                } else {
+                    sum += __shfl_xor_sync(0xffffffffu, sum, off);
+                }
+            }
+            if (valid && lane == 0) {
+                y[tl.r0 + rr] = sum;
+                if (DOT) dot[0] = Sc<T>::fma(xr, sum, dot[0]);
+            }
+        } else {
+            // chunk of a long row: the whole block strides over it, one sum for the tile
+            T part[1] = {Sc<T>::zero()};
+#pragma unroll 4
+            for (int j = tl.p0 + t; j < tl.p1; j += NT)
+                part[0] = Sc<T>::fma(vals_s[j - vb], __ldg(x + cols_s[j - cb]), part[0]);
+            block_col_reduce<T, 1>(part, 1, red);
+            if (t == 0) {
+                chunk_sum[-(tl.r1 + 1)] = red[0];
+                if (DOT) dot[0] = Sc<T>::fma(__ldg(x + tl.r0), red[0], dot[0]);
+            }
+        }
+        __syncthreads();   // every thread is done with stage s
+        if (t == 0 && i + S < count) {
+            issue(tl_issue, i + S);
+            if (i + S + 1 < count) tl_issue = tile_of(i + S + 1);
+        }
+    }
+
+    if (DOT) {
+        block_col_reduce<T, 1>(dot, 1, red);
+        if (publish_and_arrive<T, 1>(red, 1, 1, sc.partial, sc.ticket + TK_SPMV)) {
+            grid_col_reduce<T, 1>(sc.partial, 1, 1, 1, red);
+            if (t == 0) {
+                sc.dq[0] = red[0];
+                sc.ticket[TK_SPMV] = 0;
+            }
+        }
+    }
+}
+
 // y[row] = sum of the chunk sums of a long row (fixed order).  One thread per long row.
 struct LongRow {
     int row, slot0, nslots;

@@ -159,7 +159,7 @@ def test_spmv_stream_schedule_irregular_rows(gpu, cpu_ref, dname):
     n = 6000
     lens = rng.integers(0, 9, n)
     lens[100:140] = 0
-    cap = {"f32": 2044, "f64": 2046, "c64": 2046, "c128": 1023}[dname]
+    cap = 1020               # non-zeros per tile (RowTileCfg::CAP)
     lens[7] = cap            # exactly one tile
     lens[8] = cap + 1        # two chunks
     lens[3000] = 5 * cap + 17
@@ -177,7 +177,7 @@ def test_spmv_stream_schedule_irregular_rows(gpu, cpu_ref, dname):
         assert M.get_option("spmv_variant") == 0
         tol = 2e-5 if dname in ("f32", "c64") else 1e-13
         alpha = np.sum(x.astype(wide) ** 2) / np.sum(x.astype(wide) * exact)     # unconjugated, as vdot.cl:15
-        for variant in (0, 1, 2, 3, 4, 5):
+        for variant in (0, 1, 2, 3, 4, 5, 6, 7, 8, 9):
             M.set_option("spmv_variant", variant)
             y = M.spmv(x)
             assert rel(y, exact) < tol, variant
