@@ -369,11 +369,11 @@ template <typename T> struct Engine {
             case 2: return spmv_stream<DOT>(c, x, y, sc);
             case 4: return spmv_tma<3, DOT>(c, x, y, sc);
             case 5: return spmv_tma<4, DOT>(c, x, y, sc);
-            case 6: return spmv_tma_rows<2, DOT>(c, x, y, sc);
+            case 3: return spmv_tma<2, DOT>(c, x, y, sc);
             case 7: return spmv_tma_rows<3, DOT>(c, x, y, sc);
             case 8: return spmv_tma_rows<4, DOT>(c, x, y, sc);
             case 9: return spmv_tma_rows<6, DOT>(c, x, y, sc);
-            default: return spmv_tma<2, DOT>(c, x, y, sc);      // 0 (auto), 3
+            default: return spmv_tma_rows<2, DOT>(c, x, y, sc); // 0 (auto), 6
             }
         }
         if (pack_width(k) == 1) return spmm_v<1, DOT>(c, k, x, y, sc);

@@ -159,10 +159,19 @@ spmv1_kernel(int n, const T *__restrict__ vals, const int *__restrict__ rowptr,
         T sum = Sc<T>::zero();
         if (row < n) {
             const int lo = __ldg(rowptr + row), hi = __ldg(rowptr + row + 1);
-            for (int j = lo + lane; j < hi; j += LPR) {
-                const T a = ld_stream(vals + j);
-                const int c = ld_stream(cols + j);
-                sum = Sc<T>::fma(a, __ldg(x + c), sum);
+            constexpr int UB = 4;
+            for (int j0 = lo + lane; j0 < hi; j0 += UB * LPR) {
+                T av[UB], xv[UB];
+#pragma unroll
+                for (int u = 0; u < UB; u++) {
+                    const int j = j0 + u * LPR;
+                    const bool ok = j < hi;
+                    const int jj = ok ? j : j0;
+                    xv[u] = __ldg(x + ld_stream(cols + jj));
+                    av[u] = ok ? ld_stream(vals + jj) : Sc<T>::zero();
+                }
+#pragma unroll
+                for (int u = 0; u < UB; u++) sum = Sc<T>::fma(av[u], xv[u], sum);
             }
         }
         // LPR-lane segmented butterfly; all 32 lanes of the warp take part
@@ -359,6 +368,19 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long *bar, u
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// The matrix is read once per SpMV and is (for the large configs) bigger than the 126 MB L2:
+// tag its lines evict-first so that they do not push the CG vectors (x, r, d, q -- re-read by the
+// three kernels of every iteration) out of L2.
+__device__ __forceinline__ unsigned long long l2_evict_first_policy() {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void bulk_g2s_hint(void *dst, const void *src, unsigned bytes, unsigned long long *bar,
+                                              unsigned long long policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(unsigned long long *bar, unsigned parity) {
     unsigned ok;
@@ -561,6 +583,7 @@ spmv_tma_rows_kernel(int ntiles, const SpmvTile *__restrict__ tiles, const T *__
                      T *__restrict__ y, T *__restrict__ chunk_sum, CgScalars<T> sc) {
     using K = RowTmaCfg<T, S>;
     constexpr int VPT = VecW<T>::value, NT = RowTileCfg::NT;
+    constexpr int UB = (sizeof(T) == 16) ? 4 : 8;     // gathers in flight per thread
     if (DOT) {
         if (*sc.n_active == 0) return;
     }
@@ -571,6 +594,7 @@ spmv_tma_rows_kernel(int ntiles, const SpmvTile *__restrict__ tiles, const T *__
     const int t = threadIdx.x;
     const int count = ((int)blockIdx.x < ntiles) ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
     T dot[1] = {Sc<T>::zero()};
+    const unsigned long long stream_policy = l2_evict_first_policy();
 
     if (t == 0) {
         for (int s = 0; s < S; s++) mbar_init(&bars[s], 1);
@@ -593,10 +617,10 @@ spmv_tma_rows_kernel(int ntiles, const SpmvTile *__restrict__ tiles, const T *__
         const bool has_nnz = tl.p1 > tl.p0;
         mbar_arrive_expect_tx(bar, (has_nnz ? vbytes + cbytes : 0u) + rbytes);
         if (has_nnz) {
-            bulk_g2s(st, vals + vb, vbytes, bar);
-            bulk_g2s(st + K::VALS_BYTES, cols + cb, cbytes, bar);
+            bulk_g2s_hint(st, vals + vb, vbytes, bar, stream_policy);
+            bulk_g2s_hint(st + K::VALS_BYTES, cols + cb, cbytes, bar, stream_policy);
         }
-        if (rbytes) bulk_g2s(st + K::VALS_BYTES + K::COLS_BYTES, rowptr + rb, rbytes, bar);
+        if (rbytes) bulk_g2s_hint(st + K::VALS_BYTES + K::COLS_BYTES, rowptr + rb, rbytes, bar, stream_policy);
     };
     auto tile_of = [&](int i) { return tiles[blockIdx.x + (size_t)i * gridDim.x]; };
 
@@ -632,9 +656,22 @@ spmv_tma_rows_kernel(int ntiles, const SpmvTile *__restrict__ tiles, const T *__
             if (valid) {
                 if (DOT && lane == 0) xr = __ldg(x + tl.r0 + rr);
                 const int lo = rp_s[tl.r0 + rr - rb], hi = rp_s[tl.r0 + rr + 1 - rb];
-#pragma unroll 8
-                for (int j = lo + lane; j < hi; j += lpr)
-                    sum = Sc<T>::fma(vals_s[j - vb], __ldg(x + cols_s[j - cb]), sum);
+                // Batches of UB non-zeros with every load issued before the first FMA: a warp issues in
+                // order, so a plain loop would serialise one L2 round trip per non-zero.  Lanes past the
+                // end of the row re-read the batch's first entry (a valid address) with a zero coefficient.
+                for (int j0 = lo + lane; j0 < hi; j0 += UB * lpr) {
+                    T av[UB], xv[UB];
+#pragma unroll
+                    for (int u = 0; u < UB; u++) {
+                        const int j = j0 + u * lpr;
+                        const bool ok = j < hi;
+                        const int jj = ok ? j : j0;
+                        xv[u] = __ldg(x + cols_s[jj - cb]);
+                        av[u] = ok ? vals_s[jj - vb] : Sc<T>::zero();
+                    }
+#pragma unroll
+                    for (int u = 0; u < UB; u++) sum = Sc<T>::fma(av[u], xv[u], sum);
+                }
             }
             for (int off = lpr >> 1; off > 0; off >>= 1) {
                 if constexpr (Sc<T>::cplx) {
@@ -651,9 +688,19 @@ spmv_tma_rows_kernel(int ntiles, const SpmvTile *__restrict__ tiles, const T *__
         } else {
             // chunk of a long row: the whole block strides over it, one sum for the tile
             T part[1] = {Sc<T>::zero()};
-#pragma unroll 4
-            for (int j = tl.p0 + t; j < tl.p1; j += NT)
-                part[0] = Sc<T>::fma(vals_s[j - vb], __ldg(x + cols_s[j - cb]), part[0]);
+            for (int j0 = tl.p0 + t; j0 < tl.p1; j0 += UB * NT) {
+                T av[UB], xv[UB];
+#pragma unroll
+                for (int u = 0; u < UB; u++) {
+                    const int j = j0 + u * NT;
+                    const bool ok = j < tl.p1;
+                    const int jj = ok ? j : j0;
+                    xv[u] = __ldg(x + cols_s[jj - cb]);
+                    av[u] = ok ? vals_s[jj - vb] : Sc<T>::zero();
+                }
+#pragma unroll
+                for (int u = 0; u < UB; u++) part[0] = Sc<T>::fma(av[u], xv[u], part[0]);
+            }
             block_col_reduce<T, 1>(part, 1, red);
             if (t == 0) {
                 chunk_sum[-(tl.r1 + 1)] = red[0];
@@ -727,13 +774,25 @@ spmm_kernel(int n, int k, const T *__restrict__ vals, const int *__restrict__ ro
             T acc[V];
 #pragma unroll
             for (int v = 0; v < V; v++) acc[v] = Sc<T>::zero();
-#pragma unroll 4
-            for (int j = lo; j < hi; j++) {
-                const T a = __ldg(vals + j);   // one address for the G lanes of the row: a broadcast
-                const int c = __ldg(cols + j);
-                const P xv = *reinterpret_cast<const P *>(x + (size_t)c * k + (size_t)cp * V);
+            constexpr int UB = 4;
+            for (int j0 = lo; j0 < hi; j0 += UB) {
+                // all UB gathers are issued before the first FMA (in-order issue would otherwise
+                // serialise one round trip per non-zero); entries past the row end get a zero coefficient
+                T av[UB];
+                P xv[UB];
 #pragma unroll
-                for (int v = 0; v < V; v++) acc[v] = Sc<T>::fma(a, xv.v[v], acc[v]);
+                for (int u = 0; u < UB; u++) {
+                    const bool ok = j0 + u < hi;
+                    const int jj = ok ? j0 + u : j0;
+                    const int c = __ldg(cols + jj);   // one address for the G lanes of the row: a broadcast
+                    xv[u] = *reinterpret_cast<const P *>(x + (size_t)c * k + (size_t)cp * V);
+                    av[u] = ok ? __ldg(vals + jj) : Sc<T>::zero();
+                }
+#pragma unroll
+                for (int u = 0; u < UB; u++) {
+#pragma unroll
+                    for (int v = 0; v < V; v++) acc[v] = Sc<T>::fma(av[u], xv[u].v[v], acc[v]);
+                }
             }
             P out;
 #pragma unroll

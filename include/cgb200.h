@@ -67,7 +67,7 @@ CGB200_API int cgb200_set_stream(cgb200_handle h, void *cuda_stream);
 
 /* Tuning knobs (the reference's are compile-time macros, clcg.c:37-43).
  *   "spmv_variant"   [k = 1 only]
- *                    0 auto (= 3)
+ *                    0 auto (= 6)
  *                    1 CSR-vector: lanes_per_row lanes per row
  *                    2 CSR-stream: tiles of non-zeros, products staged in shared memory, plain loads
  *                    3/4/5 CSR-stream fed by TMA bulk copies through a 2/3/4-stage mbarrier ring
