@@ -305,35 +305,43 @@ def main():
     # ---- e2e through the exported cg / cgd symbol, pinned host buffers, matrix re-uploaded each step
     e2e = None
     if not args.no_e2e:
-        os.environ["CGB200_CACHE"] = "0"
         os.environ["CGB200_DEVICE"] = str(local_rank)
         pin = lambda a: torch.from_numpy(a).pin_memory().numpy()
         vals_h, ptr_h, cols_h = pin(A.data), pin(A.indptr.astype(np.intc)), pin(A.indices.astype(np.intc))
         b_h, x_h = pin(B), pin(np.zeros_like(B))
+
         def e2e_step():
             x_h[...] = 0
             t0 = time.perf_counter()
             cg_b200.cg(n, nnz, vals_h, b_h, ptr_h, cols_h, x_h, k, ITERS_PER_STEP)
             return time.perf_counter() - t0
-        for _ in range(2):
-            e2e_step()
-        barrier()
-        tt = sum(e2e_step() for _ in range(args.steps))
-        t = torch.tensor([tt], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        tt = float(t.item())
+
+        def e2e_run(mode):
+            os.environ["CGB200_CACHE"] = mode
+            for _ in range(2):
+                e2e_step()
+            barrier()
+            tt = sum(e2e_step() for _ in range(args.steps))
+            t = torch.tensor([tt], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+
         h2d = nnz * (v_bytes + 4) + 4 * (n + 1) + 2 * k * n * v_bytes
+        tt = e2e_run("2")
         e2e = {"value": world * k * ITERS_PER_STEP * args.steps / tt, "unit": "iterations/s",
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(k * n * v_bytes),
                "ms_per_step": 1e3 * tt / args.steps,
-               "how": "cg()/cgd() C symbol on pinned host numpy arrays; CSR matrix, b, x0 uploaded and x read back "
-                      "inside every timed call (CGB200_CACHE=0); wall clock around the blocking call"}
+               "how": "cg()/cgd() C symbol on pinned host numpy arrays; the CSR matrix, b and x0 are uploaded and x is "
+                      "read back inside every timed call (CGB200_CACHE=2: device buffers are reused, content is "
+                      "not); wall clock around the blocking call"}
+        # the reference's own life cycle: allocate, upload, solve, free on every call (clcg.c:142-214, :432-459)
+        tt0 = e2e_run("0")
+        e2e["alloc_every_call_value"] = world * k * ITERS_PER_STEP * args.steps / tt0
         # the as_prec pattern: same matrix on every call -> resident copy reused (content hash), only b/x move
-        os.environ["CGB200_CACHE"] = "1"
-        e2e_step()
-        tt2 = sum(e2e_step() for _ in range(args.steps))
-        e2e["resident_matrix_value"] = world * k * ITERS_PER_STEP * args.steps / tt2
+        tt1 = e2e_run("1")
+        e2e["resident_matrix_value"] = world * k * ITERS_PER_STEP * args.steps / tt1
+        e2e["resident_matrix_h2d_bytes_per_step"] = int(2 * k * n * v_bytes)
         cg_b200._lib.lib().cgb200_clear_cache()
 
     if rank == 0:

@@ -26,6 +26,7 @@ SIGNATURES = {
     "cg": (_vp, [_i, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i]),
     "cgd": (_vp, [_i, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i]),
     "cgb200_create": (_i, [ctypes.POINTER(_vp), _i, _ll, _vp, _vp, _vp, _i, _i]),
+    "cgb200_update": (_i, [_vp, _vp, _vp, _vp]),
     "cgb200_destroy": (_i, [_vp]),
     "cgb200_set_stream": (_i, [_vp, _vp]),
     "cgb200_set_option": (_i, [_vp, ctypes.c_char_p, _ll]),

@@ -72,6 +72,7 @@ struct cgb200_ctx {
     // CSR-stream schedule (k = 1): tiles of whole rows / chunks of long rows
     void *d_tiles = nullptr, *d_long = nullptr, *d_chunk_sum = nullptr;
     int ntiles = 0, nlong = 0, nslots = 0;
+    uint64_t rowptr_hash = 0;
     // options
     int opt_lpr = 0, graph_chunk = 16, use_graph = 1, blocks_per_sm = 0, spmv_variant = 0;
     // workspace (for ws_k right-hand sides)
@@ -702,6 +703,80 @@ template <typename T> struct Engine {
         return fail(CGB200_ERR_ARG, "bad dtype %d", (c)->dtype);             \
     }()
 
+static uint64_t hash_span(const unsigned char *p, size_t bytes, uint64_t seed) {
+    uint64_t h[4] = {seed ^ 0x9E3779B97F4A7C15ull, seed ^ 0xC2B2AE3D27D4EB4Full, seed ^ 0x165667B19E3779F9ull,
+                     seed ^ 0x27D4EB2F165667C5ull};
+    size_t i = 0;
+    for (; i + 32 <= bytes; i += 32) {
+        uint64_t w[4];
+        memcpy(w, p + i, 32);
+        for (int l = 0; l < 4; l++) {
+            h[l] = (h[l] ^ w[l]) * 0x100000001B3ull;
+            h[l] = (h[l] << 27) | (h[l] >> 37);
+        }
+    }
+    uint64_t tail = 0;
+    for (; i < bytes; i++) tail = tail * 131 + p[i];
+    uint64_t r = h[0];
+    for (int l = 1; l < 4; l++) r = (r ^ h[l]) * 0x9E3779B97F4A7C15ull + (r >> 29);
+    return (r ^ tail) * 0xD6E8FEB86659FD93ull;
+}
+
+static uint64_t hash_bytes(const void *ptr, size_t bytes, uint64_t seed) {
+    const unsigned char *p = (const unsigned char *)ptr;
+    const size_t min_chunk = 4u << 20;
+    int nt = (int)std::min<size_t>(8, bytes / min_chunk);
+    if (nt <= 1) return hash_span(p, bytes, seed);
+    std::vector<uint64_t> parts(nt);
+    std::vector<std::thread> th;
+    const size_t chunk = ((bytes / nt) + 31) & ~(size_t)31;
+    for (int i = 0; i < nt; i++) {
+        const size_t lo = std::min(bytes, (size_t)i * chunk), hi = (i == nt - 1) ? bytes : std::min(bytes, lo + chunk);
+        th.emplace_back([&, i, lo, hi] { parts[i] = hash_span(p + lo, hi - lo, seed + i); });
+    }
+    for (auto &t : th) t.join();
+    uint64_t r = seed;
+    for (int i = 0; i < nt; i++) r = (r ^ parts[i]) * 0x9E3779B97F4A7C15ull + (r >> 31);
+    return r;
+}
+
+
+// Copies the CSR arrays (host or device pointers) into the handle's buffers and (re)builds the
+// SpMV schedule when the sparsity pattern's row offsets changed.
+static int upload_matrix(cgb200_ctx *c, const void *aValues, const int *aPointers, const int *aCols) {
+    const int n = c->n;
+    const long long nnz = c->nnz;
+    const size_t vs = c->vsize;
+    CU(cudaMemcpyAsync(c->d_vals, aValues, (size_t)nnz * vs, cudaMemcpyDefault, c->stream));
+    CU(cudaMemcpyAsync(c->d_cols, aCols, (size_t)nnz * sizeof(int), cudaMemcpyDefault, c->stream));
+    CU(cudaMemcpyAsync(c->d_rowptr, aPointers, ((size_t)n + 1) * sizeof(int), cudaMemcpyDefault, c->stream));
+    // row-length statistics choose the SpMV schedule
+    std::vector<int> rp((size_t)n + 1);
+    CU(cudaMemcpyAsync(rp.data(), c->d_rowptr, ((size_t)n + 1) * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    const uint64_t rh = hash_bytes(rp.data(), rp.size() * sizeof(int), 7);
+    if (c->d_tiles && rh == c->rowptr_hash) return 0;       // same pattern: the tiles stand
+    if (rp[0] != 0 || rp[n] != (int)nnz)
+        return fail(CGB200_ERR_ARG, "aPointers[0]=%d aPointers[n]=%d but nnz=%lld", rp[0], rp[n], nnz);
+    int mx = 0;
+    for (int i = 0; i < n; i++) {
+        const int len = rp[i + 1] - rp[i];
+        if (len < 0) return fail(CGB200_ERR_ARG, "aPointers not monotone at row %d", i);
+        mx = std::max(mx, len);
+    }
+    c->max_row = mx;
+    c->mean_row = (double)nnz / n;
+    drop_graph(c);
+    void **old[] = {&c->d_tiles, &c->d_long, &c->d_chunk_sum};
+    for (void **b : old) {
+        if (*b) cudaFree(*b);
+        *b = nullptr;
+    }
+    TRY(DISPATCH(c, E::build_tiles(c, rp)));
+    c->rowptr_hash = rh;
+    return 0;
+}
+
 struct DeviceGuard {
     int prev = -1;
     explicit DeviceGuard(int dev) {
@@ -775,26 +850,10 @@ int cgb200_create(cgb200_handle *out, int n, long long nnz, const void *aValues,
     CUB(cudaMalloc(&c->d_rowptr, ((size_t)n + 1 + 16) * sizeof(int)));
     CUB(cudaMemsetAsync((char *)c->d_vals + (size_t)nnz * vs, 0, 16 * vs, c->stream));
     CUB(cudaMemsetAsync(c->d_cols + nnz, 0, 16 * sizeof(int), c->stream));
-    CUB(cudaMemcpyAsync(c->d_vals, aValues, (size_t)nnz * vs, cudaMemcpyDefault, c->stream));
-    CUB(cudaMemcpyAsync(c->d_cols, aCols, (size_t)nnz * sizeof(int), cudaMemcpyDefault, c->stream));
-    CUB(cudaMemcpyAsync(c->d_rowptr, aPointers, ((size_t)n + 1) * sizeof(int), cudaMemcpyDefault, c->stream));
-    // row-length statistics choose the SpMV schedule
-    std::vector<int> rp((size_t)n + 1);
-    CUB(cudaMemcpyAsync(rp.data(), c->d_rowptr, ((size_t)n + 1) * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CUB(cudaStreamSynchronize(c->stream));
 #undef CUB
-    if (rp[0] != 0 || rp[n] != (int)nnz)
-        return bail(fail(CGB200_ERR_ARG, "aPointers[0]=%d aPointers[n]=%d but nnz=%lld", rp[0], rp[n], nnz));
-    int mx = 0;
-    for (int i = 0; i < n; i++) {
-        const int len = rp[i + 1] - rp[i];
-        if (len < 0) return bail(fail(CGB200_ERR_ARG, "aPointers not monotone at row %d", i));
-        mx = std::max(mx, len);
-    }
-    c->max_row = mx;
-    c->mean_row = (double)nnz / n;
     {
-        int rc = DISPATCH(c, E::build_tiles(c, rp));
+        const int rc = upload_matrix(c, aValues, aPointers, aCols);
         if (rc < 0) return bail(rc);
     }
     if (const char *e = getenv("CGB200_LANES_PER_ROW")) c->opt_lpr = atoi(e);
@@ -804,6 +863,12 @@ int cgb200_create(cgb200_handle *out, int n, long long nnz, const void *aValues,
     if (const char *e = getenv("CGB200_SPMV_VARIANT")) c->spmv_variant = atoi(e);
     *out = c;
     return CGB200_OK;
+}
+
+int cgb200_update(cgb200_handle c, const void *aValues, const int *aPointers, const int *aCols) {
+    if (!c || !aValues || !aPointers || !aCols) return fail(CGB200_ERR_ARG, "NULL argument");
+    DeviceGuard guard(c->device);
+    return upload_matrix(c, aValues, aPointers, aCols);
 }
 
 int cgb200_destroy(cgb200_handle c) {
@@ -935,43 +1000,6 @@ struct CacheSlot {
 };
 static CacheSlot g_cache[64];
 
-static uint64_t hash_span(const unsigned char *p, size_t bytes, uint64_t seed) {
-    uint64_t h[4] = {seed ^ 0x9E3779B97F4A7C15ull, seed ^ 0xC2B2AE3D27D4EB4Full, seed ^ 0x165667B19E3779F9ull,
-                     seed ^ 0x27D4EB2F165667C5ull};
-    size_t i = 0;
-    for (; i + 32 <= bytes; i += 32) {
-        uint64_t w[4];
-        memcpy(w, p + i, 32);
-        for (int l = 0; l < 4; l++) {
-            h[l] = (h[l] ^ w[l]) * 0x100000001B3ull;
-            h[l] = (h[l] << 27) | (h[l] >> 37);
-        }
-    }
-    uint64_t tail = 0;
-    for (; i < bytes; i++) tail = tail * 131 + p[i];
-    uint64_t r = h[0];
-    for (int l = 1; l < 4; l++) r = (r ^ h[l]) * 0x9E3779B97F4A7C15ull + (r >> 29);
-    return (r ^ tail) * 0xD6E8FEB86659FD93ull;
-}
-
-static uint64_t hash_bytes(const void *ptr, size_t bytes, uint64_t seed) {
-    const unsigned char *p = (const unsigned char *)ptr;
-    const size_t min_chunk = 4u << 20;
-    int nt = (int)std::min<size_t>(8, bytes / min_chunk);
-    if (nt <= 1) return hash_span(p, bytes, seed);
-    std::vector<uint64_t> parts(nt);
-    std::vector<std::thread> th;
-    const size_t chunk = ((bytes / nt) + 31) & ~(size_t)31;
-    for (int i = 0; i < nt; i++) {
-        const size_t lo = std::min(bytes, (size_t)i * chunk), hi = (i == nt - 1) ? bytes : std::min(bytes, lo + chunk);
-        th.emplace_back([&, i, lo, hi] { parts[i] = hash_span(p + lo, hi - lo, seed + i); });
-    }
-    for (auto &t : th) t.join();
-    uint64_t r = seed;
-    for (int i = 0; i < nt; i++) r = (r ^ parts[i]) * 0x9E3779B97F4A7C15ull + (r >> 31);
-    return r;
-}
-
 static int legacy_device() {
     if (const char *e = getenv("CGB200_DEVICE")) return atoi(e);
     int d = 0;
@@ -988,9 +1016,12 @@ static int legacy_cg(int dev, int dtype, int size, int nonZeros, const void *aVa
         return fail(CGB200_ERR_ARG, "bad cg() arguments");
     if (dev < 0) dev = legacy_device();
     if (dev < 0 || dev >= 64) return fail(CGB200_ERR_ARG, "device %d", dev);
+    // CGB200_CACHE: 0 nothing is kept between calls (the reference's behaviour, clcg.c:142-214 / :432-459)
+    //               1 (default) the device copy of the last matrix is reused when the content is the same
+    //               2 buffers are kept but the matrix is uploaded on every call
     const char *ce = getenv("CGB200_CACHE");
-    const bool use_cache = !(ce && atoi(ce) == 0);
-    if (!use_cache) {
+    const int mode = ce ? atoi(ce) : 1;
+    if (mode == 0) {
         cgb200_handle h = nullptr;
         TRY(cgb200_create(&h, size, nonZeros, aValues, aPointers, aCols, dtype, dev));
         int rc = cgb200_solve(h, b, x, nRHS, nIterations, 0.0, nullptr, nullptr, nullptr, CGB200_LAYOUT_CLCG);
@@ -1000,18 +1031,30 @@ static int legacy_cg(int dev, int dtype, int size, int nonZeros, const void *aVa
     CacheSlot &s = g_cache[dev];
     std::lock_guard<std::mutex> lock(s.mu);
     const size_t vs = dtype_size(dtype);
-    uint64_t hsh = hash_bytes(aValues, (size_t)nonZeros * vs, 1);
-    hsh = hash_bytes(aCols, (size_t)nonZeros * sizeof(int), hsh);
-    hsh = hash_bytes(aPointers, ((size_t)size + 1) * sizeof(int), hsh);
-    if (!(s.h && s.n == size && s.nnz == nonZeros && s.dtype == dtype && s.hash == hsh)) {
+    uint64_t hsh = 0;
+    if (mode == 1) {
+        hsh = hash_bytes(aValues, (size_t)nonZeros * vs, 1);
+        hsh = hash_bytes(aCols, (size_t)nonZeros * sizeof(int), hsh);
+        hsh = hash_bytes(aPointers, ((size_t)size + 1) * sizeof(int), hsh);
+    }
+    const bool same_shape = s.h && s.n == size && s.nnz == nonZeros && s.dtype == dtype;
+    if (!same_shape) {
         if (s.h) cgb200_destroy(s.h);
         s.h = nullptr;
         TRY(cgb200_create(&s.h, size, nonZeros, aValues, aPointers, aCols, dtype, dev));
         s.n = size;
         s.nnz = nonZeros;
         s.dtype = dtype;
-        s.hash = hsh;
+    } else if (mode != 1 || s.hash != hsh) {
+        // same sizes, new content: refill the resident buffers, no allocation
+        const int rc = cgb200_update(s.h, aValues, aPointers, aCols);
+        if (rc < 0) {
+            cgb200_destroy(s.h);
+            s.h = nullptr;
+            return rc;
+        }
     }
+    s.hash = hsh;
     return cgb200_solve(s.h, b, x, nRHS, nIterations, 0.0, nullptr, nullptr, nullptr, CGB200_LAYOUT_CLCG);
 }
 

@@ -159,19 +159,11 @@ spmv1_kernel(int n, const T *__restrict__ vals, const int *__restrict__ rowptr,
         T sum = Sc<T>::zero();
         if (row < n) {
             const int lo = __ldg(rowptr + row), hi = __ldg(rowptr + row + 1);
-            constexpr int UB = 4;
-            for (int j0 = lo + lane; j0 < hi; j0 += UB * LPR) {
-                T av[UB], xv[UB];
-#pragma unroll
-                for (int u = 0; u < UB; u++) {
-                    const int j = j0 + u * LPR;
-                    const bool ok = j < hi;
-                    const int jj = ok ? j : j0;
-                    xv[u] = __ldg(x + ld_stream(cols + jj));
-                    av[u] = ok ? ld_stream(vals + jj) : Sc<T>::zero();
-                }
-#pragma unroll
-                for (int u = 0; u < UB; u++) sum = Sc<T>::fma(av[u], xv[u], sum);
+#pragma unroll 2
+            for (int j = lo + lane; j < hi; j += LPR) {
+                const T a = ld_stream(vals + j);
+                const int c = ld_stream(cols + j);
+                sum = Sc<T>::fma(a, __ldg(x + c), sum);
             }
         }
         // LPR-lane segmented butterfly; all 32 lanes of the warp take part
@@ -583,7 +575,7 @@ spmv_tma_rows_kernel(int ntiles, const SpmvTile *__restrict__ tiles, const T *__
                      T *__restrict__ y, T *__restrict__ chunk_sum, CgScalars<T> sc) {
     using K = RowTmaCfg<T, S>;
     constexpr int VPT = VecW<T>::value, NT = RowTileCfg::NT;
-    constexpr int UB = (sizeof(T) == 16) ? 4 : 8;     // gathers in flight per thread
+    constexpr int UB = 8;                             // gathers in flight per thread
     if (DOT) {
         if (*sc.n_active == 0) return;
     }
@@ -766,10 +758,16 @@ spmm_kernel(int n, int k, const T *__restrict__ vals, const int *__restrict__ ro
 #pragma unroll
     for (int v = 0; v < V; v++) dot[v] = Sc<T>::zero();
 
-    for (long long row0 = (long long)blockIdx.x * rows_per_block; row0 < n;
-         row0 += (long long)gridDim.x * rows_per_block) {
+    // Each block owns one contiguous range of rows and walks it front to back, so that for banded
+    // matrices (stencils) the x rows touched by neighbouring matrix rows are still in this SM's L1
+    // when the next rows need them; a grid-stride walk would send every reuse to L2.
+    const long long per_block = (((long long)n + gridDim.x - 1) / gridDim.x + rows_per_block - 1) /
+                                rows_per_block * rows_per_block;
+    const long long row_begin = (long long)blockIdx.x * per_block;
+    const long long row_end = row_begin + per_block < n ? row_begin + per_block : n;
+    for (long long row0 = row_begin; row0 < row_end; row0 += rows_per_block) {
         const int row = (int)row0 + t / G;
-        if (row < n && active) {
+        if (row < row_end && active) {
             const int lo = __ldg(rowptr + row), hi = __ldg(rowptr + row + 1);
             T acc[V];
 #pragma unroll

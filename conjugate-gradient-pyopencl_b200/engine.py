@@ -79,6 +79,15 @@ class Matrix:
         vals = A.data if dtype is None else A.data.astype(dtype)
         return cls(vals, A.indptr, A.indices, n=A.shape[0], device=device)
 
+    def update(self, values, rowptr, cols):
+        """New content with the same n / nnz / dtype (`cgb200_update`): no reallocation."""
+        values = np.ascontiguousarray(values, dtype=self.dtype)
+        rowptr = np.ascontiguousarray(rowptr, dtype=np.intc)
+        cols = np.ascontiguousarray(cols, dtype=np.intc)
+        if values.size != self.nnz or rowptr.size != self.n + 1 or cols.size != self.nnz:
+            raise ValueError("update() needs arrays of the sizes the matrix was created with")
+        check(lib().cgb200_update(self._h, ptr(values), ptr(rowptr), ptr(cols)))
+
     def close(self):
         if getattr(self, "_h", None):
             lib().cgb200_destroy(self._h)

@@ -58,6 +58,11 @@ typedef struct cgb200_ctx *cgb200_handle;
 CGB200_API int cgb200_create(cgb200_handle *out, int n, long long nnz, const void *aValues,
                   const int *aPointers, const int *aCols, int dtype, int device);
 
+/* New matrix content of the SAME sizes (n, nnz, dtype) into the resident buffers: the
+ * uploads of clcg.c:202-207 without the allocations.  The SpMV schedule is rebuilt only
+ * when the row offsets changed. */
+CGB200_API int cgb200_update(cgb200_handle h, const void *aValues, const int *aPointers, const int *aCols);
+
 /* clcg.c:432-459 (release everything). */
 CGB200_API int cgb200_destroy(cgb200_handle h);
 

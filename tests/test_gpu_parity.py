@@ -407,6 +407,38 @@ def test_legacy_cg_symbol_with_reference_argtypes(gpu, cpu_ref):
     assert rel(x3, x) > 1e-2
 
 
+def test_update_in_place_and_cache_modes(gpu, cpu_ref, monkeypatch):
+    """cgb200_update: new values / new pattern of the same sizes without reallocation; CGB200_CACHE modes."""
+    A, b = system("poisson", 40, np.float64)
+    n = A.shape[0]
+    ref, _, _ = cpu_ref.cg(A.data, A.indptr, A.indices, b, iters=30)
+    A2 = A.copy()
+    A2.data = A2.data * 1.25
+    ref2, _, _ = cpu_ref.cg(A2.data, A2.indptr, A2.indices, b, iters=30)
+    # same nnz, different pattern: reverse the node numbering
+    perm = np.arange(n)[::-1]
+    A3 = A[perm][:, perm].tocsr()
+    A3.sort_indices()
+    assert A3.nnz == A.nnz and not np.array_equal(A3.indptr, A.indptr) or not np.array_equal(A3.indices, A.indices)
+    ref3, _, _ = cpu_ref.cg(A3.data, A3.indptr, A3.indices, b, iters=30)
+    with gpu.Matrix.from_scipy(A) as M:
+        x, _ = M.solve(b, max_iterations=30)
+        assert rel(x, ref) < 1e-10
+        M.update(A2.data, A2.indptr, A2.indices)
+        x, _ = M.solve(b, max_iterations=30)
+        assert rel(x, ref2) < 1e-10
+        M.update(A3.data, A3.indptr, A3.indices)
+        x, _ = M.solve(b, max_iterations=30)
+        assert rel(x, ref3) < 1e-10
+    for mode in ("0", "1", "2"):
+        monkeypatch.setenv("CGB200_CACHE", mode)
+        for Ax, rx in ((A, ref), (A2, ref2), (A, ref), (A3, ref3)):
+            x = np.zeros(n)
+            gpu.cg(n, Ax.nnz, Ax.data, b, Ax.indptr, Ax.indices, x, 1, 30)
+            assert rel(x, rx) < 1e-10, mode
+    gpu._lib.lib().cgb200_clear_cache()
+
+
 @pytest.mark.parametrize("dname", ["f32", "f64", "c64", "c128"])
 def test_cg_and_cgd_wrappers(gpu, cpu_ref, dname):
     dt = DT[dname]
