@@ -758,39 +758,23 @@ spmm_kernel(int n, int k, const T *__restrict__ vals, const int *__restrict__ ro
 #pragma unroll
     for (int v = 0; v < V; v++) dot[v] = Sc<T>::zero();
 
-    // Each block owns one contiguous range of rows and walks it front to back, so that for banded
-    // matrices (stencils) the x rows touched by neighbouring matrix rows are still in this SM's L1
-    // when the next rows need them; a grid-stride walk would send every reuse to L2.
-    const long long per_block = (((long long)n + gridDim.x - 1) / gridDim.x + rows_per_block - 1) /
-                                rows_per_block * rows_per_block;
-    const long long row_begin = (long long)blockIdx.x * per_block;
-    const long long row_end = row_begin + per_block < n ? row_begin + per_block : n;
-    for (long long row0 = row_begin; row0 < row_end; row0 += rows_per_block) {
+    for (long long row0 = (long long)blockIdx.x * rows_per_block; row0 < n;
+         row0 += (long long)gridDim.x * rows_per_block) {
         const int row = (int)row0 + t / G;
-        if (row < row_end && active) {
+        if (row < n && active) {
             const int lo = __ldg(rowptr + row), hi = __ldg(rowptr + row + 1);
             T acc[V];
 #pragma unroll
             for (int v = 0; v < V; v++) acc[v] = Sc<T>::zero();
-            constexpr int UB = 4;
-            for (int j0 = lo; j0 < hi; j0 += UB) {
-                // all UB gathers are issued before the first FMA (in-order issue would otherwise
-                // serialise one round trip per non-zero); entries past the row end get a zero coefficient
-                T av[UB];
-                P xv[UB];
+            // (a contiguous row range per block, or batching the gathers ahead of the FMAs, both measured
+            //  slower here: with k-wide rows of x the kernel is bound by L2 -> SM traffic)
+#pragma unroll 4
+            for (int j = lo; j < hi; j++) {
+                const T a = __ldg(vals + j);   // one address for the G lanes of the row: a broadcast
+                const int c = __ldg(cols + j);
+                const P xv = *reinterpret_cast<const P *>(x + (size_t)c * k + (size_t)cp * V);
 #pragma unroll
-                for (int u = 0; u < UB; u++) {
-                    const bool ok = j0 + u < hi;
-                    const int jj = ok ? j0 + u : j0;
-                    const int c = __ldg(cols + jj);   // one address for the G lanes of the row: a broadcast
-                    xv[u] = *reinterpret_cast<const P *>(x + (size_t)c * k + (size_t)cp * V);
-                    av[u] = ok ? __ldg(vals + jj) : Sc<T>::zero();
-                }
-#pragma unroll
-                for (int u = 0; u < UB; u++) {
-#pragma unroll
-                    for (int v = 0; v < V; v++) acc[v] = Sc<T>::fma(av[u], xv[u].v[v], acc[v]);
-                }
+                for (int v = 0; v < V; v++) acc[v] = Sc<T>::fma(a, xv.v[v], acc[v]);
             }
             P out;
 #pragma unroll

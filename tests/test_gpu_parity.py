@@ -415,11 +415,11 @@ def test_update_in_place_and_cache_modes(gpu, cpu_ref, monkeypatch):
     A2 = A.copy()
     A2.data = A2.data * 1.25
     ref2, _, _ = cpu_ref.cg(A2.data, A2.indptr, A2.indices, b, iters=30)
-    # same nnz, different pattern: reverse the node numbering
-    perm = np.arange(n)[::-1]
+    # same nnz, different pattern: a random symmetric renumbering
+    perm = np.random.default_rng(0).permutation(n)
     A3 = A[perm][:, perm].tocsr()
     A3.sort_indices()
-    assert A3.nnz == A.nnz and not np.array_equal(A3.indptr, A.indptr) or not np.array_equal(A3.indices, A.indices)
+    assert A3.nnz == A.nnz and not np.array_equal(A3.indices, A.indices)
     ref3, _, _ = cpu_ref.cg(A3.data, A3.indptr, A3.indices, b, iters=30)
     with gpu.Matrix.from_scipy(A) as M:
         x, _ = M.solve(b, max_iterations=30)
