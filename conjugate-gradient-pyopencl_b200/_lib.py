@@ -38,6 +38,14 @@ SIGNATURES = {
     "cgb200_info": (_i, [_vp, ctypes.POINTER(_ll)]),
     "cgb200_cg": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _i]),
     "cgb200_clear_cache": (_i, []),
+    "cgb200_nccl_unique_id": (_i, [_vp]),
+    "cgb200_shard_create": (_i, [ctypes.POINTER(_vp), _i, _i, _vp, _i, _i, _i, _ll, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
+    "cgb200_shard_destroy": (_i, [_vp]),
+    "cgb200_shard_set_stream": (_i, [_vp, _vp]),
+    "cgb200_shard_set_option": (_i, [_vp, ctypes.c_char_p, _ll]),
+    "cgb200_shard_solve": (_i, [_vp, _vp, _vp, _i, _d, ctypes.POINTER(_i), ctypes.POINTER(_d)]),
+    "cgb200_shard_info": (_i, [_vp, ctypes.POINTER(_ll)]),
+    "cgb200_shard_last_timing": (_i, [_vp, ctypes.POINTER(_d)]),
     "cgb200_last_error": (ctypes.c_char_p, []),
     "cgb200_device_count": (_i, []),
     "cgb200_version": (ctypes.c_char_p, []),

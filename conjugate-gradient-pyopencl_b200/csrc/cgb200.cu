@@ -60,6 +60,7 @@ static int fail(int code, const char *fmt, ...) {
 // ---------------------------------------------------------------------------
 struct cgb200_ctx {
     int device = 0, dtype = 0, n = 0;
+    int extra_cols = 0;          // halo entries appended to the direction vector (row-block shards)
     long long nnz = 0;
     size_t vsize = 0;
     void *d_vals = nullptr;
@@ -183,6 +184,8 @@ template <typename T> struct Engine {
         s.n_active = (int *)take(sizeof(int));
         s.it = (int *)take(sizeof(int));
         s.ticket = (unsigned *)take(4 * sizeof(unsigned));
+        s.rr = (T *)take(kk * sizeof(T));
+        s.defer = 0;
         s.partial = (T *)c->partial;
         s.hist = hist_cap > 0 ? c->d_hist : nullptr;
         s.hist_cap = hist_cap;
@@ -191,7 +194,7 @@ template <typename T> struct Engine {
         return s;
     }
     static size_t scalars_bytes(int k) {
-        return (size_t)k * (3 * sizeof(T) + sizeof(double) + 2 * sizeof(int)) + 16 * 10 + 64;
+        return (size_t)k * (3 * sizeof(T) + sizeof(double) + 2 * sizeof(int)) + (size_t)k * sizeof(T) + 16 * 12 + 64;
     }
 
     static int ensure_workspace(cgb200_ctx *c, int k) {
@@ -200,7 +203,7 @@ template <typename T> struct Engine {
         const size_t bytes = (size_t)c->n * k * sizeof(T) + 64;
         CU(cudaMalloc(&c->x, bytes));
         CU(cudaMalloc(&c->r, bytes));
-        CU(cudaMalloc(&c->d, bytes));
+        CU(cudaMalloc(&c->d, bytes + (size_t)c->extra_cols * k * sizeof(T)));
         CU(cudaMalloc(&c->q, bytes));
         if (k > 1) CU(cudaMalloc(&c->stage, bytes));
         CU(cudaMalloc(&c->scal_mem, scalars_bytes(k)));
@@ -1089,3 +1092,5 @@ double *cgd(int size, int nonZeros, const double *aValues, const double *b, cons
 }
 
 }  // extern "C"
+
+#include "shard.cuh"

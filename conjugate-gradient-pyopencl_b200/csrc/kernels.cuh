@@ -42,7 +42,68 @@ template <typename T> struct CgScalars {
     double *hist;       // optional delta history, hist_cap x k x (1|2) doubles
     int hist_cap;
     double tol;
+    T *rr;              // [k] this device's part of r.r when `defer` is set
+    int defer;          // row-block sharded solve: the dot products are only partial sums here; the
+                        // bookkeeping runs in init_bookkeep_kernel / update_bookkeep_kernel after the
+                        // all-reduce over the devices (dq is all-reduced in place)
 };
+
+// After delta = r0.r0 is known for column c.                      clcg.c:274-292
+template <typename T> __device__ __forceinline__ void init_bookkeep(const CgScalars<T> &sc, int c, T dl) {
+    const double a0 = Sc<T>::abs(dl);
+    sc.delta_new[c] = dl;
+    sc.delta_old[c] = dl;
+    sc.dq[c] = Sc<T>::zero();
+    sc.delta0[c] = a0;
+    const bool live = (a0 > 0.0) && Sc<T>::finite(dl);
+    sc.state[c] = live ? ST_ACTIVE : (a0 == 0.0 ? ST_CONVERGED : ST_BREAKDOWN);
+    sc.iters[c] = 0;
+    if (sc.hist && sc.hist_cap > 0) Sc<T>::to_double2(dl, sc.hist + (size_t)c * (Sc<T>::cplx ? 2 : 1));
+}
+
+// After the new r.r is known for column c: delta shuffle (clcg.c:350-356), convergence test, history.
+template <typename T> __device__ __forceinline__ void update_bookkeep(const CgScalars<T> &sc, int c, int k, int it1, T nd) {
+    if (sc.state[c] == ST_ACTIVE) {
+        sc.delta_old[c] = sc.delta_new[c];
+        sc.delta_new[c] = nd;
+        const double a = Sc<T>::abs(nd);
+        int st = ST_ACTIVE;
+        if (!Sc<T>::finite(nd)) st = ST_BREAKDOWN;
+        else if (a == 0.0 || (sc.tol > 0.0 && sqrt(a / sc.delta0[c]) < sc.tol)) st = ST_CONVERGED;
+        if (st != ST_ACTIVE) {
+            sc.state[c] = st;
+            sc.iters[c] = it1;
+            atomicSub(sc.n_active, 1);
+        }
+    }
+    if (sc.hist && it1 < sc.hist_cap)
+        Sc<T>::to_double2(sc.delta_new[c], sc.hist + ((size_t)it1 * k + c) * (Sc<T>::cplx ? 2 : 1));
+}
+
+// The deferred halves of the two finalisations, one block, run after the all-reduce of sc.rr.
+template <typename T> __global__ void init_bookkeep_kernel(int k, CgScalars<T> sc) {
+    for (int c = threadIdx.x; c < k; c += blockDim.x) init_bookkeep<T>(sc, c, sc.rr[c]);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int live = 0;
+        for (int c = 0; c < k; c++) live += (sc.state[c] == ST_ACTIVE);
+        *sc.n_active = live;
+        *sc.it = 0;
+    }
+}
+template <typename T> __global__ void update_bookkeep_kernel(int k, CgScalars<T> sc) {
+    if (*sc.n_active == 0) return;
+    const int it1 = *sc.it + 1;
+    for (int c = threadIdx.x; c < k; c += blockDim.x) update_bookkeep<T>(sc, c, k, it1, sc.rr[c]);
+    __syncthreads();
+    if (threadIdx.x == 0) *sc.it = it1;
+}
+
+// Packs the entries of d that peer devices need (their halo) into one send buffer.
+template <typename T>
+__global__ void pack_kernel(int count, const int *__restrict__ idx, const T *__restrict__ d, T *__restrict__ out) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) out[i] = d[idx[i]];
+}
 
 // Matrix streams (values, column indices) are read exactly once per SpMV: mark them
 // streaming so they do not displace the gathered vector from L1/L2.
@@ -858,26 +919,19 @@ init_kernel(size_t npacks, size_t nelem, int k, int kv, const T *b /* may alias 
             for (int v = 0; v < V; v++) {
                 const int c = t * V + v;
                 if (c < k) {
-                    const T dl = smem[t * V + v];
-                    const double a0 = Sc<T>::abs(dl);
-                    sc.delta_new[c] = dl;
-                    sc.delta_old[c] = dl;
-                    sc.dq[c] = Sc<T>::zero();
-                    sc.delta0[c] = a0;
-                    const bool live = (a0 > 0.0) && Sc<T>::finite(dl);
-                    sc.state[c] = live ? ST_ACTIVE : (a0 == 0.0 ? ST_CONVERGED : ST_BREAKDOWN);
-                    sc.iters[c] = 0;
-                    if (sc.hist && sc.hist_cap > 0)
-                        Sc<T>::to_double2(dl, sc.hist + (size_t)c * (Sc<T>::cplx ? 2 : 1));
+                    if (sc.defer) sc.rr[c] = smem[t * V + v];
+                    else init_bookkeep<T>(sc, c, smem[t * V + v]);
                 }
             }
         }
         __syncthreads();
         if (t == 0) {
-            int live = 0;
-            for (int c = 0; c < k; c++) live += (sc.state[c] == ST_ACTIVE);
-            *sc.n_active = live;
-            *sc.it = 0;
+            if (!sc.defer) {
+                int live = 0;
+                for (int c = 0; c < k; c++) live += (sc.state[c] == ST_ACTIVE);
+                *sc.n_active = live;
+                *sc.it = 0;
+            }
             sc.ticket[TK_INIT] = 0;
         }
     }
@@ -942,29 +996,14 @@ update_xr_kernel(size_t npacks, size_t nelem, int k, int kv, const T *__restrict
             for (int v = 0; v < V; v++) {
                 const int c = t * V + v;
                 if (c < k) {
-                    if (sc.state[c] == ST_ACTIVE) {
-                        const T nd = smem[t * V + v];
-                        sc.delta_old[c] = sc.delta_new[c];
-                        sc.delta_new[c] = nd;
-                        const double a = Sc<T>::abs(nd);
-                        int st = ST_ACTIVE;
-                        if (!Sc<T>::finite(nd)) st = ST_BREAKDOWN;
-                        else if (a == 0.0 || (sc.tol > 0.0 && sqrt(a / sc.delta0[c]) < sc.tol)) st = ST_CONVERGED;
-                        if (st != ST_ACTIVE) {
-                            sc.state[c] = st;
-                            sc.iters[c] = it1;
-                            atomicSub(sc.n_active, 1);
-                        }
-                    }
-                    if (sc.hist && it1 < sc.hist_cap)
-                        Sc<T>::to_double2(sc.delta_new[c],
-                                          sc.hist + ((size_t)it1 * k + c) * (Sc<T>::cplx ? 2 : 1));
+                    if (sc.defer) sc.rr[c] = smem[t * V + v];
+                    else update_bookkeep<T>(sc, c, k, it1, smem[t * V + v]);
                 }
             }
         }
         __syncthreads();
         if (t == 0) {
-            *sc.it = it1;
+            if (!sc.defer) *sc.it = it1;
             sc.ticket[TK_UPDATE] = 0;
         }
     }

@@ -154,26 +154,31 @@ def rhs_a(N: int, omega: float) -> np.ndarray:
     return b.ravel()
 
 
-def laplace3d(N: int, dtype=np.float64) -> sp.csr_matrix:
+def laplace3d(N: int, dtype=np.float64, rows=None) -> sp.csr_matrix:
     """7-point Laplacian on an N^3 grid, diag 6 / off -1, Dirichlet truncation, x fastest.
 
     The 3-D extension of `Poisson` named by BASELINE.json configs 3 and 4 (not in the
-    reference).  Built straight into CSR arrays: 300^3 has 188 M non-zeros."""
+    reference).  Built straight into CSR arrays: 300^3 has 188 M non-zeros.
+    rows=(r0, r1): only that block of rows (global column indices, shape (r1-r0, N^3)) -- what one
+    rank of a row-block sharded run needs."""
     n = N ** 3
-    z, y, x = np.meshgrid(np.arange(N, dtype=np.int32), np.arange(N, dtype=np.int32),
-                          np.arange(N, dtype=np.int32), indexing="ij")
-    x, y, z = x.ravel(), y.ravel(), z.ravel()
+    r0, r1 = (0, n) if rows is None else (int(rows[0]), int(rows[1]))
+    idx = np.arange(r0, r1, dtype=np.int64)
+    x = (idx % N).astype(np.int32)
+    y = ((idx // N) % N).astype(np.int32)
+    z = (idx // (N * N)).astype(np.int32)
+    m = r1 - r0
     # neighbours in ascending column order: -N^2, -N, -1, 0, +1, +N, +N^2
-    present = np.stack([z > 0, y > 0, x > 0, np.ones(n, bool), x < N - 1, y < N - 1, z < N - 1], axis=1)
+    present = np.stack([z > 0, y > 0, x > 0, np.ones(m, bool), x < N - 1, y < N - 1, z < N - 1], axis=1)
     del x, y, z
     offs = np.array([-N * N, -N, -1, 0, 1, N, N * N], dtype=np.int64)
     counts = present.sum(axis=1, dtype=np.int64)
-    indptr = np.zeros(n + 1, dtype=np.int64)
+    indptr = np.zeros(m + 1, dtype=np.int64)
     np.cumsum(counts, out=indptr[1:])
     r, s = np.nonzero(present)
-    indices = (r + offs[s]).astype(np.int32)
+    indices = (r + r0 + offs[s]).astype(np.int32)
     data = np.where(s == 3, 6.0, -1.0).astype(dtype)
-    A = sp.csr_matrix((data, indices, indptr.astype(np.int32)), shape=(n, n))
+    A = sp.csr_matrix((data, indices, indptr.astype(np.int32)), shape=(m, n))
     A.has_sorted_indices = True
     return A
 

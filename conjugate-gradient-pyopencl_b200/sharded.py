@@ -1,0 +1,251 @@
+"""Multi-GPU drivers for the CG path: one process per GPU (torchrun / torch.distributed).
+
+Two ways the path shards:
+
+  rhs-split   what the reference does (`distribute_workloads_on_devices`,
+              p_h-PY_C-CL-multi-GPU.py:2123-2140): contiguous blocks of right-hand sides per
+              GPU, matrix replicated, no communication.  `split_rhs` reproduces its split.
+
+  row-block   what BASELINE.json's north star adds: rank g owns rows [r_g, r_g+1) of A.
+              `plan_row_block` renumbers the local columns [owned | halo] and works out which
+              owned entries each peer needs; `ShardedMatrix` hands that to the C ABI
+              (cgb200_shard_*), which moves exactly those entries over NVLink every iteration
+              and all-reduces the two dot scalars.
+
+The planning is plain numpy + torch.distributed object collectives, so it runs (and is
+tested) on CPU with the gloo backend; `reference_sharded_cg` is the same algorithm in numpy
+over any backend, used by the tests as the oracle of the communication pattern.
+"""
+import ctypes
+
+import numpy as np
+
+try:
+    from . import _lib
+except ImportError:
+    import _lib
+
+
+# ----------------------------------------------------------------------------------------
+# rhs-split (the reference's mode)
+# ----------------------------------------------------------------------------------------
+def split_rhs(n_rhs, n_devices):
+    """[(start, end)] per device: the first n_rhs % n_devices devices get one extra column
+    (p_h-PY_C-CL-multi-GPU.py:2125-2134)."""
+    per, extra = divmod(n_rhs, n_devices)
+    out, start = [], 0
+    for i in range(n_devices):
+        end = start + per + (1 if i < extra else 0)
+        out.append((start, end))
+        start = end
+    return out
+
+
+# ----------------------------------------------------------------------------------------
+# row-block
+# ----------------------------------------------------------------------------------------
+def split_rows(indptr, world, by="rows", align=1):
+    """Row boundaries [world+1].  by='rows': equal row counts (stencils: z-slabs);
+    by='nnz': equal non-zero counts (irregular matrices).  Boundaries are multiples of `align`."""
+    n = len(indptr) - 1
+    if by == "rows":
+        bounds = [(n * p) // world for p in range(world + 1)]
+    elif by == "nnz":
+        nnz = int(indptr[-1])
+        targets = [(nnz * p) // world for p in range(world + 1)]
+        bounds = [int(np.searchsorted(indptr, t, side="left")) for t in targets]
+        bounds[0], bounds[-1] = 0, n
+    else:
+        raise ValueError(by)
+    if align > 1:
+        bounds = [min(n, (b // align) * align) for b in bounds[:-1]] + [n]
+    for p in range(world):
+        if bounds[p + 1] <= bounds[p]:
+            raise ValueError(f"rank {p} would own no rows (n={n}, world={world})")
+    return np.asarray(bounds, dtype=np.int64)
+
+
+class ShardPlan:
+    """Rank-local view of a row-block partition."""
+    __slots__ = ("rank", "world", "bounds", "n_owned", "n_halo", "indptr", "cols_local", "data",
+                 "halo_globals", "recv_counts", "send_counts", "send_idx")
+
+
+def plan_row_block(indptr, indices, data, bounds, rank, exchange=None):
+    """Builds rank `rank`'s ShardPlan from the GLOBAL CSR arrays (or from its own row slice, see below).
+
+    indptr/indices/data may be the whole matrix, or only the rows [bounds[rank], bounds[rank+1]) with
+    `indptr` rebased to start at 0 (len(indptr) == n_owned + 1) -- what a rank that generated only its
+    slab has.  `exchange(obj) -> list[obj per rank]` is an all-gather of Python objects
+    (default: torch.distributed.all_gather_object); every rank must call plan_row_block together.
+    """
+    world = len(bounds) - 1
+    rb, re = int(bounds[rank]), int(bounds[rank + 1])
+    n_owned = re - rb
+    indptr = np.asarray(indptr)
+    if len(indptr) == n_owned + 1 and world > 1:
+        lp = indptr - indptr[0]
+        cols = np.asarray(indices[: lp[-1]])
+        vals = np.asarray(data[: lp[-1]])
+    else:
+        lo, hi = int(indptr[rb]), int(indptr[re])
+        lp = indptr[rb:re + 1] - lo
+        cols = np.asarray(indices[lo:hi])
+        vals = np.asarray(data[lo:hi])
+    owned = (cols >= rb) & (cols < re)
+    halo_globals = np.unique(cols[~owned])
+    owner = np.searchsorted(bounds, halo_globals, side="right") - 1
+    recv_counts = np.bincount(owner, minlength=world).astype(np.intc)
+    cols_local = np.where(owned, cols - rb, n_owned + np.searchsorted(halo_globals, cols)).astype(np.intc)
+
+    # tell every owner which of its entries this rank needs; learn what the others need from us
+    need = {int(p): halo_globals[owner == p] for p in np.nonzero(recv_counts)[0]}
+    if exchange is None:
+        import torch.distributed as dist
+
+        def exchange(obj):
+            out = [None] * world
+            dist.all_gather_object(out, obj)
+            return out
+    all_need = exchange(need) if world > 1 else [need]
+    send_counts = np.zeros(world, dtype=np.intc)
+    send_lists = []
+    for p in range(world):
+        wanted = all_need[p].get(rank) if p != rank else None
+        if wanted is not None and len(wanted):
+            wanted = np.asarray(wanted, dtype=np.int64)
+            if wanted.min() < rb or wanted.max() >= re:
+                raise ValueError(f"rank {p} asks rank {rank} for rows it does not own")
+            send_counts[p] = len(wanted)
+            send_lists.append((wanted - rb).astype(np.intc))
+    plan = ShardPlan()
+    plan.rank, plan.world, plan.bounds = rank, world, np.asarray(bounds)
+    plan.n_owned, plan.n_halo = n_owned, int(len(halo_globals))
+    plan.indptr = np.ascontiguousarray(lp, dtype=np.intc)
+    plan.cols_local = np.ascontiguousarray(cols_local)
+    plan.data = np.ascontiguousarray(vals)
+    plan.halo_globals = halo_globals
+    plan.recv_counts = recv_counts
+    plan.send_counts = send_counts
+    plan.send_idx = (np.concatenate(send_lists) if send_lists else np.zeros(0, np.intc)).astype(np.intc)
+    return plan
+
+
+class ShardedMatrix:
+    """A row block of A resident on this rank's GPU, plus the NCCL communicator (`cgb200_shard_create`)."""
+
+    def __init__(self, plan, device=None, dtype=None):
+        import torch
+        import torch.distributed as dist
+        self.plan = plan
+        data = plan.data if dtype is None else plan.data.astype(dtype)
+        self.dtype = data.dtype
+        if device is None:
+            device = torch.cuda.current_device()
+        L = _lib.lib()
+        uid = np.zeros(128, dtype=np.uint8)
+        if plan.world > 1:
+            if plan.rank == 0:
+                _lib.check(L.cgb200_nccl_unique_id(_lib.ptr(uid)))
+            box = [uid.tobytes()]
+            dist.broadcast_object_list(box, src=0)
+            uid = np.frombuffer(box[0], dtype=np.uint8).copy()
+        h = ctypes.c_void_p()
+        _lib.check(L.cgb200_shard_create(
+            ctypes.byref(h), plan.rank, plan.world, _lib.ptr(uid), int(device), plan.n_owned, plan.n_halo,
+            int(data.size), _lib.ptr(np.ascontiguousarray(data)), _lib.ptr(plan.indptr), _lib.ptr(plan.cols_local),
+            _lib.DTYPE_CODE[np.dtype(self.dtype)], _lib.ptr(np.ascontiguousarray(plan.send_counts)),
+            _lib.ptr(np.ascontiguousarray(plan.send_idx)), _lib.ptr(np.ascontiguousarray(plan.recv_counts))))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib.lib().cgb200_shard_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def set_stream(self, cuda_stream):
+        _lib.check(_lib.lib().cgb200_shard_set_stream(self._h, ctypes.c_void_p(int(cuda_stream) if cuda_stream else 0)))
+
+    def set_option(self, key, value):
+        _lib.check(_lib.lib().cgb200_shard_set_option(self._h, key.encode(), int(value)))
+
+    def info(self):
+        out = (ctypes.c_longlong * 8)()
+        _lib.check(_lib.lib().cgb200_shard_info(self._h, out))
+        return dict(zip(("n_owned", "n_halo", "sent_per_exchange", "launches", "graph_launches", "exchanges",
+                         "allreduces", "nnz"), list(out)))
+
+    def solve(self, b_owned, x_owned=None, max_iterations=1000, tol=0.0):
+        """Collective.  b_owned / x_owned: this rank's slices (numpy arrays or device tensors)."""
+        if isinstance(b_owned, np.ndarray):
+            b_owned = np.ascontiguousarray(b_owned, dtype=self.dtype)
+            if x_owned is None:
+                x_owned = np.zeros(self.plan.n_owned, dtype=self.dtype)
+        elif x_owned is None:
+            raise ValueError("x_owned is required for device pointers")
+        its, rel = ctypes.c_int(), ctypes.c_double()
+        rc = _lib.check(_lib.lib().cgb200_shard_solve(self._h, _lib.ptr(b_owned), _lib.ptr(x_owned),
+                                                      int(max_iterations), float(tol), ctypes.byref(its),
+                                                      ctypes.byref(rel)))
+        ms = (ctypes.c_double * 4)()
+        _lib.check(_lib.lib().cgb200_shard_last_timing(self._h, ms))
+        return x_owned, {"flags": rc, "iterations": its.value, "relres": rel.value,
+                         "timing_ms": dict(zip(("h2d", "init", "iterations", "d2h"), list(ms)))}
+
+
+# ----------------------------------------------------------------------------------------
+# the same algorithm in numpy over torch.distributed (any backend): oracle of the plan
+# ----------------------------------------------------------------------------------------
+def halo_exchange_numpy(plan, v_owned, dist):
+    """[v_owned | halo] for this rank: the communication pattern of ShardEngine::exchange."""
+    import torch
+    out = np.empty(plan.n_owned + plan.n_halo, dtype=v_owned.dtype)
+    out[:plan.n_owned] = v_owned
+    sendbuf = v_owned[plan.send_idx]
+    reqs, recv_t, so, ro = [], [], 0, plan.n_owned
+    # bytes are bytes: ship every dtype as float32 / float64 words
+    view = (lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.float64 if a.dtype.itemsize % 8 == 0 else np.float32)))
+    for p in range(plan.world):
+        if plan.send_counts[p]:
+            reqs.append(dist.isend(view(sendbuf[so:so + plan.send_counts[p]]), dst=p))
+            so += plan.send_counts[p]
+        if plan.recv_counts[p]:
+            buf = np.empty(plan.recv_counts[p], dtype=v_owned.dtype)
+            t = view(buf)
+            recv_t.append((ro, buf, t))
+            reqs.append(dist.irecv(t, src=p))
+            ro += plan.recv_counts[p]
+    for r in reqs:
+        r.wait()
+    for ro, buf, t in recv_t:
+        out[ro:ro + buf.size] = t.numpy().view(v_owned.dtype)
+    return out
+
+
+def reference_sharded_cg(plan, b_owned, x_owned, iters, dist):
+    """Row-block CG in numpy with the plan's halo exchange and two all-reduces per iteration:
+    the recurrence of clcg.c:253-419 / helmFE_var.py:507-544 distributed by rows."""
+    import scipy.sparse as sp
+    import torch
+    A = sp.csr_matrix((plan.data, plan.cols_local, plan.indptr), shape=(plan.n_owned, plan.n_owned + plan.n_halo))
+
+    def allsum(z):
+        z = np.asarray([z], dtype=np.complex128 if np.iscomplexobj(z) else np.float64)
+        t = torch.from_numpy(z.view(np.float64))
+        dist.all_reduce(t)
+        return z[0]
+
+    x = x_owned.copy()
+    r = b_owned - A @ halo_exchange_numpy(plan, x, dist)
+    d = r.copy()
+    delta_new = allsum(np.dot(r, r))
+    for _ in range(iters):
+        q = A @ halo_exchange_numpy(plan, d, dist)
+        alpha = delta_new / allsum(np.dot(d, q))
+        x = x + alpha * d
+        r = r - alpha * q
+        delta_old, delta_new = delta_new, allsum(np.dot(r, r))
+        d = r + (delta_new / delta_old) * d
+    return x

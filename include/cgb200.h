@@ -132,6 +132,44 @@ CGB200_API int cgb200_cg(int device, int dtype, int size, int nonZeros, const vo
 /* Drop the matrix that cg()/cgd() keep resident between calls (keyed by content). */
 CGB200_API int cgb200_clear_cache(void);
 
+/* ---------------------------------------------------------------------------------
+ * Row-block sharding across the GPUs of one box -- one process per GPU.
+ *
+ * The reference's multi-GPU script splits right-hand sides over devices and never
+ * communicates (p_h-PY_C-CL-multi-GPU.py:2123-2181): that mode is cgb200_cg() /
+ * cl.conjugate_gradient_multi_gpu() once per device.  These entry points are the other
+ * mode: rank g owns rows [r_g, r_g+1) of A.  The caller (sharded.py) renumbers the
+ * local columns as [owned 0..n_owned) | halo n_owned..n_owned+n_halo) with the halo
+ * sorted by global index (hence grouped by owner rank), and says which owned entries
+ * each peer needs.  Every iteration moves only those entries peer to peer (NCCL
+ * send/recv over NVLink) and all-reduces the two dot scalars.  One right-hand side.
+ * ------------------------------------------------------------------------------- */
+typedef struct cgb200_shard_ctx *cgb200_shard;
+
+/* ncclGetUniqueId() of rank 0, 128 bytes, to be broadcast to the other ranks. */
+CGB200_API int cgb200_nccl_unique_id(void *out128);
+
+/* aColsLocal: column indices in the local numbering.  send_counts[p] / recv_counts[p]:
+ * entries sent to / received from rank p (0 for p == rank); send_idx: the owned indices
+ * to send, concatenated in rank order; received blocks land in the halo in rank order. */
+CGB200_API int cgb200_shard_create(cgb200_shard *out, int rank, int world, const void *nccl_id128, int device,
+                                   int n_owned, int n_halo, long long nnz, const void *aValues,
+                                   const int *aPointers, const int *aColsLocal, int dtype,
+                                   const int *send_counts, const int *send_idx, const int *recv_counts);
+CGB200_API int cgb200_shard_destroy(cgb200_shard sh);
+CGB200_API int cgb200_shard_set_stream(cgb200_shard sh, void *cuda_stream);
+CGB200_API int cgb200_shard_set_option(cgb200_shard sh, const char *key, long long value);
+
+/* Collective: every rank calls it with its slice of b and x (host or device pointers).
+ * Same semantics as cgb200_solve() with k = 1; iterations / relres are global values. */
+CGB200_API int cgb200_shard_solve(cgb200_shard sh, const void *b_owned, void *x_owned, int max_iterations,
+                                  double tol, int *iterations, double *relres);
+
+/* [0] n_owned [1] n_halo [2] entries sent per exchange [3] kernels launched [4] graph launches
+ * [5] halo exchanges [6] all-reduces [7] local nnz */
+CGB200_API int cgb200_shard_info(cgb200_shard sh, long long out[8]);
+CGB200_API int cgb200_shard_last_timing(cgb200_shard sh, double ms[4]);
+
 CGB200_API const char *cgb200_last_error(void);
 CGB200_API int cgb200_device_count(void);
 CGB200_API const char *cgb200_version(void);

@@ -1,0 +1,69 @@
+"""Row-block sharded CG on N GPUs (torchrun): parity with the single-GPU engine and the oracle,
+then timing.  python -m torch.distributed.run --nproc-per-node N tools/shard_check.py [N3d] [iters]"""
+import json, os, sys, time
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import torch, torch.distributed as dist
+import cg_b200
+from cg_b200 import sharded
+import cg_b200.problems as P
+
+rank, world, lr = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+torch.cuda.set_device(lr)
+if world > 1:
+    dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
+out = {}
+# ---- parity on small systems (every rank builds the global matrix)
+import cpu_ref
+for name, A, b, tolv in (("lap3d24", P.laplace3d(24), np.ones(24 ** 3), 1e-10),
+                         ("helm64_c128", P.helmholtz_fe(64), P.rhs_a(64, 12.0), 1e-10),
+                         ("powerlaw", P.powerlaw_spd(n=20000, nnz_target=300000, max_row=3000), None, 1e-10)):
+    if b is None:
+        b = A @ np.ones(A.shape[0])
+    by = "nnz" if name == "powerlaw" else "rows"
+    bounds = sharded.split_rows(A.indptr, world, by=by)
+    plan = sharded.plan_row_block(A.indptr, A.indices, A.data, bounds, rank)
+    rb, re = bounds[rank], bounds[rank + 1]
+    M = sharded.ShardedMatrix(plan, device=lr)
+    x, info = M.solve(b[rb:re].astype(A.dtype), max_iterations=60)
+    ref, _, _ = cpu_ref.cg(A.data, A.indptr, A.indices, b.astype(A.dtype), iters=60)
+    err = float(np.linalg.norm(x - ref[rb:re]) / np.linalg.norm(ref[rb:re]))
+    x2, info2 = M.solve(b[rb:re].astype(A.dtype), max_iterations=5000, tol=1e-9)
+    _, its_ref, _ = cpu_ref.cg(A.data, A.indptr, A.indices, b.astype(A.dtype), iters=5000, tol=1e-9)
+    out[name] = dict(err60=err, iters=info2["iterations"], iters_oracle=int(its_ref[0]), n_halo=plan.n_halo, info=M.info())
+    assert err < tolv, (name, err)
+    assert abs(info2["iterations"] - int(its_ref[0])) <= 1, (name, info2, its_ref)
+    M.close()
+# ---- timing: 3-D Laplacian N^3, each rank builds only its slab
+N3 = int(sys.argv[1]) if len(sys.argv) > 1 else 300
+iters = int(sys.argv[2]) if len(sys.argv) > 2 else 256
+n = N3 ** 3
+planes = [(N3 * p) // world for p in range(world + 1)]
+bounds = np.array([pl * N3 * N3 for pl in planes], dtype=np.int64)
+rb, re = int(bounds[rank]), int(bounds[rank + 1])
+t0 = time.time()
+Al = P.laplace3d(N3, rows=(rb, re))
+plan = sharded.plan_row_block(Al.indptr, Al.indices, Al.data, bounds, rank)
+tgen = time.time() - t0
+M = sharded.ShardedMatrix(plan, device=lr)
+bt = torch.ones(re - rb, dtype=torch.float64, device="cuda")
+xt = torch.zeros_like(bt)
+for use_graph in (1, 0):
+    M.set_option("use_graph", use_graph)
+    for _ in range(2):
+        xt.zero_(); M.solve(bt, xt, max_iterations=iters)
+    if world > 1: dist.barrier()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(3):
+        xt.zero_(); _, info = M.solve(bt, xt, max_iterations=iters); ts.append(info["timing_ms"]["iterations"])
+    t = torch.tensor([min(ts)], device="cuda", dtype=torch.float64)
+    if world > 1: dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    out[f"lap{N3}_graph{use_graph}"] = dict(ms_per_iter=float(t.item()) / iters, its_per_s=iters / float(t.item()) * 1e3,
+                                            n_owned=plan.n_owned, n_halo=plan.n_halo, gen_s=tgen)
+M.close()
+if rank == 0:
+    print(json.dumps({"world": world, **out}))
+if world > 1:
+    dist.destroy_process_group()
