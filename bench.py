@@ -62,7 +62,9 @@ def make_problem(name, dtype, k):
         b = np.ones(A.shape[0])
     elif name == "c5":
         A = P.powerlaw_spd()
-        b = A @ np.ones(A.shape[0])
+        # (SURVEY.md 8(d) suggests b = A.ones, but every row of this matrix sums to 1, so ones is an
+        #  eigenvector and CG converges in one iteration; a random solution keeps the 256 iterations busy)
+        b = A @ np.random.default_rng(7).uniform(-1.0, 1.0, A.shape[0])
     else:
         raise SystemExit(f"unknown workload {name}")
     n = A.shape[0]
@@ -190,15 +192,142 @@ def run_reference(args, wl, dtype, k, rank, world):
     print(json.dumps(line), flush=True)
 
 
-def config_of(args, wl, A, k, dtype, world):
+def config_of(args, wl, A, k, dtype, world, n=None, nnz=None):
     return {"workload": f"{wl['desc']}; n={A.shape[0]}, nnz={A.nnz}, k={k} per GPU, dtype {dtype}; "
                         f"step = one cg() call of {ITERS_PER_STEP} iterations from x0=0",
             "name": args.workload, "n": int(A.shape[0]), "nnz": int(A.nnz), "k": int(k),
             "iters_per_step": ITERS_PER_STEP,
-            "parallelism": "single GPU" if world == 1 else f"rhs-split x{world} (matrix replicated, no collective)",
+            "parallelism": "single GPU" if world == 1 else
+                           (f"rhs-split x{world} (matrix replicated, one RHS per GPU, no collective)" if args.mode == "rhs-split"
+                            else f"row-block x{world} (halo of d by NCCL send/recv over NVLink + 2 all-reduces per iteration)"),
             "l2": "no L2 flush: matrix + vectors per iteration exceed the 126 MB L2"
                   if A.nnz * (A.dtype.itemsize + 4) > 126e6 else
                   "working set fits the 126 MB L2 (latency-bound config); no flush between iterations"}
+
+
+def run_row_block(args, wl, dtype, rank, local_rank, world):
+    """N > 1: the CSR matrix row-block partitioned over the ranks (strong scaling of ONE system)."""
+    import torch
+    import torch.distributed as dist
+    import cg_b200
+    import cg_b200.problems as P
+    from cg_b200 import sharded
+    np_t, _, v_bytes, cplx = P.DTYPES[dtype]
+    if args.workload in ("c3", "c4"):
+        N3 = 128 if args.workload == "c3" else 300
+        n = N3 ** 3
+        planes = [(N3 * p) // world for p in range(world + 1)]          # whole z-planes per rank
+        bounds = np.array([pl * N3 * N3 for pl in planes], dtype=np.int64)
+        rb, re = int(bounds[rank]), int(bounds[rank + 1])
+        Al = P.laplace3d(N3, dtype=np_t, rows=(rb, re))
+        nnz = 7 * n - 6 * N3 * N3
+        plan = sharded.plan_row_block(Al.indptr, Al.indices, Al.data, bounds, rank)
+        b_owned = np.ones(re - rb, dtype=np_t)
+        shape = (n, nnz)
+    else:
+        A, B = make_problem(args.workload, dtype, 1)
+        n, nnz = A.shape[0], A.nnz
+        bounds = sharded.split_rows(A.indptr, world, by="nnz" if args.workload == "c5" else "rows")
+        rb, re = int(bounds[rank]), int(bounds[rank + 1])
+        plan = sharded.plan_row_block(A.indptr, A.indices, A.data, bounds, rank)
+        b_owned = np.ascontiguousarray(B[rb:re])
+        shape = (n, nnz)
+        del A
+    M = sharded.ShardedMatrix(plan, device=local_rank)
+    stream = torch.cuda.Stream()
+    M.set_stream(stream.cuda_stream)
+    for kv in args.opt:
+        key, val = kv.split("=")
+        M.set_option(key, int(val))
+    tdt = {"f32": torch.float32, "f64": torch.float64, "c64": torch.complex64, "c128": torch.complex128}[dtype]
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    with torch.cuda.stream(stream):
+        b_dev = torch.from_numpy(b_owned).to("cuda")
+        x_dev = torch.zeros(re - rb, dtype=tdt, device="cuda")
+
+        def step():
+            x_dev.zero_()
+            return M.solve(b_dev, x_dev, max_iterations=ITERS_PER_STEP)[1]
+
+        for _ in range(args.warmup):
+            step()
+        l0 = M.info()["launches"]
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.steps):
+            info = step()
+        e1.record(stream)
+        barrier()
+        clocks = sampler.stop()
+        ms = e0.elapsed_time(e1)
+        launches = M.info()["launches"] - l0
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t.item()) / args.steps
+    value = ITERS_PER_STEP / (ms_per_step / 1e3)
+
+    # e2e: this rank's slices of b and x0 in pinned host memory, x read back, every step
+    pin = lambda a: torch.from_numpy(a).pin_memory().numpy()
+    b_h, x_h = pin(b_owned), pin(np.zeros_like(b_owned))
+    def e2e_step():
+        x_h[...] = 0
+        dist.barrier()
+        t0 = time.perf_counter()
+        M.solve(b_h, x_h, max_iterations=ITERS_PER_STEP)
+        return time.perf_counter() - t0
+    e2e_step()
+    tt = sum(e2e_step() for _ in range(args.steps))
+    t = torch.tensor([tt], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    tt = float(t.item())
+    tot = torch.tensor([float(plan.n_owned * v_bytes)], dtype=torch.float64, device="cuda")
+    dist.all_reduce(tot)
+    e2e = {"value": ITERS_PER_STEP * args.steps / tt, "unit": "iterations/s",
+           "h2d_bytes_per_step": int(2 * tot.item()), "d2h_bytes_per_step": int(tot.item()),
+           "ms_per_step": 1e3 * tt / args.steps,
+           "how": "cgb200_shard_solve on pinned host slices of b / x0 per rank, x read back; the row blocks of the "
+                  "matrix stay resident (they are placed once by cgb200_shard_create)"}
+
+    peak, peak_src = measured_peak()
+    ln, lnnz = plan.n_owned, int(plan.data.size)
+    b_spmv = lnnz * (v_bytes + 4) + 4 * (ln + 1) + 2 * ln * v_bytes
+    kernels = {}
+    reps = 50 if b_spmv > 50e6 else 400
+    for name, nbytes in (("spmv_dot", b_spmv), ("update_xr", 6 * ln * v_bytes), ("update_d", 3 * ln * v_bytes)):
+        kms = M.time_kernel(name, reps=reps)
+        kernels[name] = {"ms": kms, "algorithmic_bytes": nbytes, "gbs": nbytes / kms / 1e6, "frac": nbytes / kms / 1e6 / peak}
+    sinfo = M.info()
+    M.close()
+    if rank == 0:
+        it_ms = info["timing_ms"]["iterations"] / ITERS_PER_STEP
+
+        class _A:  # shape carrier for config_of
+            pass
+        a = _A()
+        a.shape, a.nnz, a.dtype = (shape[0], shape[0]), shape[1], np.dtype(np_t)
+        b_iter_local = b_spmv + 9 * ln * v_bytes
+        line = {
+            "metric": "CG iters/sec", "value": value, "unit": "iterations/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": dtype, "data": "synthetic", "config": config_of(args, wl, a, 1, dtype, world),
+            "roofline": {"bound": "hbm", "kernel": "spmv_dot (rank 0 row block)", "achieved": kernels["spmv_dot"]["gbs"],
+                         "peak": peak, "unit": "GB/s", "frac": kernels["spmv_dot"]["frac"], "traffic": None,
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": b_spmv,
+                         "ms_per_launch": kernels["spmv_dot"]["ms"]},
+            "kernels": kernels,
+            "iteration": {"ms": it_ms, "local_algorithmic_bytes": b_iter_local, "gbs_per_gpu": b_iter_local / it_ms / 1e6,
+                          "frac": b_iter_local / it_ms / 1e6 / peak},
+            "shard": sinfo, "options": args.opt, "cpu_baseline": None, "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": clocks, "solve_phases_ms": info["timing_ms"],
+        }
+        print(json.dumps(line), flush=True)
+    dist.destroy_process_group()
 
 
 def main():
@@ -210,6 +339,9 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--dtype", default=None, choices=["f32", "f64", "c64", "c128"])
     ap.add_argument("--k", type=int, default=None)
+    ap.add_argument("--mode", default="row-block", choices=["row-block", "rhs-split"],
+                    help="N > 1: row-block sharding with halo exchange + all-reduce (default), or the reference's "
+                         "rhs-split (matrix replicated, no collective)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--opt", action="append", default=[], help="engine option key=value (cgb200_set_option)")
@@ -235,6 +367,10 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    if world > 1 and args.mode == "row-block" and k == 1:
+        run_row_block(args, wl, dtype, rank, local_rank, world)
+        return
 
     A, B = make_problem(args.workload, dtype, k)
     if world > 1 and k == 1:

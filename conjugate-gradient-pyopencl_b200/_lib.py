@@ -41,6 +41,7 @@ SIGNATURES = {
     "cgb200_nccl_unique_id": (_i, [_vp]),
     "cgb200_shard_create": (_i, [ctypes.POINTER(_vp), _i, _i, _vp, _i, _i, _i, _ll, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
     "cgb200_shard_destroy": (_i, [_vp]),
+    "cgb200_shard_local": (_vp, [_vp]),
     "cgb200_shard_set_stream": (_i, [_vp, _vp]),
     "cgb200_shard_set_option": (_i, [_vp, ctypes.c_char_p, _ll]),
     "cgb200_shard_solve": (_i, [_vp, _vp, _vp, _i, _d, ctypes.POINTER(_i), ctypes.POINTER(_d)]),

@@ -310,6 +310,8 @@ int cgb200_shard_destroy(cgb200_shard sh) {
     return CGB200_OK;
 }
 
+cgb200_handle cgb200_shard_local(cgb200_shard sh) { return sh ? sh->m : nullptr; }
+
 int cgb200_shard_set_stream(cgb200_shard sh, void *cuda_stream) {
     if (!sh) return fail(CGB200_ERR_ARG, "NULL shard");
     return cgb200_set_stream(sh->m, cuda_stream);

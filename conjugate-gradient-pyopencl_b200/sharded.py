@@ -165,6 +165,14 @@ class ShardedMatrix:
 
     __del__ = close
 
+    def time_kernel(self, which, reps=50):
+        """Mean ms of one kernel of the loop on the local row block (see cgb200_time_kernel)."""
+        kinds = {"spmv_dot": 0, "update_xr": 1, "update_d": 2, "spmv": 3}
+        ms = ctypes.c_double()
+        h = ctypes.c_void_p(_lib.lib().cgb200_shard_local(self._h))
+        _lib.check(_lib.lib().cgb200_time_kernel(h, kinds[which], 1, int(reps), ctypes.byref(ms)))
+        return ms.value
+
     def set_stream(self, cuda_stream):
         _lib.check(_lib.lib().cgb200_shard_set_stream(self._h, ctypes.c_void_p(int(cuda_stream) if cuda_stream else 0)))
 

@@ -157,6 +157,8 @@ CGB200_API int cgb200_shard_create(cgb200_shard *out, int rank, int world, const
                                    const int *aPointers, const int *aColsLocal, int dtype,
                                    const int *send_counts, const int *send_idx, const int *recv_counts);
 CGB200_API int cgb200_shard_destroy(cgb200_shard sh);
+/* The handle of the local row block (owned by the shard): for cgb200_info / cgb200_time_kernel. */
+CGB200_API cgb200_handle cgb200_shard_local(cgb200_shard sh);
 CGB200_API int cgb200_shard_set_stream(cgb200_shard sh, void *cuda_stream);
 CGB200_API int cgb200_shard_set_option(cgb200_shard sh, const char *key, long long value);
 

@@ -9,6 +9,15 @@ import cg_b200
 from cg_b200 import sharded
 import cg_b200.problems as P
 
+import faulthandler
+faulthandler.dump_traceback_later(150, exit=True)
+
+
+def log(*a):
+    print(f"[rank {os.environ.get('RANK', 0)} +{time.time() - T0:.1f}s]", *a, file=sys.stderr, flush=True)
+
+
+T0 = time.time()
 rank, world, lr = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(lr)
 if world > 1:
@@ -23,10 +32,19 @@ for name, A, b, tolv in (("lap3d24", P.laplace3d(24), np.ones(24 ** 3), 1e-10),
         b = A @ np.ones(A.shape[0])
     by = "nnz" if name == "powerlaw" else "rows"
     bounds = sharded.split_rows(A.indptr, world, by=by)
+    log(name, "planning")
     plan = sharded.plan_row_block(A.indptr, A.indices, A.data, bounds, rank)
     rb, re = bounds[rank], bounds[rank + 1]
+    log(name, "plan done; creating shard", plan.n_owned, plan.n_halo)
     M = sharded.ShardedMatrix(plan, device=lr)
+    log(name, "shard created; plain-launch solve")
+    M.set_option("use_graph", 0)
     x, info = M.solve(b[rb:re].astype(A.dtype), max_iterations=60)
+    log(name, "plain solve done; graph solve")
+    M.set_option("use_graph", 1)
+    xg, _ = M.solve(b[rb:re].astype(A.dtype), max_iterations=60)
+    assert np.array_equal(x, xg)
+    log(name, "graph solve done")
     ref, _, _ = cpu_ref.cg(A.data, A.indptr, A.indices, b.astype(A.dtype), iters=60)
     err = float(np.linalg.norm(x - ref[rb:re]) / np.linalg.norm(ref[rb:re]))
     x2, info2 = M.solve(b[rb:re].astype(A.dtype), max_iterations=5000, tol=1e-9)
@@ -46,7 +64,10 @@ t0 = time.time()
 Al = P.laplace3d(N3, rows=(rb, re))
 plan = sharded.plan_row_block(Al.indptr, Al.indices, Al.data, bounds, rank)
 tgen = time.time() - t0
+log("timing: shard create")
 M = sharded.ShardedMatrix(plan, device=lr)
+faulthandler.cancel_dump_traceback_later()
+faulthandler.dump_traceback_later(200, exit=True)
 bt = torch.ones(re - rb, dtype=torch.float64, device="cuda")
 xt = torch.zeros_like(bt)
 for use_graph in (1, 0):
