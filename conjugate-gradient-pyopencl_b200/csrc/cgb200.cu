@@ -88,7 +88,6 @@ struct cgb200_ctx {
     // graphs: (k, chunk) -> exec ; dropped whenever buffers or options change
     cudaGraphExec_t graph = nullptr;
     int graph_k = 0, graph_chunk_built = 0;
-    double graph_tol = -1;
     int graph_hist_cap = -1;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     double last_ms[4] = {0, 0, 0, 0};
@@ -185,16 +184,17 @@ template <typename T> struct Engine {
         s.it = (int *)take(sizeof(int));
         s.ticket = (unsigned *)take(4 * sizeof(unsigned));
         s.rr = (T *)take(kk * sizeof(T));
+        s.tol = (const double *)take(sizeof(double));
         s.defer = 0;
         s.partial = (T *)c->partial;
         s.hist = hist_cap > 0 ? c->d_hist : nullptr;
         s.hist_cap = hist_cap;
-        s.tol = tol;
+        (void)tol;
         (void)k;
         return s;
     }
     static size_t scalars_bytes(int k) {
-        return (size_t)k * (3 * sizeof(T) + sizeof(double) + 2 * sizeof(int)) + (size_t)k * sizeof(T) + 16 * 12 + 64;
+        return (size_t)k * (3 * sizeof(T) + sizeof(double) + 2 * sizeof(int)) + (size_t)k * sizeof(T) + 16 * 14 + 64;
     }
 
     static int ensure_workspace(cgb200_ctx *c, int k) {
@@ -518,6 +518,7 @@ template <typename T> struct Engine {
         }
         const CgScalars<T> sc = scalars(c, k, tol, hist_cap);
         const VecGeom g = geom(c, k);
+        CU(cudaMemcpyAsync((void *)sc.tol, &tol, sizeof(double), cudaMemcpyHostToDevice, c->stream));
 
         CU(cudaEventRecord(c->ev[0], c->stream));
         // inputs: b -> d (temporarily), x0 -> x
@@ -542,8 +543,7 @@ template <typename T> struct Engine {
         int done = 0;
         const int chunk = std::max(1, c->graph_chunk);
         if (c->use_graph && maxit >= chunk) {
-            if (!c->graph || c->graph_k != k || c->graph_chunk_built != chunk || c->graph_tol != tol ||
-                c->graph_hist_cap != hist_cap) {
+            if (!c->graph || c->graph_k != k || c->graph_chunk_built != chunk || c->graph_hist_cap != hist_cap) {
                 drop_graph(c);
                 cudaGraph_t gr = nullptr;
                 const long long before = c->launches;
@@ -560,7 +560,6 @@ template <typename T> struct Engine {
                 if (ce != cudaSuccess) return fail(CGB200_ERR_CUDA, "graph instantiate: %s", cudaGetErrorString(ce));
                 c->graph_k = k;
                 c->graph_chunk_built = chunk;
-                c->graph_tol = tol;
                 c->graph_hist_cap = hist_cap;
             }
             while (done + chunk <= maxit) {
@@ -647,6 +646,7 @@ template <typename T> struct Engine {
         const VecGeom g = geom(c, k);
         // keep every column ACTIVE and the updates neutral: alpha = 0 (dq = 0), beta = 0 (delta_new = 0)
         CU(cudaMemsetAsync(sc.state, 0, k * sizeof(int), c->stream));
+        CU(cudaMemsetAsync((void *)sc.tol, 0, sizeof(double), c->stream));
         int one = k;
         CU(cudaMemcpyAsync(sc.n_active, &one, sizeof(int), cudaMemcpyHostToDevice, c->stream));
         CU(cudaStreamSynchronize(c->stream));

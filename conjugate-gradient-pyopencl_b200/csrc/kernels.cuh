@@ -41,7 +41,7 @@ template <typename T> struct CgScalars {
     T *partial;         // [grid][k] per-block partial dot products
     double *hist;       // optional delta history, hist_cap x k x (1|2) doubles
     int hist_cap;
-    double tol;
+    const double *tol;  // in device memory, so that one captured graph serves every tolerance
     T *rr;              // [k] this device's part of r.r when `defer` is set
     int defer;          // row-block sharded solve: the dot products are only partial sums here; the
                         // bookkeeping runs in init_bookkeep_kernel / update_bookkeep_kernel after the
@@ -69,7 +69,7 @@ template <typename T> __device__ __forceinline__ void update_bookkeep(const CgSc
         const double a = Sc<T>::abs(nd);
         int st = ST_ACTIVE;
         if (!Sc<T>::finite(nd)) st = ST_BREAKDOWN;
-        else if (a == 0.0 || (sc.tol > 0.0 && sqrt(a / sc.delta0[c]) < sc.tol)) st = ST_CONVERGED;
+        else if (a == 0.0 || (*sc.tol > 0.0 && sqrt(a / sc.delta0[c]) < *sc.tol)) st = ST_CONVERGED;
         if (st != ST_ACTIVE) {
             sc.state[c] = st;
             sc.iters[c] = it1;

@@ -69,6 +69,15 @@ static NcclApi *nccl_api() {
             return fail(CGB200_ERR_NCCL, "%s:%d %s -> %s", __FILE__, __LINE__, #call, nccl_api()->GetErrorString(r_)); \
     } while (0)
 
+#define DBG(...)                                   \
+    do {                                           \
+        if (getenv("CGB200_DEBUG")) {              \
+            fprintf(stderr, "[cgb200] " __VA_ARGS__); \
+            fprintf(stderr, "\n");                 \
+            fflush(stderr);                        \
+        }                                          \
+    } while (0)
+
 struct cgb200_shard_ctx {
     cgb200_ctx *m = nullptr;     // the local rows, columns renumbered [owned | halo]
     int rank = 0, world = 1;
@@ -142,6 +151,7 @@ template <typename T> struct ShardEngine {
         const typename E::VecGeom g = E::geom(c, 1);
         const size_t bytes = (size_t)sh->n_owned * sizeof(T);
 
+        CU(cudaMemcpyAsync((void *)sc.tol, &tol, sizeof(double), cudaMemcpyHostToDevice, c->stream));
         CU(cudaEventRecord(c->ev[0], c->stream));
         CU(cudaMemcpyAsync(c->x, x, bytes, cudaMemcpyDefault, c->stream));
         CU(cudaMemcpyAsync(c->d, c->x, bytes, cudaMemcpyDeviceToDevice, c->stream));
@@ -156,25 +166,33 @@ template <typename T> struct ShardEngine {
         init_bookkeep_kernel<T><<<1, 32, 0, c->stream>>>(1, sc);
         c->launches++;
         CU(cudaEventRecord(c->ev[2], c->stream));
+        DBG("rank %d: init enqueued (maxit %d tol %g graph %d)", sh->rank, maxit, tol, c->use_graph);
 
         int done = 0;
         const int chunk = std::max(1, c->graph_chunk);
         if (c->use_graph && maxit >= chunk) {
-            // the graph is rebuilt per solve: tol is baked into the kernel arguments
-            drop_graph(c);
-            cudaGraph_t gr = nullptr;
-            const long long before = c->launches;
-            CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
-            int rc = 0;
-            for (int i = 0; i < chunk && rc >= 0; i++) rc = iteration(sh, g, sc);
-            cudaError_t ce = cudaStreamEndCapture(c->stream, &gr);
-            c->graph_nodes = c->launches - before;
-            c->launches = before;
-            if (rc < 0) return rc;
-            if (ce != cudaSuccess) return fail(CGB200_ERR_CUDA, "graph capture: %s", cudaGetErrorString(ce));
-            ce = cudaGraphInstantiate(&c->graph, gr, 0);
-            cudaGraphDestroy(gr);
-            if (ce != cudaSuccess) return fail(CGB200_ERR_CUDA, "graph instantiate: %s", cudaGetErrorString(ce));
+            // captured once per shard (the tolerance lives in device memory); re-captured only when the
+            // chunk length or the stream changed
+            if (!c->graph || c->graph_k != -1 || c->graph_chunk_built != chunk) {
+                drop_graph(c);
+                cudaGraph_t gr = nullptr;
+                const long long before = c->launches;
+                DBG("rank %d: capturing %d iterations", sh->rank, chunk);
+                CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+                int rc = 0;
+                for (int i = 0; i < chunk && rc >= 0; i++) rc = iteration(sh, g, sc);
+                cudaError_t ce = cudaStreamEndCapture(c->stream, &gr);
+                c->graph_nodes = c->launches - before;
+                c->launches = before;
+                if (rc < 0) return rc;
+                if (ce != cudaSuccess) return fail(CGB200_ERR_CUDA, "graph capture: %s", cudaGetErrorString(ce));
+                ce = cudaGraphInstantiate(&c->graph, gr, 0);
+                cudaGraphDestroy(gr);
+                if (ce != cudaSuccess) return fail(CGB200_ERR_CUDA, "graph instantiate: %s", cudaGetErrorString(ce));
+                c->graph_k = -1;               // marks a shard graph (never matches a plain solve's k)
+                c->graph_chunk_built = chunk;
+                DBG("rank %d: graph ready (%lld nodes)", sh->rank, c->graph_nodes);
+            }
             while (done + chunk <= maxit) {
                 CU(cudaGraphLaunch(c->graph, c->stream));
                 c->graph_launches++;
@@ -183,6 +201,7 @@ template <typename T> struct ShardEngine {
                 if (tol > 0) {
                     CU(cudaMemcpyAsync(c->h_flag, sc.n_active, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
                     CU(cudaStreamSynchronize(c->stream));
+                    DBG("rank %d: %d iterations done, n_active=%d", sh->rank, done, *c->h_flag);
                     if (*c->h_flag == 0) { done = maxit; break; }   // identical on every rank: reduced values
                 }
             }
@@ -198,6 +217,7 @@ template <typename T> struct ShardEngine {
         CU(cudaEventRecord(c->ev[3], c->stream));
         CU(cudaMemcpyAsync(x, c->x, bytes, cudaMemcpyDefault, c->stream));
         CU(cudaEventRecord(c->ev[4], c->stream));
+        DBG("rank %d: loop enqueued, reading results", sh->rank);
 
         T dn;
         double d0;

@@ -47,7 +47,14 @@ for name, A, b, tolv in (("lap3d24", P.laplace3d(24), np.ones(24 ** 3), 1e-10),
     log(name, "graph solve done")
     ref, _, _ = cpu_ref.cg(A.data, A.indptr, A.indices, b.astype(A.dtype), iters=60)
     err = float(np.linalg.norm(x - ref[rb:re]) / np.linalg.norm(ref[rb:re]))
+    log(name, "oracle done; tolerance solve, plain launches")
+    M.set_option("use_graph", 0)
+    x2p, info2p = M.solve(b[rb:re].astype(A.dtype), max_iterations=5000, tol=1e-9)
+    log(name, "tolerance solve, graphs", info2p["iterations"])
+    M.set_option("use_graph", 1)
     x2, info2 = M.solve(b[rb:re].astype(A.dtype), max_iterations=5000, tol=1e-9)
+    log(name, "tolerance solves done", info2["iterations"])
+    assert np.array_equal(x2, x2p) and info2["iterations"] == info2p["iterations"]
     _, its_ref, _ = cpu_ref.cg(A.data, A.indptr, A.indices, b.astype(A.dtype), iters=5000, tol=1e-9)
     out[name] = dict(err60=err, iters=info2["iterations"], iters_oracle=int(its_ref[0]), n_halo=plan.n_halo, info=M.info())
     assert err < tolv, (name, err)
