@@ -75,7 +75,8 @@ struct cgb200_ctx {
     int ntiles = 0, nlong = 0, nslots = 0;
     uint64_t rowptr_hash = 0;
     // options
-    int opt_lpr = 0, graph_chunk = 16, use_graph = 1, blocks_per_sm = 0, spmv_variant = 0;
+    int opt_lpr = 0, graph_chunk = 16, use_graph = 1, blocks_per_sm = 0, spmv_variant = 0, solver = 0;
+    int coop = 0;
     // workspace (for ws_k right-hand sides)
     int ws_k = 0;
     void *x = nullptr, *r = nullptr, *d = nullptr, *q = nullptr, *stage = nullptr;
@@ -446,6 +447,56 @@ template <typename T> struct Engine {
         return 0;
     }
 
+    // ---- the whole solve in one cooperative launch (L2-resident systems) -------------
+    static bool fused_eligible(cgb200_ctx *c, int k) {
+        if (c->solver == 1 || !c->coop) return false;
+        if (k > FUSED_MAXK || kv_of(k) > 32) return false;
+        if (c->solver == 2) return true;
+        // auto: one iteration's working set (matrix + 4 vectors) comfortably inside the 126 MB L2
+        const double bytes = (double)c->nnz * (sizeof(T) + 4) + 4.0 * (c->n + 1) + 4.0 * k * c->n * sizeof(T);
+        return bytes <= 40e6;
+    }
+    template <int V, bool MULTI>
+    static int launch_fused(cgb200_ctx *c, int k, int G, const CgScalars<T> &sc, int maxit) {
+        auto kern = cg_fused_kernel<T, V, MULTI>;
+        const void *key = (const void *)kern;
+        int per_sm = 1;
+        auto it = c->occ.find(key);
+        if (it == c->occ.end()) {
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, FUSED_THREADS, 0) != cudaSuccess || per_sm < 1)
+                return fail(CGB200_ERR_CUDA, "fused CG kernel does not fit an SM");
+            c->occ[key] = per_sm;
+        } else {
+            per_sm = it->second;
+        }
+        const long long work = ((long long)c->n + (FUSED_THREADS / G) - 1) / (FUSED_THREADS / G);
+        int grid = (int)std::min<long long>((long long)c->sm_count * per_sm, std::max<long long>(work, 1));
+        grid = std::min(grid, c->grid_cap / 2);
+        int n = c->n;
+        const T *vals = (const T *)c->d_vals;
+        const int *rp = c->d_rowptr, *cl = c->d_cols;
+        const T *b = (const T *)c->d;
+        T *x = (T *)c->x, *r = (T *)c->r, *d = (T *)c->d, *q = (T *)c->q;
+        T *pa = (T *)c->partial, *pb = (T *)c->partial + (size_t)(c->grid_cap / 2) * k;
+        CgScalars<T> scv = sc;
+        void *args[] = {&n, &k, &G, &vals, &rp, &cl, &b, &x, &r, &d, &q, &pa, &pb, &scv, &maxit};
+        CU(cudaLaunchCooperativeKernel((const void *)kern, dim3(grid), dim3(FUSED_THREADS), args, 0, c->stream));
+        c->launches++;
+        return 0;
+    }
+    static int solve_fused(cgb200_ctx *c, int k, const CgScalars<T> &sc, int maxit) {
+        if (k == 1) {
+            int lpr = 1;
+            while (lpr < 32 && lpr < c->mean_row) lpr *= 2;
+            return launch_fused<1, false>(c, 1, lpr, sc, maxit);
+        }
+        const int V = pack_width(k), kv = k / V;
+        int G = 1;
+        while (G < kv) G *= 2;
+        if (V == 1) return launch_fused<1, true>(c, k, G, sc, maxit);
+        return launch_fused<VW, true>(c, k, G, sc, maxit);
+    }
+
     // ---- y = A x -------------------------------------------------------------
     static int spmv_api(cgb200_ctx *c, const void *x, void *y, int k, int layout) {
         if (layout == CGB200_LAYOUT_ROWMAJOR && !batch_ok(k))
@@ -533,53 +584,60 @@ template <typename T> struct Engine {
         }
         CU(cudaEventRecord(c->ev[1], c->stream));
 
-        // q = A x0 ; r = b - q ; d = r ; delta = r.r          clcg.c:253-292
-        TRY(spmv<false>(c, k, (const T *)c->x, (T *)c->q, sc));
-        if (g.V == 1) TRY(launch_init<1>(c, k, g, (const T *)c->d, (const T *)c->q, (T *)c->r, (T *)c->d, sc));
-        else TRY(launch_init<VW>(c, k, g, (const T *)c->d, (const T *)c->q, (T *)c->r, (T *)c->d, sc));
-        CU(cudaEventRecord(c->ev[2], c->stream));
+        if (fused_eligible(c, k)) {
+            // initialisation and every iteration in one cooperative launch; converged columns freeze and
+            // the kernel returns by itself once none is active, so there is nothing to poll
+            CU(cudaEventRecord(c->ev[2], c->stream));
+            TRY(solve_fused(c, k, sc, maxit));
+        } else {
+            // q = A x0 ; r = b - q ; d = r ; delta = r.r          clcg.c:253-292
+            TRY(spmv<false>(c, k, (const T *)c->x, (T *)c->q, sc));
+            if (g.V == 1) TRY(launch_init<1>(c, k, g, (const T *)c->d, (const T *)c->q, (T *)c->r, (T *)c->d, sc));
+            else TRY(launch_init<VW>(c, k, g, (const T *)c->d, (const T *)c->q, (T *)c->r, (T *)c->d, sc));
+            CU(cudaEventRecord(c->ev[2], c->stream));
 
-        // the loop, clcg.c:296-419
-        int done = 0;
-        const int chunk = std::max(1, c->graph_chunk);
-        if (c->use_graph && maxit >= chunk) {
-            if (!c->graph || c->graph_k != k || c->graph_chunk_built != chunk || c->graph_hist_cap != hist_cap) {
-                drop_graph(c);
-                cudaGraph_t gr = nullptr;
-                const long long before = c->launches;
-                CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
-                int rc = 0;
-                for (int i = 0; i < chunk && rc == 0; i++) rc = iteration(c, k, g, sc);
-                cudaError_t ce = cudaStreamEndCapture(c->stream, &gr);
-                c->graph_nodes = c->launches - before;
-                c->launches = before;
-                if (rc < 0) return rc;
-                if (ce != cudaSuccess) return fail(CGB200_ERR_CUDA, "graph capture: %s", cudaGetErrorString(ce));
-                ce = cudaGraphInstantiate(&c->graph, gr, 0);
-                cudaGraphDestroy(gr);
-                if (ce != cudaSuccess) return fail(CGB200_ERR_CUDA, "graph instantiate: %s", cudaGetErrorString(ce));
-                c->graph_k = k;
-                c->graph_chunk_built = chunk;
-                c->graph_hist_cap = hist_cap;
-            }
-            while (done + chunk <= maxit) {
-                CU(cudaGraphLaunch(c->graph, c->stream));
-                c->graph_launches++;
-                c->launches += c->graph_nodes;
-                done += chunk;
-                if (tol > 0) {
-                    CU(cudaMemcpyAsync(c->h_flag, sc.n_active, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-                    CU(cudaStreamSynchronize(c->stream));
-                    if (*c->h_flag == 0) { done = maxit; break; }
+            // the loop, clcg.c:296-419
+            int done = 0;
+            const int chunk = std::max(1, c->graph_chunk);
+            if (c->use_graph && maxit >= chunk) {
+                if (!c->graph || c->graph_k != k || c->graph_chunk_built != chunk || c->graph_hist_cap != hist_cap) {
+                    drop_graph(c);
+                    cudaGraph_t gr = nullptr;
+                    const long long before = c->launches;
+                    CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+                    int rc = 0;
+                    for (int i = 0; i < chunk && rc == 0; i++) rc = iteration(c, k, g, sc);
+                    cudaError_t ce = cudaStreamEndCapture(c->stream, &gr);
+                    c->graph_nodes = c->launches - before;
+                    c->launches = before;
+                    if (rc < 0) return rc;
+                    if (ce != cudaSuccess) return fail(CGB200_ERR_CUDA, "graph capture: %s", cudaGetErrorString(ce));
+                    ce = cudaGraphInstantiate(&c->graph, gr, 0);
+                    cudaGraphDestroy(gr);
+                    if (ce != cudaSuccess) return fail(CGB200_ERR_CUDA, "graph instantiate: %s", cudaGetErrorString(ce));
+                    c->graph_k = k;
+                    c->graph_chunk_built = chunk;
+                    c->graph_hist_cap = hist_cap;
+                }
+                while (done + chunk <= maxit) {
+                    CU(cudaGraphLaunch(c->graph, c->stream));
+                    c->graph_launches++;
+                    c->launches += c->graph_nodes;
+                    done += chunk;
+                    if (tol > 0) {
+                        CU(cudaMemcpyAsync(c->h_flag, sc.n_active, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+                        CU(cudaStreamSynchronize(c->stream));
+                        if (*c->h_flag == 0) { done = maxit; break; }
+                    }
                 }
             }
-        }
-        for (; done < maxit; done++) {
-            TRY(iteration(c, k, g, sc));
-            if (tol > 0 && (done % chunk) == chunk - 1) {
-                CU(cudaMemcpyAsync(c->h_flag, sc.n_active, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-                CU(cudaStreamSynchronize(c->stream));
-                if (*c->h_flag == 0) break;
+            for (; done < maxit; done++) {
+                TRY(iteration(c, k, g, sc));
+                if (tol > 0 && (done % chunk) == chunk - 1) {
+                    CU(cudaMemcpyAsync(c->h_flag, sc.n_active, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+                    CU(cudaStreamSynchronize(c->stream));
+                    if (*c->h_flag == 0) break;
+                }
             }
         }
         CU(cudaEventRecord(c->ev[3], c->stream));
@@ -842,6 +900,7 @@ int cgb200_create(cgb200_handle *out, int n, long long nnz, const void *aValues,
     cudaDeviceProp prop;
     CUB(cudaGetDeviceProperties(&prop, device));
     c->sm_count = prop.multiProcessorCount;
+    c->coop = prop.cooperativeLaunch;
     c->grid_cap = c->sm_count * 16;
     CUB(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     c->own_stream = true;
@@ -864,6 +923,7 @@ int cgb200_create(cgb200_handle *out, int n, long long nnz, const void *aValues,
     if (const char *e = getenv("CGB200_USE_GRAPH")) c->use_graph = atoi(e);
     if (const char *e = getenv("CGB200_BLOCKS_PER_SM")) c->blocks_per_sm = atoi(e);
     if (const char *e = getenv("CGB200_SPMV_VARIANT")) c->spmv_variant = atoi(e);
+    if (const char *e = getenv("CGB200_SOLVER")) c->solver = atoi(e);
     *out = c;
     return CGB200_OK;
 }
@@ -916,6 +976,7 @@ static int *option_slot(cgb200_handle c, const char *key) {
     if (!strcmp(key, "use_graph")) return &c->use_graph;
     if (!strcmp(key, "blocks_per_sm")) return &c->blocks_per_sm;
     if (!strcmp(key, "spmv_variant")) return &c->spmv_variant;
+    if (!strcmp(key, "solver")) return &c->solver;
     return nullptr;
 }
 

@@ -20,6 +20,8 @@
 // All kernels are persistent grid-stride kernels: the grid is a multiple of the SM
 // count and each block walks the work with stride gridDim.
 #pragma once
+#include <cooperative_groups.h>
+
 #include "scalar.cuh"
 
 namespace cgb {
@@ -1038,6 +1040,330 @@ update_d_kernel(size_t npacks, size_t nelem, int k, int kv, const T *__restrict_
     if (V > 1 && blockIdx.x == 0) {
         const size_t e = npacks * V + t;
         if (e < nelem) d[e] = Sc<T>::fma(beta[0], d[e], r[e]);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// The whole solve in ONE cooperative launch -- the schedule for systems whose iteration fits
+// the L2 (config C1, and the subdomain solves the reference's as_prec actually makes:
+// n ~ 16 k, k = M_s^2 right-hand sides, 256 fixed iterations).  There the three-kernel
+// iteration is bound by launch and reduction latency (~15 us), not by bytes.
+//
+// One block of 1024 threads per SM, two grid-wide barriers per iteration:
+//
+//   phase 1   q = A (r + beta d)       the direction update d = r + beta d (aypx.cl) is NOT a
+//             partial d.q               separate pass: the gather recomputes it on the fly
+//   -- grid.sync; every block sums the per-block partials in the same order -> alpha
+//   phase 2   dn = r + beta d ; x += alpha dn ; r -= alpha q ; d = dn ; partial r.r
+//   -- grid.sync; every block sums the partials -> delta_new, beta, convergence state
+//
+// alpha, beta, delta and the per-column state are replicated in the shared memory of every
+// block (the same deterministic arithmetic everywhere), so no block ever waits for a scalar
+// written by another one; block 0 mirrors them to HBM for the host.  Rows are owned by G
+// lanes: for k > 1 lane cp owns the 128-bit column pack cp (as spmm_kernel); for k = 1 the
+// G lanes split the non-zeros of the row (as spmv1_kernel).
+// ---------------------------------------------------------------------------
+constexpr int FUSED_THREADS = 1024;
+constexpr int FUSED_MAXK = 128;
+
+// sums over the lanes with equal (lane % G) in every warp, then over the 32 warps (fixed order);
+// s_out[c], c < G*V, holds the block's sum for column c
+template <typename T, int V>
+__device__ __forceinline__ void fused_block_reduce(T (&acc)[V], int G, T *s_warp, T *s_out) {
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    for (int off = 16; off >= G; off >>= 1) {
+#pragma unroll
+        for (int v = 0; v < V; v++) {
+            if constexpr (Sc<T>::cplx) {
+                acc[v].x += __shfl_xor_sync(0xffffffffu, acc[v].x, off);
+                acc[v].y += __shfl_xor_sync(0xffffffffu, acc[v].y, off);
+            } else {
+                acc[v] += __shfl_xor_sync(0xffffffffu, acc[v], off);
+            }
+        }
+    }
+    if (lane < G) {
+#pragma unroll
+        for (int v = 0; v < V; v++) s_warp[warp * (G * V) + lane * V + v] = acc[v];
+    }
+    __syncthreads();
+    if (t < G * V) {
+        T sum = Sc<T>::zero();
+        for (int w = 0; w < FUSED_THREADS / 32; w++) sum = Sc<T>::add(sum, s_warp[w * (G * V) + t]);
+        s_out[t] = sum;
+    }
+    __syncthreads();
+}
+
+// publish the block's column sums, grid barrier, then EVERY block adds up all blocks' partials
+template <typename T>
+__device__ __forceinline__ void fused_grid_sum(cooperative_groups::grid_group &grid, const T *s_out, int k, T *partial,
+                                               T *s_tot) {
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    if (t < k) partial[(size_t)blockIdx.x * k + t] = s_out[t];
+    grid.sync();
+    for (int c = warp; c < k; c += FUSED_THREADS / 32) {
+        T sum = Sc<T>::zero();
+        for (int b = lane; b < (int)gridDim.x; b += 32) sum = Sc<T>::add(sum, ld_cg(partial + (size_t)b * k + c));
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            if constexpr (Sc<T>::cplx) {
+                sum.x += __shfl_xor_sync(0xffffffffu, sum.x, off);
+                sum.y += __shfl_xor_sync(0xffffffffu, sum.y, off);
+            } else {
+                sum += __shfl_xor_sync(0xffffffffu, sum, off);
+            }
+        }
+        if (lane == 0) s_tot[c] = sum;
+    }
+    __syncthreads();
+}
+
+template <typename T, int V, bool MULTI>
+__global__ void __launch_bounds__(FUSED_THREADS, 1)
+cg_fused_kernel(int n, int k, int G, const T *__restrict__ vals, const int *__restrict__ rowptr,
+                const int *__restrict__ cols, const T *b /* aliases d */, T *x, T *r, T *d, T *q,
+                T *partial_a, T *partial_b, CgScalars<T> sc, int maxit) {
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    using P = Pack<T, V>;
+    __shared__ T s_warp[32 * 32 * V];
+    __shared__ T s_out[32 * V];
+    __shared__ T s_tot[FUSED_MAXK];
+    __shared__ T s_alpha[FUSED_MAXK], s_beta[FUSED_MAXK], s_dnew[FUSED_MAXK], s_dold[FUSED_MAXK];
+    __shared__ double s_d0[FUSED_MAXK];
+    __shared__ int s_state[FUSED_MAXK], s_iters[FUSED_MAXK];
+    __shared__ int s_live;
+
+    const int t = threadIdx.x;
+    const int cp = t % G;                       // column pack (MULTI) or lane within the row (k = 1)
+    const int kv = MULTI ? k / V : 1;
+    const bool active = MULTI ? (cp < kv) : true;
+    const int rows_per_block = FUSED_THREADS / G;
+    const double tol = *sc.tol;
+    const int ncomp = Sc<T>::cplx ? 2 : 1;
+
+    // y = A * w(col) for this thread's share of one row; w is produced by `load_w`
+    auto row_product = [&](int row, bool valid, auto load_w, T (&acc)[V]) {
+#pragma unroll
+        for (int v = 0; v < V; v++) acc[v] = Sc<T>::zero();
+        int lo = 0, hi = 0;
+        if (valid) {
+            lo = __ldg(rowptr + row);
+            hi = __ldg(rowptr + row + 1);
+        }
+        if constexpr (MULTI) {
+            for (int j = lo; j < hi; j++) {
+                const T a = __ldg(vals + j);
+                const int c = __ldg(cols + j);
+                T w[V];
+                load_w(c, w);
+#pragma unroll
+                for (int v = 0; v < V; v++) acc[v] = Sc<T>::fma(a, w[v], acc[v]);
+            }
+        } else {
+            for (int j = lo + cp; j < hi; j += G) {
+                const T a = __ldg(vals + j);
+                const int c = __ldg(cols + j);
+                T w[V];
+                load_w(c, w);
+                acc[0] = Sc<T>::fma(a, w[0], acc[0]);
+            }
+            // every lane of the warp takes part, whatever its row
+            for (int off = G >> 1; off > 0; off >>= 1) {
+                if constexpr (Sc<T>::cplx) {
+                    acc[0].x += __shfl_xor_sync(0xffffffffu, acc[0].x, off);
+                    acc[0].y += __shfl_xor_sync(0xffffffffu, acc[0].y, off);
+                } else {
+                    acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], off);
+                }
+            }
+        }
+    };
+    // element index of this thread's pack in row `row` (MULTI) / of the row's single value (k = 1)
+    auto at = [&](int row) -> size_t { return MULTI ? (size_t)row * k + (size_t)cp * V : (size_t)row; };
+    const bool owner = MULTI ? active : (cp == 0);   // the thread that stores a row's result
+
+    // ---------------- initialisation: q = A x0 ; r = b - q ; d = r ; delta = r.r    clcg.c:253-292
+    for (long long row0 = (long long)blockIdx.x * rows_per_block; row0 < n; row0 += (long long)gridDim.x * rows_per_block) {
+        const int row = (int)row0 + t / G;
+        const bool valid = row < n;
+        T acc[V];
+        row_product(row, valid && active, [&](int c, T (&w)[V]) {
+            if constexpr (MULTI) {
+                const P p = *reinterpret_cast<const P *>(x + (size_t)c * k + (size_t)cp * V);
+#pragma unroll
+                for (int v = 0; v < V; v++) w[v] = p.v[v];
+            } else {
+                w[0] = x[c];
+            }
+        }, acc);
+        if (valid && owner) {
+            if constexpr (MULTI) {
+                P out;
+#pragma unroll
+                for (int v = 0; v < V; v++) out.v[v] = acc[v];
+                *reinterpret_cast<P *>(q + at(row)) = out;
+            } else {
+                q[row] = acc[0];
+            }
+        }
+    }
+    grid.sync();
+    {
+        T acc[V];
+#pragma unroll
+        for (int v = 0; v < V; v++) acc[v] = Sc<T>::zero();
+        for (long long row0 = (long long)blockIdx.x * rows_per_block; row0 < n; row0 += (long long)gridDim.x * rows_per_block) {
+            const int row = (int)row0 + t / G;
+            if (row < n && owner) {
+                const size_t e = at(row);
+#pragma unroll
+                for (int v = 0; v < V; v++) {
+                    const T rv = Sc<T>::sub(b[e + v], q[e + v]);
+                    r[e + v] = rv;
+                    d[e + v] = rv;
+                    acc[v] = Sc<T>::fma(rv, rv, acc[v]);
+                }
+            }
+        }
+        fused_block_reduce<T, V>(acc, G, s_warp, s_out);
+        fused_grid_sum<T>(grid, s_out, k, partial_b, s_tot);
+    }
+    if (t < k) {
+        const T dl = s_tot[t];
+        const double a0 = Sc<T>::abs(dl);
+        s_dnew[t] = dl;
+        s_dold[t] = dl;
+        s_d0[t] = a0;
+        s_beta[t] = Sc<T>::zero();
+        s_alpha[t] = Sc<T>::zero();
+        s_state[t] = ((a0 > 0.0) && Sc<T>::finite(dl)) ? ST_ACTIVE : (a0 == 0.0 ? ST_CONVERGED : ST_BREAKDOWN);
+        s_iters[t] = 0;
+        if (blockIdx.x == 0 && sc.hist && sc.hist_cap > 0) Sc<T>::to_double2(dl, sc.hist + (size_t)t * ncomp);
+    }
+    __syncthreads();
+    if (t == 0) {
+        int live = 0;
+        for (int c = 0; c < k; c++) live += (s_state[c] == ST_ACTIVE);
+        s_live = live;
+    }
+    __syncthreads();
+
+    // ---------------- the loop, clcg.c:296-419
+    int it = 0;
+    for (; it < maxit && s_live > 0; it++) {
+        // partials of phase 1 go to buffer a, of phase 2 (and of the initialisation) to buffer b: a fast
+        // block can then never overwrite partials that a slow block is still summing
+        // phase 1: q = A (r + beta d), partial (r + beta d).q
+        T dot[V];
+#pragma unroll
+        for (int v = 0; v < V; v++) dot[v] = Sc<T>::zero();
+        T beta[V];
+#pragma unroll
+        for (int v = 0; v < V; v++) beta[v] = MULTI ? (active ? s_beta[cp * V + v] : Sc<T>::zero()) : s_beta[0];
+        for (long long row0 = (long long)blockIdx.x * rows_per_block; row0 < n; row0 += (long long)gridDim.x * rows_per_block) {
+            const int row = (int)row0 + t / G;
+            const bool valid = row < n;
+            T acc[V];
+            row_product(row, valid && active, [&](int c, T (&w)[V]) {
+                if constexpr (MULTI) {
+                    const size_t e = (size_t)c * k + (size_t)cp * V;
+                    const P rp = *reinterpret_cast<const P *>(r + e);
+                    const P dp = *reinterpret_cast<const P *>(d + e);
+#pragma unroll
+                    for (int v = 0; v < V; v++) w[v] = Sc<T>::fma(beta[v], dp.v[v], rp.v[v]);
+                } else {
+                    w[0] = Sc<T>::fma(beta[0], d[c], r[c]);
+                }
+            }, acc);
+            if (valid && owner) {
+                const size_t e = at(row);
+#pragma unroll
+                for (int v = 0; v < V; v++) {
+                    q[e + v] = acc[v];
+                    const T dn = Sc<T>::fma(beta[v], d[e + v], r[e + v]);
+                    dot[v] = Sc<T>::fma(dn, acc[v], dot[v]);
+                }
+            }
+        }
+        if (!MULTI && cp != 0) dot[0] = Sc<T>::zero();
+        fused_block_reduce<T, V>(dot, MULTI ? G : 1, s_warp, s_out);
+        fused_grid_sum<T>(grid, s_out, k, partial_a, s_tot);
+        if (t < k) {
+            T al = Sc<T>::zero();
+            if (s_state[t] == ST_ACTIVE && !Sc<T>::is_zero(s_tot[t])) al = Sc<T>::div(s_dnew[t], s_tot[t]);
+            s_alpha[t] = al;
+        }
+        __syncthreads();
+
+        // phase 2: dn = r + beta d ; x += alpha dn ; r -= alpha q ; d = dn ; partial r.r
+        T acc2[V], alpha[V];
+#pragma unroll
+        for (int v = 0; v < V; v++) {
+            acc2[v] = Sc<T>::zero();
+            alpha[v] = MULTI ? (active ? s_alpha[cp * V + v] : Sc<T>::zero()) : s_alpha[0];
+        }
+        for (long long row0 = (long long)blockIdx.x * rows_per_block; row0 < n; row0 += (long long)gridDim.x * rows_per_block) {
+            const int row = (int)row0 + t / G;
+            if (row < n && owner) {
+                const size_t e = at(row);
+#pragma unroll
+                for (int v = 0; v < V; v++) {
+                    const T dn = Sc<T>::fma(beta[v], d[e + v], r[e + v]);
+                    x[e + v] = Sc<T>::fma(alpha[v], dn, x[e + v]);
+                    const T rv = Sc<T>::fnma(alpha[v], q[e + v], r[e + v]);
+                    r[e + v] = rv;
+                    d[e + v] = dn;
+                    acc2[v] = Sc<T>::fma(rv, rv, acc2[v]);
+                }
+            }
+        }
+        fused_block_reduce<T, V>(acc2, MULTI ? G : 1, s_warp, s_out);
+        fused_grid_sum<T>(grid, s_out, k, partial_b, s_tot);
+        if (t < k) {
+            T be = Sc<T>::zero();
+            if (s_state[t] == ST_ACTIVE) {
+                const T nd = s_tot[t];
+                s_dold[t] = s_dnew[t];
+                s_dnew[t] = nd;
+                const double a = Sc<T>::abs(nd);
+                int st = ST_ACTIVE;
+                if (!Sc<T>::finite(nd)) st = ST_BREAKDOWN;
+                else if (a == 0.0 || (tol > 0.0 && sqrt(a / s_d0[t]) < tol)) st = ST_CONVERGED;
+                if (st != ST_ACTIVE) {
+                    s_state[t] = st;
+                    s_iters[t] = it + 1;
+                } else if (!Sc<T>::is_zero(s_dold[t])) {
+                    be = Sc<T>::div(nd, s_dold[t]);
+                }
+            }
+            s_beta[t] = be;
+            if (blockIdx.x == 0 && sc.hist && it + 1 < sc.hist_cap)
+                Sc<T>::to_double2(s_dnew[t], sc.hist + ((size_t)(it + 1) * k + t) * ncomp);
+        }
+        __syncthreads();
+        if (t == 0) {
+            int live = 0;
+            for (int c = 0; c < k; c++) live += (s_state[c] == ST_ACTIVE);
+            s_live = live;
+        }
+        __syncthreads();
+    }
+
+    // ---------------- a column that is still active ends with d = r + beta d pending: nothing reads d again.
+    if (blockIdx.x == 0) {
+        if (t < k) {
+            sc.delta_new[t] = s_dnew[t];
+            sc.delta_old[t] = s_dold[t];
+            sc.delta0[t] = s_d0[t];
+            sc.state[t] = s_state[t];
+            sc.iters[t] = s_iters[t];
+        }
+        if (t == 0) {
+            *sc.n_active = s_live;
+            *sc.it = it;
+        }
     }
 }
 

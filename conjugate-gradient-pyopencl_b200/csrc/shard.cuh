@@ -321,6 +321,7 @@ int cgb200_shard_destroy(cgb200_shard sh) {
     if (sh->m) {
         DeviceGuard guard(sh->m->device);
         if (sh->m->stream) cudaStreamSynchronize(sh->m->stream);
+        drop_graph(sh->m);      // a captured graph holds NCCL resources: it must go before the communicator
         if (sh->comm) nccl_api()->CommDestroy(sh->comm);
         if (sh->d_send_idx) cudaFree(sh->d_send_idx);
         if (sh->d_sendbuf) cudaFree(sh->d_sendbuf);

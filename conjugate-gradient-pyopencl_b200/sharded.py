@@ -41,6 +41,50 @@ def split_rhs(n_rhs, n_devices):
     return out
 
 
+def cg_rhs_split(size, non_zeros, a_values, b_values, a_pointers, a_cols, x_values, n_rhs, n_iterations,
+                 devices=None):
+    """The reference's multi-GPU solve in one process (`distribute_computations_with_threads`,
+    p_h-PY_C-CL-multi-GPU.py:2142-2181): contiguous blocks of right-hand sides per device, the matrix
+    replicated, one host thread per device, no device-to-device traffic.  x_values is filled in place.
+
+    devices: CUDA ordinals (default: every visible GPU)."""
+    import threading
+    L = _lib.lib()
+    if devices is None:
+        devices = list(range(L.cgb200_device_count()))
+    if not devices:
+        raise RuntimeError("no CUDA device: the engine has no CPU fallback")
+    a_values = np.ascontiguousarray(a_values)
+    dt = a_values.dtype
+    code = _lib.DTYPE_CODE[dt]
+    b_values = np.ascontiguousarray(b_values, dtype=dt)
+    if x_values.dtype != dt or not x_values.flags["C_CONTIGUOUS"]:
+        raise TypeError("x_values must be a C-contiguous array of the matrix dtype")
+    a_pointers = np.ascontiguousarray(a_pointers, dtype=np.intc)
+    a_cols = np.ascontiguousarray(a_cols, dtype=np.intc)
+    errors = []
+
+    def worker(dev, start, end):
+        if end <= start:
+            return
+        b = b_values[start * size:end * size]
+        x = x_values[start * size:end * size]          # a view: the C call writes the caller's array directly
+        rc = L.cgb200_cg(int(dev), code, int(size), int(non_zeros), _lib.ptr(a_values), _lib.ptr(b),
+                         _lib.ptr(a_pointers), _lib.ptr(a_cols), _lib.ptr(x), end - start, int(n_iterations))
+        if rc < 0:
+            errors.append((dev, L.cgb200_last_error().decode(errors="replace")))
+
+    threads = [threading.Thread(target=worker, args=(dev, s, e))
+               for dev, (s, e) in zip(devices, split_rhs(n_rhs, len(devices)))]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    if errors:
+        raise _lib.CgError(-2, f"rhs-split solve failed: {errors}")
+    return x_values
+
+
 # ----------------------------------------------------------------------------------------
 # row-block
 # ----------------------------------------------------------------------------------------

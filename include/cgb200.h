@@ -77,6 +77,9 @@ CGB200_API int cgb200_set_stream(cgb200_handle h, void *cuda_stream);
  *                    2 CSR-stream: tiles of non-zeros, products staged in shared memory, plain loads
  *                    3/4/5 CSR-stream fed by TMA bulk copies through a 2/3/4-stage mbarrier ring
  *                    6/7/8/9 row-direct CSR-stream fed by TMA (2/3/4/6 stages, no product buffer)
+ *   "solver"         0 auto: one cooperative launch for the whole solve when an iteration's working set
+ *                      fits the L2 (2 grid barriers per iteration), else three kernels per iteration
+ *                    1 three kernels per iteration in CUDA graphs     2 single cooperative launch
  *   "lanes_per_row"  0 auto | 1,2,4,8,16,32   lanes cooperating on one row (variant 1)
  *   "graph_chunk"    CG iterations captured per CUDA graph launch (default 16)
  *   "use_graph"      0/1

@@ -477,6 +477,22 @@ def test_cl_module_drop_in(gpu, cpu_ref, monkeypatch):
     sys.modules.pop("cl", None)
 
 
+def test_rhs_split_over_the_visible_gpus(gpu, cpu_ref):
+    """The reference's multi-GPU mode (RHS columns split across devices, one thread per device)."""
+    from cg_b200 import sharded
+    A, b = system("poisson", 32, np.complex64)
+    n, k = A.shape[0], 7
+    B = np.concatenate([b * (r + 1) for r in range(k)])
+    ndev = gpu.device_count()
+    for devices in ([0], list(range(ndev)), [0] * 3):          # [0]*3: three host threads sharing device 0
+        x = np.zeros(n * k, np.complex64)
+        out = sharded.cg_rhs_split(n, A.nnz, A.data, B, A.indptr, A.indices, x, k, 40, devices=devices)
+        assert out is x
+        ref, wide = oracle_pair(cpu_ref, "c64", A.data, A.indptr, A.indices, B, k=k, iters=40)
+        check_parity(x, ref, wide, "c64")
+    gpu._lib.lib().cgb200_clear_cache()
+
+
 def test_solve_with_device_tensors(gpu, cpu_ref):
     import torch
     A, b = system("helm", 48, np.complex128)
@@ -488,9 +504,50 @@ def test_solve_with_device_tensors(gpu, cpu_ref):
     assert rel(xt.cpu().numpy(), ref) < 1e-10
 
 
+@pytest.mark.parametrize("dname", ["f32", "f64", "c64", "c128"])
+@pytest.mark.parametrize("k", [1, 2, 3, 4, 9, 16, 32])
+def test_fused_single_launch_solver_matches_three_kernel_path(gpu, cpu_ref, dname, k):
+    """solver=2: the whole solve in one cooperative launch (2 grid barriers per iteration, direction update
+    folded into the gather) against solver=1 (three kernels per iteration) and the oracle."""
+    dt = DT[dname]
+    A, b = system("poisson", 36, dt)
+    n = A.shape[0]
+    rng = np.random.default_rng(k)
+    B = np.concatenate([b] + [rand(rng, n, dt) for _ in range(k - 1)])
+    X0 = rand(rng, n * k, dt) * dt(0.05)
+    with gpu.Matrix.from_scipy(A) as M:
+        M.set_option("solver", 1)
+        x1, i1 = M.solve(B, x=X0.copy(), k=k, max_iterations=45, history=True)
+        M.set_option("solver", 2)
+        x2, i2 = M.solve(B, x=X0.copy(), k=k, max_iterations=45, history=True)
+        launches = M.info()["launches"]
+        x3, i3 = M.solve(B, x=X0.copy(), k=k, max_iterations=3000, tol=1e-6 if dname in ("f32", "c64") else 1e-11)
+        assert M.info()["launches"] - launches <= 6          # copies/transposes aside: ONE solver launch
+        M.set_option("solver", 1)
+        x4, i4 = M.solve(B, x=X0.copy(), k=k, max_iterations=3000, tol=1e-6 if dname in ("f32", "c64") else 1e-11)
+    ref, wide = oracle_pair(cpu_ref, dname, A.data, A.indptr, A.indices, B, x0=X0, k=k, iters=45)
+    check_parity(x2, ref, wide, dname)
+    assert rel(x2, x1) < (1e-5 if dname in ("f32", "c64") else 1e-12)
+    h1, h2 = i1.delta_hist, i2.delta_hist
+    assert np.all(np.abs(h1 - h2) <= (1e-3 if dname in ("f32", "c64") else 1e-9) * np.abs(h1))
+    assert np.all(np.abs(i3.iterations - i4.iterations) <= 1), (i3.iterations, i4.iterations)
+    assert i3.flags == 0 and np.all(i3.relres < (1e-6 if dname in ("f32", "c64") else 1e-11))
+
+
+def test_fused_solver_is_the_default_for_l2_resident_systems(gpu, cpu_ref):
+    A, b = system("helm", 48, np.complex128)
+    with gpu.Matrix.from_scipy(A) as M:
+        l0 = M.info()["launches"]
+        x, info = M.solve(b, max_iterations=80)
+        assert M.info()["launches"] - l0 == 1 and M.info()["graph_launches"] == 0
+    ref, _, _ = cpu_ref.cg(A.data, A.indptr, A.indices, b, iters=80)
+    assert rel(x, ref) < 1e-10
+
+
 def test_graph_and_plain_launch_paths_agree(gpu):
     A, b = system("helm", 40, np.complex128)
     with gpu.Matrix.from_scipy(A) as M:
+        M.set_option("solver", 1)                # the three-kernel path (this system would default to the fused one)
         M.set_option("use_graph", 0)
         x0, _ = M.solve(b, max_iterations=50)
         M.set_option("use_graph", 1)
