@@ -460,15 +460,17 @@ template <typename T> struct Engine {
     static int launch_fused(cgb200_ctx *c, int k, int G, const CgScalars<T> &sc, int maxit) {
         auto kern = cg_fused_kernel<T, V, MULTI>;
         const void *key = (const void *)kern;
+        // shared-memory row cache of the k > 1 variant: 8 (coefficient, column) slots per row of the block
+        const size_t smem = MULTI ? (size_t)(FUSED_THREADS / G) * 8 * (sizeof(T) + sizeof(int)) : 0;
         int per_sm = 1;
         auto it = c->occ.find(key);
         if (it == c->occ.end()) {
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, FUSED_THREADS, 0) != cudaSuccess || per_sm < 1)
+            CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, FUSED_THREADS, smem) != cudaSuccess || per_sm < 1)
                 return fail(CGB200_ERR_CUDA, "fused CG kernel does not fit an SM");
-            c->occ[key] = per_sm;
-        } else {
-            per_sm = it->second;
+            c->occ[key] = 1;
         }
+        per_sm = 1;
         const long long work = ((long long)c->n + (FUSED_THREADS / G) - 1) / (FUSED_THREADS / G);
         int grid = (int)std::min<long long>((long long)c->sm_count * per_sm, std::max<long long>(work, 1));
         grid = std::min(grid, c->grid_cap / 2);
@@ -480,14 +482,17 @@ template <typename T> struct Engine {
         T *pa = (T *)c->partial, *pb = (T *)c->partial + (size_t)(c->grid_cap / 2) * k;
         CgScalars<T> scv = sc;
         void *args[] = {&n, &k, &G, &vals, &rp, &cl, &b, &x, &r, &d, &q, &pa, &pb, &scv, &maxit};
-        CU(cudaLaunchCooperativeKernel((const void *)kern, dim3(grid), dim3(FUSED_THREADS), args, 0, c->stream));
+        CU(cudaLaunchCooperativeKernel((const void *)kern, dim3(grid), dim3(FUSED_THREADS), args, smem, c->stream));
         c->launches++;
         return 0;
     }
     static int solve_fused(cgb200_ctx *c, int k, const CgScalars<T> &sc, int maxit) {
         if (k == 1) {
+            // lanes per row: enough for the mean row, but few enough that one pass of the (one block per SM)
+            // grid covers every row, so that the rows can stay in registers
             int lpr = 1;
             while (lpr < 32 && lpr < c->mean_row) lpr *= 2;
+            while (lpr > 1 && (long long)(FUSED_THREADS / lpr) * c->sm_count < c->n) lpr /= 2;
             return launch_fused<1, false>(c, 1, lpr, sc, maxit);
         }
         const int V = pack_width(k), kv = k / V;

@@ -1104,7 +1104,17 @@ __device__ __forceinline__ void fused_grid_sum(cooperative_groups::grid_group &g
     grid.sync();
     for (int c = warp; c < k; c += FUSED_THREADS / 32) {
         T sum = Sc<T>::zero();
-        for (int b = lane; b < (int)gridDim.x; b += 32) sum = Sc<T>::add(sum, ld_cg(partial + (size_t)b * k + c));
+        // 8 partials per lane per round, all loads issued before the first add (one L2 round trip)
+        for (int b0 = 0; b0 < (int)gridDim.x; b0 += 256) {
+            T part[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int bb = b0 + lane + 32 * u;
+                part[u] = bb < (int)gridDim.x ? ld_cg(partial + (size_t)bb * k + c) : Sc<T>::zero();
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u++) sum = Sc<T>::add(sum, part[u]);
+        }
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) {
             if constexpr (Sc<T>::cplx) {
@@ -1144,31 +1154,115 @@ cg_fused_kernel(int n, int k, int G, const T *__restrict__ vals, const int *__re
     const int ncomp = Sc<T>::cplx ? 2 : 1;
 
     // y = A * w(col) for this thread's share of one row; w is produced by `load_w`
-    auto row_product = [&](int row, bool valid, auto load_w, T (&acc)[V]) {
+    // When one pass of the grid covers every row, a thread works on the same row in every iteration:
+    // the row (<= UB coefficients and column indices per thread for k = 1, per row for k > 1) is then
+    // read from HBM/L2 once and kept on chip for the whole solve -- in registers for k = 1, in shared
+    // memory (broadcast to the row's G lanes) for k > 1 -- and phase 1 is a single round of gathers.
+    // cnt_my: -1 not cached (generic path), >= 0 cached.
+    constexpr int UB = MULTI ? 8 : 4;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    T *s_a = reinterpret_cast<T *>(smem_raw);                                  // [rows_per_block][UB]  (MULTI)
+    int *s_c = reinterpret_cast<int *>(smem_raw + (size_t)rows_per_block * UB * sizeof(T));
+    int c_my[MULTI ? 1 : UB];
+    T a_my[MULTI ? 1 : UB];
+    int cnt_my = -1;
+    const int lrow = t / G;                                                    // row slot inside the block
+    if ((long long)gridDim.x * rows_per_block >= n) {
+        const int row = (int)blockIdx.x * rows_per_block + lrow;
+        cnt_my = 0;
+        if constexpr (!MULTI) {
 #pragma unroll
-        for (int v = 0; v < V; v++) acc[v] = Sc<T>::zero();
+            for (int u = 0; u < UB; u++) {
+                c_my[u] = 0;
+                a_my[u] = Sc<T>::zero();
+            }
+        }
         int lo = 0, hi = 0;
-        if (valid) {
+        if (row < n) {
             lo = __ldg(rowptr + row);
             hi = __ldg(rowptr + row + 1);
         }
         if constexpr (MULTI) {
-            for (int j = lo; j < hi; j++) {
-                const T a = __ldg(vals + j);
-                const int c = __ldg(cols + j);
-                T w[V];
-                load_w(c, w);
+            const int cnt = hi - lo;
+            // the row's G lanes fill its UB slots together (slot u by lane u, u + G, ...)
+            for (int u = cp; u < UB; u += G) {
+                const bool ok = u < cnt && cnt <= UB;
+                s_c[lrow * UB + u] = ok ? __ldg(cols + lo + u) : 0;
+                s_a[lrow * UB + u] = ok ? __ldg(vals + lo + u) : Sc<T>::zero();
+            }
+            cnt_my = (cnt <= UB) ? cnt : -1;
+            __syncthreads();
+        } else {
+            const int start = lo + cp;
+            const int cnt = start < hi ? (hi - start + G - 1) / G : 0;
+            if (cnt <= UB) {
+                cnt_my = cnt;
 #pragma unroll
-                for (int v = 0; v < V; v++) acc[v] = Sc<T>::fma(a, w[v], acc[v]);
+                for (int u = 0; u < UB; u++) {
+                    if (u < cnt) {
+                        c_my[u] = __ldg(cols + start + u * G);
+                        a_my[u] = __ldg(vals + start + u * G);
+                    }
+                }
+            } else {
+                cnt_my = -1;
+            }
+        }
+    }
+    auto row_product = [&](int row, bool valid, auto load_w, T (&acc)[V]) {
+#pragma unroll
+        for (int v = 0; v < V; v++) acc[v] = Sc<T>::zero();
+        if (cnt_my >= 0) {
+            if constexpr (MULTI) {
+                if (valid) {
+                    // two half batches: 4 gathers (8 packs in phase 1) in flight per thread
+#pragma unroll
+                    for (int h = 0; h < UB; h += 4) {
+                        if (h < cnt_my) {
+                            T w[4][V];
+#pragma unroll
+                            for (int u = 0; u < 4; u++) load_w(s_c[lrow * UB + h + u], w[u]);   // padded: column 0, coefficient 0
+#pragma unroll
+                            for (int u = 0; u < 4; u++) {
+                                const T a = s_a[lrow * UB + h + u];
+#pragma unroll
+                                for (int v = 0; v < V; v++) acc[v] = Sc<T>::fma(a, w[u][v], acc[v]);
+                            }
+                        }
+                    }
+                }
+            } else {
+                T w[UB][V];
+#pragma unroll
+                for (int u = 0; u < UB; u++) load_w(c_my[u], w[u]);
+#pragma unroll
+                for (int u = 0; u < UB; u++) acc[0] = Sc<T>::fma(a_my[u], w[u][0], acc[0]);
             }
         } else {
-            for (int j = lo + cp; j < hi; j += G) {
-                const T a = __ldg(vals + j);
-                const int c = __ldg(cols + j);
-                T w[V];
-                load_w(c, w);
-                acc[0] = Sc<T>::fma(a, w[0], acc[0]);
+            int lo = 0, hi = 0;
+            if (valid) {
+                lo = __ldg(rowptr + row);
+                hi = __ldg(rowptr + row + 1);
             }
+            const int start = MULTI ? lo : lo + cp, stride = MULTI ? 1 : G;
+            for (int j0 = start; j0 < hi; j0 += 4 * stride) {
+                T a[4], w[4][V];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int j = j0 + u * stride;
+                    const bool ok = j < hi;
+                    const int jj = ok ? j : j0;
+                    load_w(__ldg(cols + jj), w[u]);
+                    a[u] = ok ? __ldg(vals + jj) : Sc<T>::zero();
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+#pragma unroll
+                    for (int v = 0; v < V; v++) acc[v] = Sc<T>::fma(a[u], w[u][v], acc[v]);
+                }
+            }
+        }
+        if constexpr (!MULTI) {
             // every lane of the warp takes part, whatever its row
             for (int off = G >> 1; off > 0; off >>= 1) {
                 if constexpr (Sc<T>::cplx) {
