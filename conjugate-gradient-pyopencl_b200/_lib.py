@@ -42,6 +42,9 @@ SIGNATURES = {
     "cgb200_shard_create": (_i, [ctypes.POINTER(_vp), _i, _i, _vp, _i, _i, _i, _ll, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
     "cgb200_shard_destroy": (_i, [_vp]),
     "cgb200_shard_local": (_vp, [_vp]),
+    "cgb200_shard_p2p_export": (_i, [_vp, _vp]),
+    "cgb200_shard_p2p_import": (_i, [_vp, _vp, _vp]),
+    "cgb200_shard_p2p_enable": (_i, [_vp, _i]),
     "cgb200_shard_set_stream": (_i, [_vp, _vp]),
     "cgb200_shard_set_option": (_i, [_vp, ctypes.c_char_p, _ll]),
     "cgb200_shard_solve": (_i, [_vp, _vp, _vp, _i, _d, ctypes.POINTER(_i), ctypes.POINTER(_d)]),

@@ -187,6 +187,7 @@ template <typename T> struct Engine {
         s.rr = (T *)take(kk * sizeof(T));
         s.tol = (const double *)take(sizeof(double));
         s.defer = 0;
+        s.peer = nullptr;
         s.partial = (T *)c->partial;
         s.hist = hist_cap > 0 ? c->d_hist : nullptr;
         s.hist_cap = hist_cap;

@@ -29,6 +29,96 @@ namespace cgb {
 enum : int { ST_ACTIVE = 0, ST_CONVERGED = 1, ST_BREAKDOWN = 2 };
 enum : int { TK_SPMV = 0, TK_UPDATE = 1, TK_INIT = 2 };
 
+// ---------------------------------------------------------------------------
+// Peer memory: the collectives of the row-block sharded solve done by the compute kernels
+// themselves through NVLink-mapped pointers (CUDA IPC), instead of separate NCCL launches.
+//
+//   all-reduce of a dot product   the last block of spmv_dot / update_xr stores its GPU's
+//       partial sum (+ a sequence number) straight into a slot in EVERY peer's memory, then
+//       waits until all peers' slots of the same sequence number have arrived in its own
+//       memory and adds them up in rank order -- every GPU gets the bit-identical sum, in
+//       about one NVLink round trip, inside the kernel that produced the partial.
+//   halo of d                     halo_push_kernel writes the entries a peer needs directly
+//       into that peer's d vector and then raises a flag there; the peer's SpMV waits for
+//       the flags after it has already started streaming its matrix tiles.
+//
+// The two dot products per iteration double as barriers, so neither the slots (double
+// buffered by sequence parity) nor the halo regions can be overwritten while still in use.
+// ---------------------------------------------------------------------------
+constexpr int PEER_MAX = 8;
+struct PeerSlot {              // 32 bytes
+    double re, im;
+    unsigned long long seq;
+    unsigned long long pad;
+};
+struct PeerComm {
+    int rank, world;
+    unsigned long long seq;                     // all-reduces completed on this GPU
+    unsigned long long halo_seq;                // halo exchanges started on this GPU
+    PeerSlot *slots[PEER_MAX];                  // slots[p]: rank p's [2][world] slot array (peer mapped; [rank] is local)
+    unsigned long long *halo_flag[PEER_MAX];    // halo_flag[p]: rank p's [world] arrival flags
+    void *d_peer[PEER_MAX];                     // rank p's direction vector [owned | halo]
+    long long remote_off[PEER_MAX];             // element offset in rank p's d where this rank's entries land
+    int send_off[PEER_MAX + 1];                 // this rank's send list is segmented by destination rank
+    int recv_from[PEER_MAX];                    // 1 if rank p sends halo entries to this rank
+    unsigned int push_ticket[PEER_MAX];
+};
+
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long *p) {
+    return *reinterpret_cast<const volatile unsigned long long *>(p);
+}
+
+// Called by ALL threads of ONE block per GPU.  Returns the sum over the GPUs (same bits everywhere).
+template <typename T> __device__ __forceinline__ T peer_allreduce(PeerComm *pc, T local) {
+    __shared__ double s_sum[2];
+    const int t = threadIdx.x;
+    const unsigned long long seq = pc->seq + 1;
+    const int parity = (int)(seq & 1);
+    if (t < pc->world) {
+        PeerSlot *dst = pc->slots[t] + (size_t)parity * pc->world + pc->rank;
+        double v[2] = {0.0, 0.0};
+        Sc<T>::to_double2(local, v);
+        dst->re = v[0];
+        dst->im = v[1];
+        __threadfence_system();
+        *reinterpret_cast<volatile unsigned long long *>(&dst->seq) = seq;
+    }
+    if (t < pc->world) {
+        const PeerSlot *src = pc->slots[pc->rank] + (size_t)parity * pc->world + t;
+        unsigned long long spins = 0;
+        while (ld_volatile_u64(&src->seq) != seq)
+            if (++spins > (1ull << 31)) __trap();
+    }
+    __syncthreads();
+    if (t == 0) {
+        __threadfence_system();
+        double re = 0.0, im = 0.0;
+        for (int p = 0; p < pc->world; p++) {
+            const volatile PeerSlot *src = pc->slots[pc->rank] + (size_t)parity * pc->world + p;
+            re += src->re;
+            im += src->im;
+        }
+        s_sum[0] = re;
+        s_sum[1] = im;
+        pc->seq = seq;
+    }
+    __syncthreads();
+    if constexpr (Sc<T>::cplx) return Sc<T>::make((typename Sc<T>::real)s_sum[0], (typename Sc<T>::real)s_sum[1]);
+    else return (T)s_sum[0];
+}
+
+// Waits (one thread per block) until every sending peer's entries of the current exchange have landed.
+__device__ __forceinline__ void peer_wait_halo(const PeerComm *pc) {
+    const unsigned long long want = pc->halo_seq;
+    for (int p = 0; p < pc->world; p++) {
+        if (!pc->recv_from[p]) continue;
+        unsigned long long spins = 0;
+        while (ld_volatile_u64(pc->halo_flag[pc->rank] + p) < want)
+            if (++spins > (1ull << 31)) __trap();
+    }
+    __threadfence_system();
+}
+
 // Device-resident scalar state of one solve (all arrays have k entries).
 template <typename T> struct CgScalars {
     T *dq;              // d.q of the current iteration
@@ -45,6 +135,7 @@ template <typename T> struct CgScalars {
     int hist_cap;
     const double *tol;  // in device memory, so that one captured graph serves every tolerance
     T *rr;              // [k] this device's part of r.r when `defer` is set
+    PeerComm *peer;     // non-NULL: the dot products are all-reduced inside the kernels through peer memory
     int defer;          // row-block sharded solve: the dot products are only partial sums here; the
                         // bookkeeping runs in init_bookkeep_kernel / update_bookkeep_kernel after the
                         // all-reduce over the devices (dq is all-reduced in place)
@@ -100,6 +191,30 @@ template <typename T> __global__ void update_bookkeep_kernel(int k, CgScalars<T>
     __syncthreads();
     if (threadIdx.x == 0) *sc.it = it1;
 }
+
+// blockIdx.y = destination rank.  Writes this rank's entries that rank needs straight into its d vector
+// over NVLink; the last block to finish for that destination raises the arrival flag there.
+template <typename T>
+__global__ void __launch_bounds__(256)
+halo_push_kernel(PeerComm *pc, const int *__restrict__ idx, const T *__restrict__ d) {
+    const int p = blockIdx.y;
+    const int lo = pc->send_off[p], hi = pc->send_off[p + 1];
+    if (hi <= lo) return;
+    T *dst = reinterpret_cast<T *>(pc->d_peer[p]) + pc->remote_off[p];
+    for (int i = lo + blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += gridDim.x * blockDim.x) dst[i - lo] = d[idx[i]];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned prev = atomicAdd(&pc->push_ticket[p], 1u);
+        if (prev == gridDim.x - 1) {
+            pc->push_ticket[p] = 0;
+            __threadfence_system();
+            *reinterpret_cast<volatile unsigned long long *>(pc->halo_flag[p] + pc->rank) = pc->halo_seq;
+        }
+    }
+}
+// one thread: a new exchange starts (must precede halo_push_kernel in stream order)
+__global__ void halo_begin_kernel(PeerComm *pc) { pc->halo_seq = pc->halo_seq + 1; }
 
 // Packs the entries of d that peer devices need (their halo) into one send buffer.
 template <typename T>
@@ -688,6 +803,13 @@ spmv_tma_rows_kernel(int ntiles, const SpmvTile *__restrict__ tiles, const T *__
     SpmvTile tl_next = {0, 0, 0, 0};
     if (count > 0) tl_next = tile_of(0);
 
+    // row-block shards: the matrix tiles above are already in flight; now make sure the peers' entries of
+    // x (the halo) have landed before the first gather
+    if (sc.peer && sc.peer->world > 1) {
+        if (t == 0) peer_wait_halo(sc.peer);
+        __syncthreads();
+    }
+
     for (int i = 0; i < count; i++) {
         const SpmvTile tl = tl_next;
         if (i + 1 < count) tl_next = tile_of(i + 1);
@@ -773,8 +895,10 @@ spmv_tma_rows_kernel(int ntiles, const SpmvTile *__restrict__ tiles, const T *__
         block_col_reduce<T, 1>(dot, 1, red);
         if (publish_and_arrive<T, 1>(red, 1, 1, sc.partial, sc.ticket + TK_SPMV)) {
             grid_col_reduce<T, 1>(sc.partial, 1, 1, 1, red);
+            T total = red[0];
+            if (sc.peer) total = peer_allreduce<T>(sc.peer, red[0]);    // sum over the GPUs, inside this kernel
             if (t == 0) {
-                sc.dq[0] = red[0];
+                sc.dq[0] = total;
                 sc.ticket[TK_SPMV] = 0;
             }
         }
@@ -916,13 +1040,15 @@ init_kernel(size_t npacks, size_t nelem, int k, int kv, const T *b /* may alias 
     block_col_reduce<T, V>(acc, kv, smem);
     if (publish_and_arrive<T, V>(smem, kv, k, sc.partial, sc.ticket + TK_INIT)) {
         grid_col_reduce<T, V>(sc.partial, kv, kv, k, smem);
+        T total0 = smem[0];
+        if (sc.peer) total0 = peer_allreduce<T>(sc.peer, smem[0]);     // k == 1: sum over the GPUs
         if (t < kv) {
 #pragma unroll
             for (int v = 0; v < V; v++) {
                 const int c = t * V + v;
                 if (c < k) {
                     if (sc.defer) sc.rr[c] = smem[t * V + v];
-                    else init_bookkeep<T>(sc, c, smem[t * V + v]);
+                    else init_bookkeep<T>(sc, c, sc.peer ? total0 : smem[t * V + v]);
                 }
             }
         }
@@ -993,13 +1119,15 @@ update_xr_kernel(size_t npacks, size_t nelem, int k, int kv, const T *__restrict
     if (publish_and_arrive<T, V>(smem, kv, k, sc.partial, sc.ticket + TK_UPDATE)) {
         grid_col_reduce<T, V>(sc.partial, kv, kv, k, smem);
         const int it1 = *sc.it + 1;
+        T total0 = smem[0];
+        if (sc.peer) total0 = peer_allreduce<T>(sc.peer, smem[0]);     // k == 1: sum over the GPUs
         if (t < kv) {
 #pragma unroll
             for (int v = 0; v < V; v++) {
                 const int c = t * V + v;
                 if (c < k) {
                     if (sc.defer) sc.rr[c] = smem[t * V + v];
-                    else update_bookkeep<T>(sc, c, k, it1, smem[t * V + v]);
+                    else update_bookkeep<T>(sc, c, k, it1, sc.peer ? total0 : smem[t * V + v]);
                 }
             }
         }

@@ -88,7 +88,16 @@ struct cgb200_shard_ctx {
     int *d_send_idx = nullptr;
     void *d_sendbuf = nullptr;
     long long exchanges = 0, allreduces = 0;
+    // peer-memory collectives (CUDA IPC): see PeerComm in kernels.cuh
+    bool p2p = false;
+    void *p2p_buf = nullptr;             // this rank's slots + arrival flags, mapped by every peer
+    PeerComm *d_peer = nullptr;          // device copy of the PeerComm
+    std::vector<void *> opened;          // peers' mappings to close
+    int max_send = 0;
 };
+
+static constexpr size_t P2P_SLOTS_BYTES = 2 * PEER_MAX * sizeof(PeerSlot);
+static constexpr size_t P2P_BUF_BYTES = P2P_SLOTS_BYTES + PEER_MAX * sizeof(unsigned long long) + 256;
 
 template <typename T> struct ShardEngine {
     using E = Engine<T>;
@@ -98,8 +107,19 @@ template <typename T> struct ShardEngine {
     // halo of v (v has n_owned + n_halo entries): pack what the peers need, one grouped send/recv
     static int exchange(cgb200_shard_ctx *sh, T *v) {
         cgb200_ctx *c = sh->m;
-        NcclApi *N = nccl_api();
         if (sh->world == 1) return 0;
+        if (sh->p2p) {
+            // entries go straight into the peers' d vectors over NVLink; the consumer (SpMV) waits for the flags
+            halo_begin_kernel<<<1, 1, 0, c->stream>>>(sh->d_peer);
+            if (sh->send_total > 0) {
+                const int nb = std::max(1, std::min(32, (sh->max_send + 2047) / 2048));
+                halo_push_kernel<T><<<dim3(nb, sh->world), 256, 0, c->stream>>>(sh->d_peer, sh->d_send_idx, v);
+            }
+            c->launches += 2;
+            sh->exchanges++;
+            return 0;
+        }
+        NcclApi *N = nccl_api();
         if (sh->send_total > 0) {
             const int grid = std::min(c->sm_count * 8, (sh->send_total + 255) / 256);
             pack_kernel<T><<<grid, 256, 0, c->stream>>>(sh->send_total, sh->d_send_idx, v, (T *)sh->d_sendbuf);
@@ -121,7 +141,7 @@ template <typename T> struct ShardEngine {
     }
 
     static int allreduce(cgb200_shard_ctx *sh, T *buf, int k) {
-        if (sh->world == 1) return 0;
+        if (sh->world == 1 || sh->p2p) return 0;      // p2p: done inside the producing kernel
         NC(nccl_api()->AllReduce(buf, buf, (size_t)k * NCOMP, nccl_type(), ncclSum, sh->comm, sh->m->stream));
         sh->allreduces++;
         return 0;
@@ -134,9 +154,11 @@ template <typename T> struct ShardEngine {
         TRY(allreduce(sh, sc.dq, 1));
         if (g.V == 1) TRY(E::template launch_update_xr<1>(c, 1, g, sc));            // local r.r -> sc.rr
         else TRY(E::template launch_update_xr<E::VW>(c, 1, g, sc));
-        TRY(allreduce(sh, sc.rr, 1));
-        update_bookkeep_kernel<T><<<1, 32, 0, c->stream>>>(1, sc);
-        c->launches++;
+        if (sc.defer) {
+            TRY(allreduce(sh, sc.rr, 1));
+            update_bookkeep_kernel<T><<<1, 32, 0, c->stream>>>(1, sc);
+            c->launches++;
+        }
         if (g.V == 1) TRY(E::template launch_update_d<1>(c, 1, g, sc));
         else TRY(E::template launch_update_d<E::VW>(c, 1, g, sc));
         return 0;
@@ -147,7 +169,10 @@ template <typename T> struct ShardEngine {
         cgb200_ctx *c = sh->m;
         TRY(E::ensure_workspace(c, 1));
         CgScalars<T> sc = E::scalars(c, 1, tol, 0);
-        sc.defer = 1;
+        sc.defer = sh->p2p ? 0 : 1;                    // p2p: reduced and book-kept inside the kernels
+        sc.peer = sh->p2p ? sh->d_peer : nullptr;
+        if (sh->p2p && c->spmv_variant != 0 && c->spmv_variant != 6)
+            return fail(CGB200_ERR_UNSUPPORTED, "peer-memory collectives need the default SpMV schedule (spmv_variant 0)");
         const typename E::VecGeom g = E::geom(c, 1);
         const size_t bytes = (size_t)sh->n_owned * sizeof(T);
 
@@ -162,9 +187,11 @@ template <typename T> struct ShardEngine {
         CU(cudaMemcpyAsync(c->d, b, bytes, cudaMemcpyDefault, c->stream));
         if (g.V == 1) TRY(E::template launch_init<1>(c, 1, g, (const T *)c->d, (const T *)c->q, (T *)c->r, (T *)c->d, sc));
         else TRY(E::template launch_init<E::VW>(c, 1, g, (const T *)c->d, (const T *)c->q, (T *)c->r, (T *)c->d, sc));
-        TRY(allreduce(sh, sc.rr, 1));
-        init_bookkeep_kernel<T><<<1, 32, 0, c->stream>>>(1, sc);
-        c->launches++;
+        if (sc.defer) {
+            TRY(allreduce(sh, sc.rr, 1));
+            init_bookkeep_kernel<T><<<1, 32, 0, c->stream>>>(1, sc);
+            c->launches++;
+        }
         CU(cudaEventRecord(c->ev[2], c->stream));
         DBG("rank %d: init enqueued (maxit %d tol %g graph %d)", sh->rank, maxit, tol, c->use_graph);
 
@@ -173,7 +200,8 @@ template <typename T> struct ShardEngine {
         if (c->use_graph && maxit >= chunk) {
             // captured once per shard (the tolerance lives in device memory); re-captured only when the
             // chunk length or the stream changed
-            if (!c->graph || c->graph_k != -1 || c->graph_chunk_built != chunk) {
+            const int gkey = sh->p2p ? -2 : -1;
+            if (!c->graph || c->graph_k != gkey || c->graph_chunk_built != chunk) {
                 drop_graph(c);
                 cudaGraph_t gr = nullptr;
                 const long long before = c->launches;
@@ -189,7 +217,7 @@ template <typename T> struct ShardEngine {
                 ce = cudaGraphInstantiate(&c->graph, gr, 0);
                 cudaGraphDestroy(gr);
                 if (ce != cudaSuccess) return fail(CGB200_ERR_CUDA, "graph instantiate: %s", cudaGetErrorString(ce));
-                c->graph_k = -1;               // marks a shard graph (never matches a plain solve's k)
+                c->graph_k = gkey;             // marks a shard graph (never matches a plain solve's k)
                 c->graph_chunk_built = chunk;
                 DBG("rank %d: graph ready (%lld nodes)", sh->rank, c->graph_nodes);
             }
@@ -322,6 +350,9 @@ int cgb200_shard_destroy(cgb200_shard sh) {
         DeviceGuard guard(sh->m->device);
         if (sh->m->stream) cudaStreamSynchronize(sh->m->stream);
         drop_graph(sh->m);      // a captured graph holds NCCL resources: it must go before the communicator
+        for (void *p : sh->opened) cudaIpcCloseMemHandle(p);
+        if (sh->d_peer) cudaFree(sh->d_peer);
+        if (sh->p2p_buf) cudaFree(sh->p2p_buf);
         if (sh->comm) nccl_api()->CommDestroy(sh->comm);
         if (sh->d_send_idx) cudaFree(sh->d_send_idx);
         if (sh->d_sendbuf) cudaFree(sh->d_sendbuf);
@@ -332,6 +363,68 @@ int cgb200_shard_destroy(cgb200_shard sh) {
 }
 
 cgb200_handle cgb200_shard_local(cgb200_shard sh) { return sh ? sh->m : nullptr; }
+
+int cgb200_shard_p2p_export(cgb200_shard sh, void *out128) {
+    if (!sh || !out128) return fail(CGB200_ERR_ARG, "NULL argument");
+    if (sh->world > PEER_MAX) return fail(CGB200_ERR_UNSUPPORTED, "peer-memory collectives support up to %d ranks", PEER_MAX);
+    cgb200_ctx *c = sh->m;
+    DeviceGuard guard(c->device);
+    TRY(DISPATCH(c, E::ensure_workspace(c, 1)));
+    if (!sh->p2p_buf) {
+        CU(cudaMalloc(&sh->p2p_buf, P2P_BUF_BYTES));
+        CU(cudaMemset(sh->p2p_buf, 0, P2P_BUF_BYTES));
+    }
+    cudaIpcMemHandle_t h[2];
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+    CU(cudaIpcGetMemHandle(&h[0], sh->p2p_buf));
+    CU(cudaIpcGetMemHandle(&h[1], c->d));
+    memcpy(out128, h, sizeof(h));
+    return CGB200_OK;
+}
+
+int cgb200_shard_p2p_import(cgb200_shard sh, const void *all_handles, const long long *remote_off) {
+    if (!sh || !all_handles || !remote_off) return fail(CGB200_ERR_ARG, "NULL argument");
+    if (!sh->p2p_buf) return fail(CGB200_ERR_ARG, "call cgb200_shard_p2p_export first");
+    cgb200_ctx *c = sh->m;
+    DeviceGuard guard(c->device);
+    PeerComm pc;
+    memset(&pc, 0, sizeof(pc));
+    pc.rank = sh->rank;
+    pc.world = sh->world;
+    const cudaIpcMemHandle_t *h = (const cudaIpcMemHandle_t *)all_handles;
+    sh->max_send = 0;
+    for (int p = 0; p < sh->world; p++) {
+        void *buf = sh->p2p_buf, *dvec = c->d;
+        if (p != sh->rank) {
+            CU(cudaIpcOpenMemHandle(&buf, h[2 * p], cudaIpcMemLazyEnablePeerAccess));
+            sh->opened.push_back(buf);
+            CU(cudaIpcOpenMemHandle(&dvec, h[2 * p + 1], cudaIpcMemLazyEnablePeerAccess));
+            sh->opened.push_back(dvec);
+        }
+        pc.slots[p] = (PeerSlot *)buf;
+        pc.halo_flag[p] = (unsigned long long *)((char *)buf + P2P_SLOTS_BYTES);
+        pc.d_peer[p] = dvec;
+        pc.remote_off[p] = remote_off[p];
+        pc.send_off[p] = sh->send_off[p];
+        pc.recv_from[p] = sh->recv_counts[p] > 0;
+        sh->max_send = std::max(sh->max_send, sh->send_counts[p]);
+    }
+    pc.send_off[sh->world] = sh->send_total;
+    for (int p = sh->world; p < PEER_MAX; p++) pc.send_off[p + 1] = sh->send_total;
+    if (!sh->d_peer) CU(cudaMalloc((void **)&sh->d_peer, sizeof(PeerComm)));
+    CU(cudaMemcpy(sh->d_peer, &pc, sizeof(pc), cudaMemcpyHostToDevice));
+    drop_graph(c);
+    sh->p2p = true;
+    return CGB200_OK;
+}
+
+int cgb200_shard_p2p_enable(cgb200_shard sh, int on) {
+    if (!sh) return fail(CGB200_ERR_ARG, "NULL shard");
+    if (on && !sh->d_peer) return fail(CGB200_ERR_ARG, "peer memory was not set up (export / import)");
+    drop_graph(sh->m);
+    sh->p2p = on != 0;
+    return CGB200_OK;
+}
 
 int cgb200_shard_set_stream(cgb200_shard sh, void *cuda_stream) {
     if (!sh) return fail(CGB200_ERR_ARG, "NULL shard");

@@ -178,7 +178,7 @@ def plan_row_block(indptr, indices, data, bounds, rank, exchange=None):
 class ShardedMatrix:
     """A row block of A resident on this rank's GPU, plus the NCCL communicator (`cgb200_shard_create`)."""
 
-    def __init__(self, plan, device=None, dtype=None):
+    def __init__(self, plan, device=None, dtype=None, p2p=True):
         import torch
         import torch.distributed as dist
         self.plan = plan
@@ -201,6 +201,27 @@ class ShardedMatrix:
             _lib.DTYPE_CODE[np.dtype(self.dtype)], _lib.ptr(np.ascontiguousarray(plan.send_counts)),
             _lib.ptr(np.ascontiguousarray(plan.send_idx)), _lib.ptr(np.ascontiguousarray(plan.recv_counts))))
         self._h = h
+        self.p2p = False
+        if p2p and 1 < plan.world <= 8:
+            self._setup_peer_memory(dist)
+
+    def _setup_peer_memory(self, dist):
+        """CUDA-IPC handles of every rank's exchange buffer and direction vector, all-gathered; afterwards the
+        halo and the dot-product all-reduces go through NVLink-mapped pointers inside the kernels."""
+        plan, L = self.plan, _lib.lib()
+        mine = np.zeros(128, dtype=np.uint8)
+        _lib.check(L.cgb200_shard_p2p_export(self._h, _lib.ptr(mine)))
+        recv_off = np.concatenate([[0], np.cumsum(plan.recv_counts)[:-1]]).astype(np.int64)
+        box = [None] * plan.world
+        dist.all_gather_object(box, (mine.tobytes(), int(plan.n_owned), recv_off.tolist()))
+        handles = np.frombuffer(b"".join(h for h, _, _ in box), dtype=np.uint8).copy()
+        remote_off = np.array([box[p][1] + box[p][2][plan.rank] for p in range(plan.world)], dtype=np.int64)
+        _lib.check(L.cgb200_shard_p2p_import(self._h, _lib.ptr(handles), _lib.ptr(remote_off)))
+        self.p2p = True
+
+    def enable_peer_memory(self, on=True):
+        _lib.check(_lib.lib().cgb200_shard_p2p_enable(self._h, 1 if on else 0))
+        self.p2p = bool(on)
 
     def close(self):
         if getattr(self, "_h", None):

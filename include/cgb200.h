@@ -165,6 +165,17 @@ CGB200_API cgb200_handle cgb200_shard_local(cgb200_shard sh);
 CGB200_API int cgb200_shard_set_stream(cgb200_shard sh, void *cuda_stream);
 CGB200_API int cgb200_shard_set_option(cgb200_shard sh, const char *key, long long value);
 
+/* Peer-memory collectives (optional, <= 8 ranks of one NVLink domain).  With them the halo entries are
+ * written straight into the peers' vectors and the two dot products are all-reduced by the compute kernels
+ * themselves through CUDA-IPC mapped pointers: no NCCL launch inside the iteration.
+ *   export: this rank's two 64-byte IPC handles (exchange buffer, direction vector) -> out128
+ *   import: all ranks' handles (world x 128 bytes, rank order) and, per peer p, the element offset in
+ *           p's direction vector where this rank's entries land (n_owned_p + p's receive offset for us)
+ *   enable: switch between peer memory (1) and NCCL (0) afterwards */
+CGB200_API int cgb200_shard_p2p_export(cgb200_shard sh, void *out128);
+CGB200_API int cgb200_shard_p2p_import(cgb200_shard sh, const void *all_handles, const long long *remote_off);
+CGB200_API int cgb200_shard_p2p_enable(cgb200_shard sh, int on);
+
 /* Collective: every rank calls it with its slice of b and x (host or device pointers).
  * Same semantics as cgb200_solve() with k = 1; iterations / relres are global values. */
 CGB200_API int cgb200_shard_solve(cgb200_shard sh, const void *b_owned, void *x_owned, int max_iterations,

@@ -37,9 +37,16 @@ for name, A, b, tolv in (("lap3d24", P.laplace3d(24), np.ones(24 ** 3), 1e-10),
     rb, re = bounds[rank], bounds[rank + 1]
     log(name, "plan done; creating shard", plan.n_owned, plan.n_halo)
     M = sharded.ShardedMatrix(plan, device=lr)
-    log(name, "shard created; plain-launch solve")
+    log(name, "shard created; plain-launch solve", "p2p" if M.p2p else "nccl")
     M.set_option("use_graph", 0)
     x, info = M.solve(b[rb:re].astype(A.dtype), max_iterations=60)
+    if world > 1:
+        M.enable_peer_memory(False)
+        xn, _ = M.solve(b[rb:re].astype(A.dtype), max_iterations=60)
+        M.enable_peer_memory(True)
+        en = float(np.linalg.norm(x - xn) / np.linalg.norm(xn))
+        log(name, "peer-memory vs NCCL collectives:", en)
+        assert en < 1e-12, en
     log(name, "plain solve done; graph solve")
     M.set_option("use_graph", 1)
     xg, _ = M.solve(b[rb:re].astype(A.dtype), max_iterations=60)
@@ -77,7 +84,11 @@ faulthandler.cancel_dump_traceback_later()
 faulthandler.dump_traceback_later(200, exit=True)
 bt = torch.ones(re - rb, dtype=torch.float64, device="cuda")
 xt = torch.zeros_like(bt)
-for use_graph in (1, 0):
+for use_graph, p2p in ((1, 1), (1, 0), (0, 1)):
+    if world > 1:
+        M.enable_peer_memory(bool(p2p))
+    elif not p2p:
+        continue
     M.set_option("use_graph", use_graph)
     for _ in range(2):
         xt.zero_(); M.solve(bt, xt, max_iterations=iters)
@@ -88,7 +99,7 @@ for use_graph in (1, 0):
         xt.zero_(); _, info = M.solve(bt, xt, max_iterations=iters); ts.append(info["timing_ms"]["iterations"])
     t = torch.tensor([min(ts)], device="cuda", dtype=torch.float64)
     if world > 1: dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    out[f"lap{N3}_graph{use_graph}"] = dict(ms_per_iter=float(t.item()) / iters, its_per_s=iters / float(t.item()) * 1e3,
+    out[f"lap{N3}_graph{use_graph}_p2p{p2p}"] = dict(ms_per_iter=float(t.item()) / iters, its_per_s=iters / float(t.item()) * 1e3,
                                             n_owned=plan.n_owned, n_halo=plan.n_halo, gen_s=tgen)
 M.close()
 if rank == 0:
