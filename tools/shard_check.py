@@ -101,6 +101,7 @@ for use_graph, p2p in ((1, 1), (1, 0), (0, 1)):
     if world > 1: dist.all_reduce(t, op=dist.ReduceOp.MAX)
     out[f"lap{N3}_graph{use_graph}_p2p{p2p}"] = dict(ms_per_iter=float(t.item()) / iters, its_per_s=iters / float(t.item()) * 1e3,
                                             n_owned=plan.n_owned, n_halo=plan.n_halo, gen_s=tgen)
+out["local_kernels_us"] = {nm: round(1e3 * M.time_kernel(nm, reps=100), 2) for nm in ("spmv_dot", "update_xr", "update_d")}
 M.close()
 if rank == 0:
     print(json.dumps({"world": world, **out}))
