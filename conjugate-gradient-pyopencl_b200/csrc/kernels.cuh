@@ -64,8 +64,13 @@ struct PeerComm {
     unsigned int push_ticket[PEER_MAX];
 };
 
-__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long *p) {
-    return *reinterpret_cast<const volatile unsigned long long *>(p);
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
 // Called by ALL threads of ONE block per GPU.  Returns the sum over the GPUs (same bits everywhere).
@@ -75,23 +80,20 @@ template <typename T> __device__ __forceinline__ T peer_allreduce(PeerComm *pc, 
     const unsigned long long seq = pc->seq + 1;
     const int parity = (int)(seq & 1);
     if (t < pc->world) {
+        // value, then the sequence number with release semantics: whoever acquires the number sees the value
         PeerSlot *dst = pc->slots[t] + (size_t)parity * pc->world + pc->rank;
         double v[2] = {0.0, 0.0};
         Sc<T>::to_double2(local, v);
         dst->re = v[0];
         dst->im = v[1];
-        __threadfence_system();
-        *reinterpret_cast<volatile unsigned long long *>(&dst->seq) = seq;
-    }
-    if (t < pc->world) {
+        st_release_sys_u64(&dst->seq, seq);
         const PeerSlot *src = pc->slots[pc->rank] + (size_t)parity * pc->world + t;
         unsigned long long spins = 0;
-        while (ld_volatile_u64(&src->seq) != seq)
+        while (ld_acquire_sys_u64(&src->seq) != seq)
             if (++spins > (1ull << 31)) __trap();
     }
     __syncthreads();
     if (t == 0) {
-        __threadfence_system();
         double re = 0.0, im = 0.0;
         for (int p = 0; p < pc->world; p++) {
             const volatile PeerSlot *src = pc->slots[pc->rank] + (size_t)parity * pc->world + p;
@@ -108,15 +110,16 @@ template <typename T> __device__ __forceinline__ T peer_allreduce(PeerComm *pc, 
 }
 
 // Waits (one thread per block) until every sending peer's entries of the current exchange have landed.
+// An exchange is identified by the number of all-reduces completed so far (+1): every exchange of the
+// solve is separated from the next by at least one all-reduce, and all GPUs count them in lockstep.
 __device__ __forceinline__ void peer_wait_halo(const PeerComm *pc) {
-    const unsigned long long want = pc->halo_seq;
+    const unsigned long long want = pc->seq + 1;
     for (int p = 0; p < pc->world; p++) {
         if (!pc->recv_from[p]) continue;
         unsigned long long spins = 0;
-        while (ld_volatile_u64(pc->halo_flag[pc->rank] + p) < want)
+        while (ld_acquire_sys_u64(pc->halo_flag[pc->rank] + p) < want)
             if (++spins > (1ull << 31)) __trap();
     }
-    __threadfence_system();
 }
 
 // Device-resident scalar state of one solve (all arrays have k entries).
@@ -209,12 +212,10 @@ halo_push_kernel(PeerComm *pc, const int *__restrict__ idx, const T *__restrict_
         if (prev == gridDim.x - 1) {
             pc->push_ticket[p] = 0;
             __threadfence_system();
-            *reinterpret_cast<volatile unsigned long long *>(pc->halo_flag[p] + pc->rank) = pc->halo_seq;
+            st_release_sys_u64(pc->halo_flag[p] + pc->rank, pc->seq + 1);
         }
     }
 }
-// one thread: a new exchange starts (must precede halo_push_kernel in stream order)
-__global__ void halo_begin_kernel(PeerComm *pc) { pc->halo_seq = pc->halo_seq + 1; }
 
 // Packs the entries of d that peer devices need (their halo) into one send buffer.
 template <typename T>

@@ -110,12 +110,11 @@ template <typename T> struct ShardEngine {
         if (sh->world == 1) return 0;
         if (sh->p2p) {
             // entries go straight into the peers' d vectors over NVLink; the consumer (SpMV) waits for the flags
-            halo_begin_kernel<<<1, 1, 0, c->stream>>>(sh->d_peer);
             if (sh->send_total > 0) {
                 const int nb = std::max(1, std::min(32, (sh->max_send + 2047) / 2048));
                 halo_push_kernel<T><<<dim3(nb, sh->world), 256, 0, c->stream>>>(sh->d_peer, sh->d_send_idx, v);
+                c->launches++;
             }
-            c->launches += 2;
             sh->exchanges++;
             return 0;
         }
