@@ -16,8 +16,15 @@ driver default, p_h-PY_C-CL.py:3553), i.e. 256 CG iterations on one batch of k r
           bytes B_spmv = nnz(v+4) + 4(n+1) + 2knv against MEASURED_PEAKS.json.
   cpu_baseline  the oracle port (oracle/cpu_ref.c, OpenMP, all host cores) on a bounded sample.
 
-N > 1 (torchrun, one rank per GPU): the reference's own multi-GPU mode -- right-hand sides split
-across GPUs, matrix replicated, no collective (p_h-PY_C-CL-multi-GPU.py:2123-2181).
+Default workload: C4, the 3-D 7-point Laplacian 300^3 (27 M unknowns, f64) -- the configuration
+BASELINE.json's metric ("... at 1/2/4/8 B200") and scaling target are quoted on; it fits one GPU, so the
+same system is measured at every N (strong scaling).  At N = 1 the line also carries the C2 figures
+(complex-symmetric Helmholtz FE 1024^2, c128) under "also".
+
+N > 1 (torchrun, one rank per GPU): the CSR matrix is row-block partitioned (whole z-planes per rank);
+every iteration moves only the halo of d peer to peer over NVLink and all-reduces the two dot scalars
+(--mode rhs-split: the reference's own multi-GPU mode, RHS columns split, no collective,
+p_h-PY_C-CL-multi-GPU.py:2123-2181).
 """
 import argparse
 import json
@@ -140,6 +147,7 @@ def measured_peak():
 
 def calibrate(cpu_ref, A, B, k):
     """Seconds per CG iteration of the oracle on this host (after one warm call)."""
+    cpu_ref.lib().cpu_ref_set_threads(os.cpu_count() or 1)      # torchrun exports OMP_NUM_THREADS=1
     cpu_ref.cg(A.data, A.indptr, A.indices, B, k=k, iters=1)
     t0 = time.perf_counter()
     cpu_ref.cg(A.data, A.indptr, A.indices, B, k=k, iters=7)
@@ -199,10 +207,47 @@ def config_of(args, wl, A, k, dtype, world, n=None, nnz=None):
             "iters_per_step": ITERS_PER_STEP,
             "parallelism": "single GPU" if world == 1 else
                            (f"rhs-split x{world} (matrix replicated, one RHS per GPU, no collective)" if args.mode == "rhs-split"
-                            else f"row-block x{world} (halo of d by NCCL send/recv over NVLink + 2 all-reduces per iteration)"),
+                            else f"row-block x{world}: halo of d pushed peer to peer over NVLink, the 2 dot products per "
+                                 f"iteration all-reduced inside the kernels through peer memory"),
             "l2": "no L2 flush: matrix + vectors per iteration exceed the 126 MB L2"
                   if A.nnz * (A.dtype.itemsize + 4) > 126e6 else
                   "working set fits the 126 MB L2 (latency-bound config); no flush between iterations"}
+
+
+def also_single_gpu(name, dtype, peak, tdt_of, stream):
+    """Short resident-data measurement of another BASELINE config on this GPU (value + kernel rooflines)."""
+    import torch
+    import cg_b200
+    import cg_b200.problems as P
+    A, B = make_problem(name, dtype, 1)
+    n, nnz = A.shape[0], A.nnz
+    v = P.DTYPES[dtype][2]
+    b_spmv, b_iter = P.algorithmic_bytes(n, nnz, 1, dtype)
+    M = cg_b200.Matrix.from_scipy(A)
+    M.set_stream(stream.cuda_stream)
+    with torch.cuda.stream(stream):
+        b_dev = torch.from_numpy(B).to("cuda")
+        x_dev = torch.zeros(n, dtype=tdt_of[dtype], device="cuda")
+        for _ in range(3):
+            x_dev.zero_()
+            M.solve(b_dev, x=x_dev, max_iterations=ITERS_PER_STEP)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(10):
+            x_dev.zero_()
+            info = M.solve(b_dev, x=x_dev, max_iterations=ITERS_PER_STEP)[1]
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        out = {"workload": WORKLOADS[name]["desc"], "n": int(n), "nnz": int(nnz), "dtype": dtype,
+               "value": ITERS_PER_STEP / (ms / 1e3), "unit": "iterations/s", "ms_per_step": ms, "kernels": {}}
+        for kn, nb in (("spmv_dot", b_spmv), ("update_xr", 6 * n * v), ("update_d", 3 * n * v)):
+            kms = M.time_kernel(kn, reps=100)
+            out["kernels"][kn] = {"ms": kms, "gbs": nb / kms / 1e6, "frac": nb / kms / 1e6 / peak}
+        it_ms = info.timing_ms["iterations"] / ITERS_PER_STEP
+        out["iteration"] = {"ms": it_ms, "gbs": b_iter / it_ms / 1e6, "frac": b_iter / it_ms / 1e6 / peak}
+    M.close()
+    return out
 
 
 def run_row_block(args, wl, dtype, rank, local_rank, world):
@@ -336,7 +381,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-also", action="store_true", help="N = 1: skip the extra C2 (Helmholtz, complex) figures")
     ap.add_argument("--dtype", default=None, choices=["f32", "f64", "c64", "c128"])
     ap.add_argument("--k", type=int, default=None)
     ap.add_argument("--mode", default="row-block", choices=["row-block", "rhs-split"],
@@ -383,7 +429,8 @@ def main():
     b_spmv, b_iter = P.algorithmic_bytes(n, nnz, k, dtype)
 
     stream = torch.cuda.Stream()
-    tdt = {"f32": torch.float32, "f64": torch.float64, "c64": torch.complex64, "c128": torch.complex128}[dtype]
+    tdt_of = {"f32": torch.float32, "f64": torch.float64, "c64": torch.complex64, "c128": torch.complex128}
+    tdt = tdt_of[dtype]
     M = cg_b200.Matrix.from_scipy(A, device=local_rank)
     M.set_stream(stream.cuda_stream)
     for kv in args.opt:
@@ -504,6 +551,8 @@ def main():
             "solve_phases_ms": timing,
         }
         line["iteration"]["spmv_pct_of_nominal_8TBs"] = 100.0 * kernels["spmv_dot"]["gbs"] / 8000.0
+        if world == 1 and not args.no_also and args.workload != "c2":
+            line["also"] = {"c2_c128": also_single_gpu("c2", "c128", peak, tdt_of, stream)}
         print(json.dumps(line), flush=True)
     M.close()
     if world > 1:

@@ -39,7 +39,7 @@ SIGNATURES = {
     "cgb200_cg": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _i]),
     "cgb200_clear_cache": (_i, []),
     "cgb200_nccl_unique_id": (_i, [_vp]),
-    "cgb200_shard_create": (_i, [ctypes.POINTER(_vp), _i, _i, _vp, _i, _i, _i, _ll, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
+    "cgb200_shard_create": (_i, [ctypes.POINTER(_vp), _i, _i, _vp, _i, _i, _i, _ll, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
     "cgb200_shard_destroy": (_i, [_vp]),
     "cgb200_shard_local": (_vp, [_vp]),
     "cgb200_shard_p2p_export": (_i, [_vp, _vp]),

@@ -73,6 +73,8 @@ struct cgb200_ctx {
     // CSR-stream schedule (k = 1): tiles of whole rows / chunks of long rows
     void *d_tiles = nullptr, *d_long = nullptr, *d_chunk_sum = nullptr;
     int ntiles = 0, nlong = 0, nslots = 0;
+    int ntiles_interior = 0;                 // tiles [0, ntiles_interior) touch no halo column (row-block shards)
+    std::vector<unsigned char> row_boundary;  // per row: references a halo column (set by the shard layer)
     uint64_t rowptr_hash = 0;
     // options
     int opt_lpr = 0, graph_chunk = 16, use_graph = 1, blocks_per_sm = 0, spmv_variant = 0, solver = 0;
@@ -275,6 +277,19 @@ template <typename T> struct Engine {
             tiles.push_back(SpmvTile{r, e, rp[r], rp[e]});
             r = e;
         }
+        // row-block shards: tiles that reference halo entries go last, so that a block only has to wait for
+        // the peers' data when it reaches them (the interior tiles hide the exchange)
+        c->ntiles_interior = (int)tiles.size();
+        if (!c->row_boundary.empty()) {
+            auto touches_halo = [&](const SpmvTile &tl) {
+                const int r1 = tl.r1 >= 0 ? tl.r1 : tl.r0 + 1;
+                for (int r = tl.r0; r < r1; r++)
+                    if (c->row_boundary[r]) return true;
+                return false;
+            };
+            auto mid = std::stable_partition(tiles.begin(), tiles.end(), [&](const SpmvTile &tl) { return !touches_halo(tl); });
+            c->ntiles_interior = (int)(mid - tiles.begin());
+        }
         c->ntiles = (int)tiles.size();
         c->nlong = (int)longs.size();
         c->nslots = slots;
@@ -335,8 +350,9 @@ template <typename T> struct Engine {
             CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const int grid = persistent_grid(c, kern, RowTileCfg::NT, smem, c->ntiles);
         c->spmv_grid_last = grid;
-        kern<<<grid, RowTileCfg::NT, smem, c->stream>>>(c->ntiles, (const SpmvTile *)c->d_tiles, (const T *)c->d_vals,
-                                                        c->d_rowptr, c->d_cols, x, y, (T *)c->d_chunk_sum, sc);
+        kern<<<grid, RowTileCfg::NT, smem, c->stream>>>(c->ntiles, c->ntiles_interior, (const SpmvTile *)c->d_tiles,
+                                                        (const T *)c->d_vals, c->d_rowptr, c->d_cols, x, y,
+                                                        (T *)c->d_chunk_sum, sc);
         c->launches++;
         if (c->nlong > 0) {
             combine_long_rows_kernel<T><<<(c->nlong + 127) / 128, 128, 0, c->stream>>>(

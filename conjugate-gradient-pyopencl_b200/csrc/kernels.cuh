@@ -749,7 +749,7 @@ template <typename T, int S> struct RowTmaCfg {
 
 template <typename T, int S, bool DOT>
 __global__ void __launch_bounds__(RowTileCfg::NT)
-spmv_tma_rows_kernel(int ntiles, const SpmvTile *__restrict__ tiles, const T *__restrict__ vals,
+spmv_tma_rows_kernel(int ntiles, int ntiles_interior, const SpmvTile *__restrict__ tiles, const T *__restrict__ vals,
                      const int *__restrict__ rowptr, const int *__restrict__ cols, const T *__restrict__ x,
                      T *__restrict__ y, T *__restrict__ chunk_sum, CgScalars<T> sc) {
     using K = RowTmaCfg<T, S>;
@@ -804,14 +804,16 @@ spmv_tma_rows_kernel(int ntiles, const SpmvTile *__restrict__ tiles, const T *__
     SpmvTile tl_next = {0, 0, 0, 0};
     if (count > 0) tl_next = tile_of(0);
 
-    // row-block shards: the matrix tiles above are already in flight; now make sure the peers' entries of
-    // x (the halo) have landed before the first gather
-    if (sc.peer && sc.peer->world > 1) {
-        if (t == 0) peer_wait_halo(sc.peer);
-        __syncthreads();
-    }
+    // row-block shards: tiles [ntiles_interior, ntiles) gather entries that peers push into this GPU's vector;
+    // a block waits for them only when it reaches its first such tile (its matrix data is already in flight)
+    bool halo_ready = !(sc.peer && sc.peer->world > 1);
 
     for (int i = 0; i < count; i++) {
+        if (!halo_ready && (int)blockIdx.x + i * (int)gridDim.x >= ntiles_interior) {
+            if (t == 0) peer_wait_halo(sc.peer);
+            __syncthreads();
+            halo_ready = true;
+        }
         const SpmvTile tl = tl_next;
         if (i + 1 < count) tl_next = tile_of(i + 1);
         const int s = i % S;

@@ -94,6 +94,9 @@ struct cgb200_shard_ctx {
     PeerComm *d_peer = nullptr;          // device copy of the PeerComm
     std::vector<void *> opened;          // peers' mappings to close
     int max_send = 0;
+    cudaStream_t side = nullptr;         // the halo push runs beside the interior rows of the SpMV
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool push_pending = false;
 };
 
 static constexpr size_t P2P_SLOTS_BYTES = 2 * PEER_MAX * sizeof(PeerSlot);
@@ -111,8 +114,14 @@ template <typename T> struct ShardEngine {
         if (sh->p2p) {
             // entries go straight into the peers' d vectors over NVLink; the consumer (SpMV) waits for the flags
             if (sh->send_total > 0) {
+                // fork: the push reads v while the SpMV (which only reads v too) already runs on the main stream;
+                // joined again before the next kernel that writes v (join_push)
                 const int nb = std::max(1, std::min(32, (sh->max_send + 2047) / 2048));
-                halo_push_kernel<T><<<dim3(nb, sh->world), 256, 0, c->stream>>>(sh->d_peer, sh->d_send_idx, v);
+                CU(cudaEventRecord(sh->ev_fork, c->stream));
+                CU(cudaStreamWaitEvent(sh->side, sh->ev_fork, 0));
+                halo_push_kernel<T><<<dim3(nb, sh->world), 256, 0, sh->side>>>(sh->d_peer, sh->d_send_idx, v);
+                CU(cudaEventRecord(sh->ev_join, sh->side));
+                sh->push_pending = true;
                 c->launches++;
             }
             sh->exchanges++;
@@ -139,6 +148,14 @@ template <typename T> struct ShardEngine {
         return 0;
     }
 
+    static int join_push(cgb200_shard_ctx *sh) {
+        if (sh->push_pending) {
+            CU(cudaStreamWaitEvent(sh->m->stream, sh->ev_join, 0));
+            sh->push_pending = false;
+        }
+        return 0;
+    }
+
     static int allreduce(cgb200_shard_ctx *sh, T *buf, int k) {
         if (sh->world == 1 || sh->p2p) return 0;      // p2p: done inside the producing kernel
         NC(nccl_api()->AllReduce(buf, buf, (size_t)k * NCOMP, nccl_type(), ncclSum, sh->comm, sh->m->stream));
@@ -158,6 +175,7 @@ template <typename T> struct ShardEngine {
             update_bookkeep_kernel<T><<<1, 32, 0, c->stream>>>(1, sc);
             c->launches++;
         }
+        TRY(join_push(sh));                                                         // update_d rewrites d
         if (g.V == 1) TRY(E::template launch_update_d<1>(c, 1, g, sc));
         else TRY(E::template launch_update_d<E::VW>(c, 1, g, sc));
         return 0;
@@ -183,6 +201,7 @@ template <typename T> struct ShardEngine {
         // q = A x0 (x0 with its halo) ; r = b - q ; d = r ; delta = r.r           clcg.c:253-292
         TRY(exchange(sh, (T *)c->d));
         TRY(E::template spmv<false>(c, 1, (const T *)c->d, (T *)c->q, sc));
+        TRY(join_push(sh));
         CU(cudaMemcpyAsync(c->d, b, bytes, cudaMemcpyDefault, c->stream));
         if (g.V == 1) TRY(E::template launch_init<1>(c, 1, g, (const T *)c->d, (const T *)c->q, (T *)c->r, (T *)c->d, sc));
         else TRY(E::template launch_init<E::VW>(c, 1, g, (const T *)c->d, (const T *)c->q, (T *)c->r, (T *)c->d, sc));
@@ -287,7 +306,8 @@ int cgb200_nccl_unique_id(void *out128) {
 
 int cgb200_shard_create(cgb200_shard *out, int rank, int world, const void *nccl_id128, int device, int n_owned,
                         int n_halo, long long nnz, const void *aValues, const int *aPointers, const int *aColsLocal,
-                        int dtype, const int *send_counts, const int *send_idx, const int *recv_counts) {
+                        int dtype, const int *send_counts, const int *send_idx, const int *recv_counts,
+                        const unsigned char *row_boundary) {
     if (!out) return fail(CGB200_ERR_ARG, "out is NULL");
     *out = nullptr;
     if (world < 1 || rank < 0 || rank >= world || n_owned <= 0 || n_halo < 0)
@@ -305,6 +325,14 @@ int cgb200_shard_create(cgb200_shard *out, int rank, int world, const void *nccl
     int rc = cgb200_create(&sh->m, n_owned, nnz, aValues, aPointers, aColsLocal, dtype, device);
     if (rc < 0) return bail(rc);
     sh->m->extra_cols = n_halo;
+    if (row_boundary && world > 1) {
+        // rebuild the SpMV schedule with the halo-touching tiles last
+        sh->m->row_boundary.assign(row_boundary, row_boundary + n_owned);
+        sh->m->rowptr_hash = 0;
+        DeviceGuard g0(device);
+        rc = upload_matrix(sh->m, aValues, aPointers, aColsLocal);
+        if (rc < 0) return bail(rc);
+    }
     DeviceGuard guard(device);
     sh->send_counts.assign(world, 0);
     sh->recv_counts.assign(world, 0);
@@ -349,6 +377,12 @@ int cgb200_shard_destroy(cgb200_shard sh) {
         DeviceGuard guard(sh->m->device);
         if (sh->m->stream) cudaStreamSynchronize(sh->m->stream);
         drop_graph(sh->m);      // a captured graph holds NCCL resources: it must go before the communicator
+        if (sh->side) {
+            cudaStreamSynchronize(sh->side);
+            cudaStreamDestroy(sh->side);
+            cudaEventDestroy(sh->ev_fork);
+            cudaEventDestroy(sh->ev_join);
+        }
         for (void *p : sh->opened) cudaIpcCloseMemHandle(p);
         if (sh->d_peer) cudaFree(sh->d_peer);
         if (sh->p2p_buf) cudaFree(sh->p2p_buf);
@@ -411,6 +445,11 @@ int cgb200_shard_p2p_import(cgb200_shard sh, const void *all_handles, const long
     pc.send_off[sh->world] = sh->send_total;
     for (int p = sh->world; p < PEER_MAX; p++) pc.send_off[p + 1] = sh->send_total;
     if (!sh->d_peer) CU(cudaMalloc((void **)&sh->d_peer, sizeof(PeerComm)));
+    if (!sh->side) {
+        CU(cudaStreamCreateWithFlags(&sh->side, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&sh->ev_fork, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&sh->ev_join, cudaEventDisableTiming));
+    }
     CU(cudaMemcpy(sh->d_peer, &pc, sizeof(pc), cudaMemcpyHostToDevice));
     drop_graph(c);
     sh->p2p = true;

@@ -112,7 +112,7 @@ def split_rows(indptr, world, by="rows", align=1):
 class ShardPlan:
     """Rank-local view of a row-block partition."""
     __slots__ = ("rank", "world", "bounds", "n_owned", "n_halo", "indptr", "cols_local", "data",
-                 "halo_globals", "recv_counts", "send_counts", "send_idx")
+                 "halo_globals", "recv_counts", "send_counts", "send_idx", "row_boundary")
 
 
 def plan_row_block(indptr, indices, data, bounds, rank, exchange=None):
@@ -172,6 +172,12 @@ def plan_row_block(indptr, indices, data, bounds, rank, exchange=None):
     plan.recv_counts = recv_counts
     plan.send_counts = send_counts
     plan.send_idx = (np.concatenate(send_lists) if send_lists else np.zeros(0, np.intc)).astype(np.intc)
+    # rows that reference a halo column: their SpMV tiles are scheduled last (the exchange hides behind the rest)
+    nz_per_row = np.diff(lp)
+    plan.row_boundary = (np.add.reduceat(~owned, lp[:-1][nz_per_row > 0]) > 0 if owned.size else np.zeros(0, bool))
+    rbnd = np.zeros(n_owned, dtype=np.uint8)
+    rbnd[np.nonzero(nz_per_row > 0)[0]] = plan.row_boundary.astype(np.uint8)
+    plan.row_boundary = rbnd
     return plan
 
 
@@ -199,7 +205,8 @@ class ShardedMatrix:
             ctypes.byref(h), plan.rank, plan.world, _lib.ptr(uid), int(device), plan.n_owned, plan.n_halo,
             int(data.size), _lib.ptr(np.ascontiguousarray(data)), _lib.ptr(plan.indptr), _lib.ptr(plan.cols_local),
             _lib.DTYPE_CODE[np.dtype(self.dtype)], _lib.ptr(np.ascontiguousarray(plan.send_counts)),
-            _lib.ptr(np.ascontiguousarray(plan.send_idx)), _lib.ptr(np.ascontiguousarray(plan.recv_counts))))
+            _lib.ptr(np.ascontiguousarray(plan.send_idx)), _lib.ptr(np.ascontiguousarray(plan.recv_counts)),
+            _lib.ptr(np.ascontiguousarray(plan.row_boundary))))
         self._h = h
         self.p2p = False
         if p2p and 1 < plan.world <= 8:

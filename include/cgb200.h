@@ -154,11 +154,14 @@ CGB200_API int cgb200_nccl_unique_id(void *out128);
 
 /* aColsLocal: column indices in the local numbering.  send_counts[p] / recv_counts[p]:
  * entries sent to / received from rank p (0 for p == rank); send_idx: the owned indices
- * to send, concatenated in rank order; received blocks land in the halo in rank order. */
+ * to send, concatenated in rank order; received blocks land in the halo in rank order.
+ * row_boundary (optional, n_owned bytes): 1 for rows that reference a halo column; their SpMV tiles are
+ * scheduled last so that the exchange is hidden behind the interior rows. */
 CGB200_API int cgb200_shard_create(cgb200_shard *out, int rank, int world, const void *nccl_id128, int device,
                                    int n_owned, int n_halo, long long nnz, const void *aValues,
                                    const int *aPointers, const int *aColsLocal, int dtype,
-                                   const int *send_counts, const int *send_idx, const int *recv_counts);
+                                   const int *send_counts, const int *send_idx, const int *recv_counts,
+                                   const unsigned char *row_boundary);
 CGB200_API int cgb200_shard_destroy(cgb200_shard sh);
 /* The handle of the local row block (owned by the shard): for cgb200_info / cgb200_time_kernel. */
 CGB200_API cgb200_handle cgb200_shard_local(cgb200_shard sh);

@@ -55,3 +55,18 @@ def test_input_validation(pcl):
         pcl.CG(2, 3, a, np.ones(2, np.csingle), p, c, np.zeros(4, np.csingle), 2, 1)
     with pytest.raises(TypeError):
         pcl.CG(2, 3, a.astype(np.int32), np.ones(2), p, c, np.zeros(2), 1, 1)
+
+
+def test_oclcgex_cli_arguments(tmp_path, capsys):
+    """The example executable's four arguments and error paths (main.c:15-24), without a GPU."""
+    from cg_b200 import oclcgex
+    assert oclcgex.main(["only", "three", "args"]) == 1
+    assert "Usage: ./CG <input matrix file>" in capsys.readouterr().err
+    assert oclcgex.main([str(tmp_path / "missing.mtx"), "1", "1", "10"]) == 1
+    assert "Could not read matrix" in capsys.readouterr().out
+    # a symmetric Matrix Market file is expanded to full storage, as main.c:25 does
+    import scipy.io, scipy.sparse as sp
+    A = sp.csr_matrix(np.array([[4.0, -1, 0], [-1, 4, -1], [0, -1, 4]]))
+    scipy.io.mmwrite(str(tmp_path / "sym.mtx"), sp.tril(A), symmetry="symmetric")
+    B = oclcgex.load_csr(str(tmp_path / "sym.mtx"))
+    assert abs(B - A).max() == 0 and B.has_sorted_indices

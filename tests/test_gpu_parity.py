@@ -493,6 +493,23 @@ def test_rhs_split_over_the_visible_gpus(gpu, cpu_ref):
     gpu._lib.lib().cgb200_clear_cache()
 
 
+def test_oclcgex_example_executable(gpu, tmp_path, capsys):
+    """main.c's flow: Matrix Market file (symmetric storage) -> CSR -> b = 5(r+1) -> cg()."""
+    import scipy.io
+    from cg_b200 import oclcgex
+    import cg_b200.problems as P
+    A = P.helmholtz_fe(24)
+    scipy.io.mmwrite(str(tmp_path / "helm.mtx"), sp.tril(A), symmetry="symmetric")
+    assert oclcgex.main([str(tmp_path / "helm.mtx"), "2", "1", "400", "--double"]) == 0
+    out = capsys.readouterr().out
+    res = [float(l.split()[4]) for l in out.splitlines() if l.startswith("rhs")]
+    assert len(res) == 2 and max(res) < 1e-8, out
+    P2 = P.poisson2d(20)
+    scipy.io.mmwrite(str(tmp_path / "poisson.mtx"), P2)
+    assert oclcgex.main([str(tmp_path / "poisson.mtx"), "1", "0", "100"]) == 0
+    assert float(capsys.readouterr().out.split()[4]) < 1e-5
+
+
 def test_solve_with_device_tensors(gpu, cpu_ref):
     import torch
     A, b = system("helm", 48, np.complex128)

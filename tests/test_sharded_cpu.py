@@ -56,6 +56,9 @@ def _worker(rank, world, port, kind, by, out_dir):
         for f in ("indptr", "cols_local", "send_idx", "send_counts", "recv_counts"):
             assert np.array_equal(getattr(plan, f), getattr(plan2, f)), f
         assert plan.n_owned == re - rb and plan.recv_counts[rank] == 0 and plan.send_counts[rank] == 0
+        touches = np.array([(plan.cols_local[plan.indptr[i]:plan.indptr[i + 1]] >= plan.n_owned).any()
+                            for i in range(plan.n_owned)])
+        assert np.array_equal(plan.row_boundary.astype(bool), touches)
         assert plan.recv_counts.sum() == plan.n_halo and plan.send_counts.sum() == plan.send_idx.size
         # halo exchange delivers exactly the referenced remote entries
         v = (np.arange(n) * 1.5 + 0.25).astype(A.dtype)
