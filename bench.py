@@ -47,10 +47,32 @@ WORKLOADS = {
     "c3": dict(desc="C3 3-D 7-point Laplacian 128^3, 32 right-hand sides", dtype="f64", k=32),
     "c4": dict(desc="C4 3-D 7-point Laplacian 300^3", dtype="f64", k=1),
     "c5": dict(desc="C5 power-law SPD, 5M rows, 50M nnz", dtype="f64", k=1),
+    # not a BASELINE config: what ONE of 8 GPUs holds of C4 (38 of the 300 z-planes), to tune the shard-sized
+    # kernels on a single GPU
+    "c4slab8": dict(desc="one eighth of C4: 3-D 7-point Laplacian 300x300x38", dtype="f64", k=1),
 }
 
 
 def make_problem(name, dtype, k):
+    """make_problem_uncached, or its result kept under $CGB200_PROBLEM_CACHE (a directory) between the
+    runs of one measuring session -- generating C4 / C5 takes longer than benching them."""
+    import scipy.sparse as sp
+    cache = os.environ.get("CGB200_PROBLEM_CACHE")
+    if not cache:
+        return make_problem_uncached(name, dtype, k)
+    path = os.path.join(cache, f"{name}_{dtype}_{k}.npz")
+    if os.path.exists(path):
+        z = np.load(path)
+        A = sp.csr_matrix((z["data"], z["indices"], z["indptr"]), shape=tuple(z["shape"]))
+        A.has_sorted_indices = True
+        return A, z["B"]
+    A, B = make_problem_uncached(name, dtype, k)
+    os.makedirs(cache, exist_ok=True)
+    np.savez(path, data=A.data, indices=A.indices, indptr=A.indptr, shape=np.array(A.shape), B=B)
+    return A, B
+
+
+def make_problem_uncached(name, dtype, k):
     """(A scipy CSR, B flat [k][n]) of BASELINE.json config `name` (SURVEY.md 8(d) inputs)."""
     import cg_b200.problems as P
     np_t = P.DTYPES[dtype][0]
@@ -66,6 +88,9 @@ def make_problem(name, dtype, k):
         b = None
     elif name == "c4":
         A = P.laplace3d(300)
+        b = np.ones(A.shape[0])
+    elif name == "c4slab8":
+        A = P.laplace3d(300, nz=38)
         b = np.ones(A.shape[0])
     elif name == "c5":
         A = P.powerlaw_spd()
@@ -214,6 +239,15 @@ def config_of(args, wl, A, k, dtype, world, n=None, nnz=None):
                   "working set fits the 126 MB L2 (latency-bound config); no flush between iterations"}
 
 
+def save_trace(args, M, world, rank):
+    """--opt trace=N: keep the kernels' own timeline of the last step (gpurun_out/trace_<workload>_n<world>_r<rank>.npy)."""
+    n = [int(o.split("=")[1]) for o in args.opt if o.startswith("trace=")]
+    if n and n[0] > 0:
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        np.save(os.path.join(ROOT, "gpurun_out", f"trace_{args.workload}_n{world}_r{rank}.npy"),
+                M.read_trace(min(n[0], ITERS_PER_STEP)))
+
+
 def also_single_gpu(name, dtype, peak, tdt_of, stream):
     """Short resident-data measurement of another BASELINE config on this GPU (value + kernel rooflines)."""
     import torch
@@ -312,6 +346,7 @@ def run_row_block(args, wl, dtype, rank, local_rank, world):
         clocks = sampler.stop()
         ms = e0.elapsed_time(e1)
         launches = M.info()["launches"] - l0
+        save_trace(args, M, world, rank)
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_per_step = float(t.item()) / args.steps
@@ -464,6 +499,7 @@ def main():
         clocks = sampler.stop()
         ms = e0.elapsed_time(e1)
         launches = M.info()["launches"] - launches0
+        save_trace(args, M, world, rank)
         timing = M.solve(b_dev, x=x_dev, k=k, max_iterations=ITERS_PER_STEP)[1].timing_ms
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
     if world > 1:

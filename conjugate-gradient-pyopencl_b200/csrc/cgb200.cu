@@ -78,6 +78,10 @@ struct cgb200_ctx {
     uint64_t rowptr_hash = 0;
     // options
     int opt_lpr = 0, graph_chunk = 16, use_graph = 1, blocks_per_sm = 0, spmv_variant = 0, solver = 0;
+    int pdl = 7;                 // programmatic dependent launch of the loop kernels: 1 spmv, 2 update_xr, 4 update_d
+    int trace_iters = 0;         // > 0: the kernels stamp a timeline of that many iterations into d_trace
+    unsigned long long *d_trace = nullptr;
+    int defer_len = 16;          // rows longer than this (per lane) are walked by a whole warp, see spmv_tma_rows_kernel
     int coop = 0;
     // workspace (for ws_k right-hand sides)
     int ws_k = 0;
@@ -123,6 +127,24 @@ static void free_workspace(cgb200_ctx *c) {
         *b = nullptr;
     }
     c->ws_k = 0;
+}
+
+// Launch with (pdl = true) or without the programmatic-stream-serialization attribute, see pdl_wait() in kernels.cuh.
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, bool pdl,
+                                 Args... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
 }
 
 // persistent grid for `kernel` with `block` threads and `smem` bytes, capped by `work_blocks`
@@ -193,6 +215,8 @@ template <typename T> struct Engine {
         s.partial = (T *)c->partial;
         s.hist = hist_cap > 0 ? c->d_hist : nullptr;
         s.hist_cap = hist_cap;
+        s.trace = c->trace_iters > 0 ? c->d_trace : nullptr;
+        s.trace_cap = c->trace_iters;
         (void)tol;
         (void)k;
         return s;
@@ -350,9 +374,9 @@ template <typename T> struct Engine {
             CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const int grid = persistent_grid(c, kern, RowTileCfg::NT, smem, c->ntiles);
         c->spmv_grid_last = grid;
-        kern<<<grid, RowTileCfg::NT, smem, c->stream>>>(c->ntiles, c->ntiles_interior, (const SpmvTile *)c->d_tiles,
-                                                        (const T *)c->d_vals, c->d_rowptr, c->d_cols, x, y,
-                                                        (T *)c->d_chunk_sum, sc);
+        CU(launch_kernel(kern, dim3(grid), dim3(RowTileCfg::NT), smem, c->stream, DOT && (c->pdl & 1), c->ntiles,
+                         c->ntiles_interior, c->defer_len, (const SpmvTile *)c->d_tiles, (const T *)c->d_vals,
+                         (const int *)c->d_rowptr, (const int *)c->d_cols, x, y, (T *)c->d_chunk_sum, sc));
         c->launches++;
         if (c->nlong > 0) {
             combine_long_rows_kernel<T><<<(c->nlong + 127) / 128, 128, 0, c->stream>>>(
@@ -369,7 +393,8 @@ template <typename T> struct Engine {
         const long long work = ((long long)c->n + (block / G) - 1) / (block / G);
         const int grid = persistent_grid(c, kern, block, smem, work);
         c->spmv_grid_last = grid;
-        kern<<<grid, block, smem, c->stream>>>(c->n, k, (const T *)c->d_vals, c->d_rowptr, c->d_cols, x, y, sc);
+        CU(launch_kernel(kern, dim3(grid), dim3(block), smem, c->stream, DOT && (c->pdl & 1), c->n, k, (const T *)c->d_vals,
+                         (const int *)c->d_rowptr, (const int *)c->d_cols, x, y, sc));
         c->launches++;
         return 0;
     }
@@ -431,7 +456,8 @@ template <typename T> struct Engine {
         auto kern = update_xr_kernel<T, V>;
         const size_t smem = (size_t)g.block * V * sizeof(T);
         const int grid = persistent_grid(c, kern, g.block, smem, (long long)((g.npacks + g.block - 1) / g.block));
-        kern<<<grid, g.block, smem, c->stream>>>(g.npacks, g.nelem, k, g.kv, (const T *)c->d, (const T *)c->q, (T *)c->x, (T *)c->r, sc);
+        CU(launch_kernel(kern, dim3(grid), dim3(g.block), smem, c->stream, (c->pdl & 2) != 0, g.npacks, g.nelem, k, g.kv,
+                         (const T *)c->d, (const T *)c->q, (T *)c->x, (T *)c->r, sc));
         c->launches++;
         return 0;
     }
@@ -439,7 +465,8 @@ template <typename T> struct Engine {
     static int launch_update_d(cgb200_ctx *c, int k, const VecGeom &g, const CgScalars<T> &sc) {
         auto kern = update_d_kernel<T, V>;
         const int grid = persistent_grid(c, kern, g.block, 0, (long long)((g.npacks + g.block - 1) / g.block));
-        kern<<<grid, g.block, 0, c->stream>>>(g.npacks, g.nelem, k, g.kv, (const T *)c->r, (T *)c->d, sc);
+        CU(launch_kernel(kern, dim3(grid), dim3(g.block), 0, c->stream, (c->pdl & 4) != 0, g.npacks, g.nelem, k, g.kv,
+                         (const T *)c->r, (T *)c->d, sc));
         c->launches++;
         return 0;
     }
@@ -946,6 +973,8 @@ int cgb200_create(cgb200_handle *out, int n, long long nnz, const void *aValues,
     if (const char *e = getenv("CGB200_BLOCKS_PER_SM")) c->blocks_per_sm = atoi(e);
     if (const char *e = getenv("CGB200_SPMV_VARIANT")) c->spmv_variant = atoi(e);
     if (const char *e = getenv("CGB200_SOLVER")) c->solver = atoi(e);
+    if (const char *e = getenv("CGB200_DEFER_LEN")) c->defer_len = atoi(e);
+    if (const char *e = getenv("CGB200_PDL")) c->pdl = atoi(e);
     *out = c;
     return CGB200_OK;
 }
@@ -962,6 +991,7 @@ int cgb200_destroy(cgb200_handle c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     free_workspace(c);
     if (c->d_hist) cudaFree(c->d_hist);
+    if (c->d_trace) cudaFree(c->d_trace);
     if (c->d_tiles) cudaFree(c->d_tiles);
     if (c->d_long) cudaFree(c->d_long);
     if (c->d_chunk_sum) cudaFree(c->d_chunk_sum);
@@ -999,6 +1029,9 @@ static int *option_slot(cgb200_handle c, const char *key) {
     if (!strcmp(key, "blocks_per_sm")) return &c->blocks_per_sm;
     if (!strcmp(key, "spmv_variant")) return &c->spmv_variant;
     if (!strcmp(key, "solver")) return &c->solver;
+    if (!strcmp(key, "defer_len")) return &c->defer_len;
+    if (!strcmp(key, "pdl")) return &c->pdl;
+    if (!strcmp(key, "trace")) return &c->trace_iters;
     return nullptr;
 }
 
@@ -1010,6 +1043,16 @@ int cgb200_set_option(cgb200_handle c, const char *key, long long value) {
         value != 16 && value != 32)
         return fail(CGB200_ERR_ARG, "lanes_per_row must be 0 or a power of two <= 32");
     if (!strcmp(key, "graph_chunk") && value < 1) return fail(CGB200_ERR_ARG, "graph_chunk must be >= 1");
+    if (!strcmp(key, "trace")) {
+        if (value < 0 || value > (1 << 20)) return fail(CGB200_ERR_ARG, "trace: 0 .. 2^20 iterations");
+        DeviceGuard guard(c->device);
+        if (c->d_trace) cudaFree(c->d_trace);
+        c->d_trace = nullptr;
+        if (value > 0) {
+            CU(cudaMalloc(&c->d_trace, (size_t)value * 8 * sizeof(unsigned long long)));
+            CU(cudaMemset(c->d_trace, 0, (size_t)value * 8 * sizeof(unsigned long long)));
+        }
+    }
     *slot = (int)value;
     drop_graph(c);
     return CGB200_OK;
@@ -1020,6 +1063,15 @@ int cgb200_get_option(cgb200_handle c, const char *key, long long *value) {
     int *slot = option_slot(c, key);
     if (!slot) return fail(CGB200_ERR_ARG, "unknown option '%s'", key);
     *value = *slot;
+    return CGB200_OK;
+}
+
+int cgb200_read_trace(cgb200_handle c, unsigned long long *out, int iterations) {
+    if (!c || !out || iterations < 0) return fail(CGB200_ERR_ARG, "bad trace arguments");
+    if (iterations > c->trace_iters) return fail(CGB200_ERR_ARG, "only %d iterations are traced", c->trace_iters);
+    DeviceGuard guard(c->device);
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaMemcpy(out, c->d_trace, (size_t)iterations * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     return CGB200_OK;
 }
 

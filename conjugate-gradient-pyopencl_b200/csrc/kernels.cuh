@@ -122,6 +122,24 @@ __device__ __forceinline__ void peer_wait_halo(const PeerComm *pc) {
     }
 }
 
+// Programmatic dependent launch: the three kernels of an iteration are launched with the
+// programmatic-stream-serialization attribute, so the blocks of the next kernel are placed on SMs as
+// the blocks of the running one retire and run their prologue (barrier set-up, the first matrix tiles
+// by TMA -- nothing a previous kernel writes) before `pdl_wait` returns, which is when the previous
+// kernel has completed and its writes are visible.  Every block of every kernel waits, so completion
+// is transitive along the chain.  Without the launch attribute both instructions are no-ops.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// timeline events of one iteration (CgScalars::trace, 8 slots per iteration)
+enum : int { TR_SPMV_START = 0, TR_SPMV_ALL_DONE = 1, TR_SPMV_END = 2, TR_XR_START = 3, TR_XR_ALL_DONE = 4, TR_XR_END = 5,
+             TR_D_START = 6, TR_HALO_READY = 7 };
+
 // Device-resident scalar state of one solve (all arrays have k entries).
 template <typename T> struct CgScalars {
     T *dq;              // d.q of the current iteration
@@ -139,10 +157,16 @@ template <typename T> struct CgScalars {
     const double *tol;  // in device memory, so that one captured graph serves every tolerance
     T *rr;              // [k] this device's part of r.r when `defer` is set
     PeerComm *peer;     // non-NULL: the dot products are all-reduced inside the kernels through peer memory
+    unsigned long long *trace;   // optional timeline, [trace_cap][8] globaltimer stamps (TR_*)
+    int trace_cap;
     int defer;          // row-block sharded solve: the dot products are only partial sums here; the
                         // bookkeeping runs in init_bookkeep_kernel / update_bookkeep_kernel after the
                         // all-reduce over the devices (dq is all-reduced in place)
 };
+
+template <typename T> __device__ __forceinline__ void trace_mark(const CgScalars<T> &sc, int it, int ev) {
+    if (sc.trace && it >= 0 && it < sc.trace_cap) sc.trace[(size_t)it * 8 + ev] = global_timer_ns();
+}
 
 // After delta = r0.r0 is known for column c.                      clcg.c:274-292
 template <typename T> __device__ __forceinline__ void init_bookkeep(const CgScalars<T> &sc, int c, T dl) {
@@ -241,6 +265,22 @@ template <typename P> __device__ __forceinline__ P ld_stream_bytes(const P *p) {
         memcpy(&out, &v, 4);
     }
     return out;
+}
+template <typename P> __device__ __forceinline__ void st_stream_bytes(P *p, const P &val) {
+    if constexpr (sizeof(P) == 16) {
+        uint4 v;
+        memcpy(&v, &val, 16);
+        __stcs(reinterpret_cast<uint4 *>(p), v);
+    } else if constexpr (sizeof(P) == 8) {
+        uint2 v;
+        memcpy(&v, &val, 8);
+        __stcs(reinterpret_cast<uint2 *>(p), v);
+    } else {
+        static_assert(sizeof(P) == 4, "st_stream_bytes: 4, 8 or 16 bytes");
+        unsigned v;
+        memcpy(&v, &val, 4);
+        __stcs(reinterpret_cast<unsigned *>(p), v);
+    }
 }
 // Cross-block data (partials) must come from L2, never from a stale L1 line.
 template <typename T> __device__ __forceinline__ T ld_cg(const T *p) { return __ldcg(p); }
@@ -749,15 +789,12 @@ template <typename T, int S> struct RowTmaCfg {
 
 template <typename T, int S, bool DOT>
 __global__ void __launch_bounds__(RowTileCfg::NT)
-spmv_tma_rows_kernel(int ntiles, int ntiles_interior, const SpmvTile *__restrict__ tiles, const T *__restrict__ vals,
+spmv_tma_rows_kernel(int ntiles, int ntiles_interior, int defer_len, const SpmvTile *__restrict__ tiles, const T *__restrict__ vals,
                      const int *__restrict__ rowptr, const int *__restrict__ cols, const T *__restrict__ x,
                      T *__restrict__ y, T *__restrict__ chunk_sum, CgScalars<T> sc) {
     using K = RowTmaCfg<T, S>;
     constexpr int VPT = VecW<T>::value, NT = RowTileCfg::NT;
     constexpr int UB = 8;                             // gathers in flight per thread
-    if (DOT) {
-        if (*sc.n_active == 0) return;
-    }
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem_raw);
     T *red = reinterpret_cast<T *>(smem_raw + K::BAR_BYTES);
@@ -804,13 +841,33 @@ spmv_tma_rows_kernel(int ntiles, int ntiles_interior, const SpmvTile *__restrict
     SpmvTile tl_next = {0, 0, 0, 0};
     if (count > 0) tl_next = tile_of(0);
 
+    // Everything above touched the matrix only.  The vectors and scalars are the previous kernel's output.
+    pdl_wait();
+    pdl_trigger();
+    if (DOT) {
+        if (*sc.n_active == 0) {
+            // nothing to do, but the copies already in flight must land before this block's shared memory is released
+            if (t == 0)
+                for (int i = 0; i < S && i < count; i++) mbar_wait(&bars[i], 0u);
+            return;
+        }
+    }
+    int trace_it = -1;
+    if (DOT && sc.trace) {
+        trace_it = *sc.it;
+        if (blockIdx.x == 0 && t == 0) trace_mark<T>(sc, trace_it, TR_SPMV_START);
+    }
+
     // row-block shards: tiles [ntiles_interior, ntiles) gather entries that peers push into this GPU's vector;
     // a block waits for them only when it reaches its first such tile (its matrix data is already in flight)
     bool halo_ready = !(sc.peer && sc.peer->world > 1);
 
     for (int i = 0; i < count; i++) {
         if (!halo_ready && (int)blockIdx.x + i * (int)gridDim.x >= ntiles_interior) {
-            if (t == 0) peer_wait_halo(sc.peer);
+            if (t == 0) {
+                peer_wait_halo(sc.peer);
+                if ((int)blockIdx.x == ntiles_interior % (int)gridDim.x) trace_mark<T>(sc, trace_it, TR_HALO_READY);
+            }
             __syncthreads();
             halo_ready = true;
         }
@@ -833,9 +890,17 @@ spmv_tma_rows_kernel(int ntiles, int ntiles_interior, const SpmvTile *__restrict
             const bool valid = rr < rows;
             T sum = Sc<T>::zero();
             T xr = Sc<T>::zero();
+            int lo = 0, hi = 0;
             if (valid) {
                 if (DOT && lane == 0) xr = __ldg(x + tl.r0 + rr);
-                const int lo = rp_s[tl.r0 + rr - rb], hi = rp_s[tl.r0 + rr + 1 - rb];
+                lo = rp_s[tl.r0 + rr - rb];
+                hi = rp_s[tl.r0 + rr + 1 - rb];
+            }
+            // A row much longer than its neighbours (power-law matrices: a 300-entry row among 3-entry rows)
+            // would keep its lpr lanes walking it while the rest of the block idles.  Such a row is left
+            // out here and walked by the whole warp below.
+            const bool deferred = valid && lpr < 32 && defer_len > 0 && (hi - lo) > defer_len * lpr;
+            if (valid && !deferred) {
                 // Batches of UB non-zeros with every load issued before the first FMA: a warp issues in
                 // order, so a plain loop would serialise one L2 round trip per non-zero.  Lanes past the
                 // end of the row re-read the batch's first entry (a valid address) with a zero coefficient.
@@ -860,6 +925,38 @@ spmv_tma_rows_kernel(int ntiles, int ntiles_interior, const SpmvTile *__restrict
                 } else {
                     sum += __shfl_xor_sync(0xffffffffu, sum, off);
                 }
+            }
+            // the deferred rows of this warp, one after the other, 32 lanes x UB gathers in flight each
+            unsigned pending = __ballot_sync(0xffffffffu, deferred && lane == 0);
+            while (pending) {
+                const int src = __ffs(pending) - 1;
+                pending &= pending - 1;
+                const int rlo = __shfl_sync(0xffffffffu, lo, src), rhi = __shfl_sync(0xffffffffu, hi, src);
+                const int wl = t & 31;
+                T part = Sc<T>::zero();
+                for (int j0 = rlo + wl; j0 < rhi; j0 += UB * 32) {
+                    T av[UB], xv[UB];
+#pragma unroll
+                    for (int u = 0; u < UB; u++) {
+                        const int j = j0 + u * 32;
+                        const bool ok = j < rhi;
+                        const int jj = ok ? j : j0;
+                        xv[u] = __ldg(x + cols_s[jj - cb]);
+                        av[u] = ok ? vals_s[jj - vb] : Sc<T>::zero();
+                    }
+#pragma unroll
+                    for (int u = 0; u < UB; u++) part = Sc<T>::fma(av[u], xv[u], part);
+                }
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) {
+                    if constexpr (Sc<T>::cplx) {
+                        part.x += __shfl_xor_sync(0xffffffffu, part.x, off);
+                        part.y += __shfl_xor_sync(0xffffffffu, part.y, off);
+                    } else {
+                        part += __shfl_xor_sync(0xffffffffu, part, off);
+                    }
+                }
+                if (wl == src) sum = part;
             }
             if (valid && lane == 0) {
                 y[tl.r0 + rr] = sum;
@@ -897,12 +994,14 @@ spmv_tma_rows_kernel(int ntiles, int ntiles_interior, const SpmvTile *__restrict
     if (DOT) {
         block_col_reduce<T, 1>(dot, 1, red);
         if (publish_and_arrive<T, 1>(red, 1, 1, sc.partial, sc.ticket + TK_SPMV)) {
+            if (t == 0) trace_mark<T>(sc, trace_it, TR_SPMV_ALL_DONE);
             grid_col_reduce<T, 1>(sc.partial, 1, 1, 1, red);
             T total = red[0];
             if (sc.peer) total = peer_allreduce<T>(sc.peer, red[0]);    // sum over the GPUs, inside this kernel
             if (t == 0) {
                 sc.dq[0] = total;
                 sc.ticket[TK_SPMV] = 0;
+                trace_mark<T>(sc, trace_it, TR_SPMV_END);
             }
         }
     }
@@ -933,6 +1032,8 @@ __global__ void __launch_bounds__(256)
 spmm_kernel(int n, int k, const T *__restrict__ vals, const int *__restrict__ rowptr,
             const int *__restrict__ cols, const T *__restrict__ x, T *__restrict__ y,
             CgScalars<T> sc) {
+    pdl_wait();
+    pdl_trigger();
     if (DOT) {
         if (*sc.n_active == 0) return;
     }
@@ -1074,11 +1175,14 @@ template <typename T, int V>
 __global__ void __launch_bounds__(256)
 update_xr_kernel(size_t npacks, size_t nelem, int k, int kv, const T *__restrict__ d,
                  const T *__restrict__ q, T *__restrict__ x, T *__restrict__ r, CgScalars<T> sc) {
+    pdl_wait();
+    pdl_trigger();
     if (*sc.n_active == 0) return;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     T *smem = reinterpret_cast<T *>(smem_raw);
     using P = Pack<T, V>;
     const int t = threadIdx.x;
+    if (sc.trace && blockIdx.x == 0 && t == 0) trace_mark<T>(sc, *sc.it, TR_XR_START);
     T alpha[V], acc[V];
 #pragma unroll
     for (int v = 0; v < V; v++) {
@@ -1094,7 +1198,9 @@ update_xr_kernel(size_t npacks, size_t nelem, int k, int kv, const T *__restrict
     for (size_t p = (size_t)blockIdx.x * blockDim.x + t; p < npacks; p += stride) {
         const P dv = reinterpret_cast<const P *>(d)[p];
         const P qv = reinterpret_cast<const P *>(q)[p];
-        P xv = reinterpret_cast<const P *>(x)[p];
+        // x is touched by this kernel only, once per iteration: streamed (evict-first) in both directions so
+        // that it never displaces r, d and q -- which three kernels share -- from the 126 MB L2
+        P xv = ld_stream_bytes(reinterpret_cast<const P *>(x) + p);
         P rv = reinterpret_cast<const P *>(r)[p];
 #pragma unroll
         for (int v = 0; v < V; v++) {
@@ -1102,7 +1208,7 @@ update_xr_kernel(size_t npacks, size_t nelem, int k, int kv, const T *__restrict
             rv.v[v] = Sc<T>::fnma(alpha[v], qv.v[v], rv.v[v]);
             acc[v] = Sc<T>::fma(rv.v[v], rv.v[v], acc[v]);
         }
-        reinterpret_cast<P *>(x)[p] = xv;
+        st_stream_bytes(reinterpret_cast<P *>(x) + p, xv);
         reinterpret_cast<P *>(r)[p] = rv;
     }
     if (V > 1 && blockIdx.x == 0) {
@@ -1120,8 +1226,9 @@ update_xr_kernel(size_t npacks, size_t nelem, int k, int kv, const T *__restrict
     }
     block_col_reduce<T, V>(acc, kv, smem);
     if (publish_and_arrive<T, V>(smem, kv, k, sc.partial, sc.ticket + TK_UPDATE)) {
-        grid_col_reduce<T, V>(sc.partial, kv, kv, k, smem);
         const int it1 = *sc.it + 1;
+        if (t == 0) trace_mark<T>(sc, it1 - 1, TR_XR_ALL_DONE);
+        grid_col_reduce<T, V>(sc.partial, kv, kv, k, smem);
         T total0 = smem[0];
         if (sc.peer) total0 = peer_allreduce<T>(sc.peer, smem[0]);     // k == 1: sum over the GPUs
         if (t < kv) {
@@ -1138,6 +1245,7 @@ update_xr_kernel(size_t npacks, size_t nelem, int k, int kv, const T *__restrict
         if (t == 0) {
             if (!sc.defer) *sc.it = it1;
             sc.ticket[TK_UPDATE] = 0;
+            trace_mark<T>(sc, it1 - 1, TR_XR_END);
         }
     }
 }
@@ -1147,9 +1255,12 @@ template <typename T, int V>
 __global__ void __launch_bounds__(256)
 update_d_kernel(size_t npacks, size_t nelem, int k, int kv, const T *__restrict__ r,
                 T *__restrict__ d, CgScalars<T> sc) {
+    pdl_wait();
+    pdl_trigger();
     if (*sc.n_active == 0) return;
     using P = Pack<T, V>;
     const int t = threadIdx.x;
+    if (sc.trace && blockIdx.x == 0 && t == 0) trace_mark<T>(sc, *sc.it - 1, TR_D_START);
     T beta[V];
 #pragma unroll
     for (int v = 0; v < V; v++) {

@@ -48,6 +48,12 @@ class SolveInfo:
                 f"relres={self.relres.tolist()}, timing_ms={self.timing_ms})")
 
 
+def read_trace(handle, iterations):
+    out = np.zeros((int(iterations), 8), dtype=np.uint64)
+    check(lib().cgb200_read_trace(handle, out.ctypes.data_as(ctypes.c_void_p), int(iterations)))
+    return out
+
+
 class Matrix:
     """A CSR matrix resident in the HBM of one B200 (`cgb200_create`)."""
 
@@ -119,6 +125,14 @@ class Matrix:
         keys = ("n", "nnz", "dtype", "lanes_per_row", "spmv_grid", "sm_count", "launches", "graph_launches",
                 "max_row", "device")
         return dict(zip(keys, list(out)))
+
+    TRACE_EVENTS = ("spmv_start", "spmv_all_done", "spmv_end", "xr_start", "xr_all_done", "xr_end", "d_start",
+                    "halo_ready")
+
+    def read_trace(self, iterations):
+        """Timeline of the last solve (set_option("trace", n) first): uint64 [iterations][8] nanoseconds,
+        columns TRACE_EVENTS, 0 = not recorded."""
+        return read_trace(self._h, iterations)
 
     KERNELS = {"spmv_dot": 0, "update_xr": 1, "update_d": 2, "spmv": 3}
 

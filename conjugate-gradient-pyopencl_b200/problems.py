@@ -154,14 +154,16 @@ def rhs_a(N: int, omega: float) -> np.ndarray:
     return b.ravel()
 
 
-def laplace3d(N: int, dtype=np.float64, rows=None) -> sp.csr_matrix:
-    """7-point Laplacian on an N^3 grid, diag 6 / off -1, Dirichlet truncation, x fastest.
+def laplace3d(N: int, dtype=np.float64, rows=None, nz=None) -> sp.csr_matrix:
+    """7-point Laplacian on an N^3 grid (N x N x nz when nz is given), diag 6 / off -1, Dirichlet
+    truncation, x fastest.
 
     The 3-D extension of `Poisson` named by BASELINE.json configs 3 and 4 (not in the
     reference).  Built straight into CSR arrays: 300^3 has 188 M non-zeros.
     rows=(r0, r1): only that block of rows (global column indices, shape (r1-r0, N^3)) -- what one
     rank of a row-block sharded run needs."""
-    n = N ** 3
+    NZ = N if nz is None else int(nz)
+    n = N * N * NZ
     r0, r1 = (0, n) if rows is None else (int(rows[0]), int(rows[1]))
     idx = np.arange(r0, r1, dtype=np.int64)
     x = (idx % N).astype(np.int32)
@@ -169,7 +171,7 @@ def laplace3d(N: int, dtype=np.float64, rows=None) -> sp.csr_matrix:
     z = (idx // (N * N)).astype(np.int32)
     m = r1 - r0
     # neighbours in ascending column order: -N^2, -N, -1, 0, +1, +N, +N^2
-    present = np.stack([z > 0, y > 0, x > 0, np.ones(m, bool), x < N - 1, y < N - 1, z < N - 1], axis=1)
+    present = np.stack([z > 0, y > 0, x > 0, np.ones(m, bool), x < N - 1, y < N - 1, z < NZ - 1], axis=1)
     del x, y, z
     offs = np.array([-N * N, -N, -1, 0, 1, N, N * N], dtype=np.int64)
     counts = present.sum(axis=1, dtype=np.int64)

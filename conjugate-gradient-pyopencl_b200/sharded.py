@@ -245,6 +245,11 @@ class ShardedMatrix:
         _lib.check(_lib.lib().cgb200_time_kernel(h, kinds[which], 1, int(reps), ctypes.byref(ms)))
         return ms.value
 
+    def read_trace(self, iterations):
+        """Timeline of the local row block's kernels in the last solve (set_option("trace", n) first)."""
+        from . import engine
+        return engine.read_trace(ctypes.c_void_p(_lib.lib().cgb200_shard_local(self._h)), iterations)
+
     def set_stream(self, cuda_stream):
         _lib.check(_lib.lib().cgb200_shard_set_stream(self._h, ctypes.c_void_p(int(cuda_stream) if cuda_stream else 0)))
 

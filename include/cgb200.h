@@ -84,6 +84,12 @@ CGB200_API int cgb200_set_stream(cgb200_handle h, void *cuda_stream);
  *   "graph_chunk"    CG iterations captured per CUDA graph launch (default 16)
  *   "use_graph"      0/1
  *   "blocks_per_sm"  0 auto | n               persistent-grid size multiplier
+ *   "defer_len"      rows with more than this many non-zeros per lane are walked by a whole warp (default 16,
+ *                    0 off): keeps a tile of a power-law matrix from waiting for its longest row
+ *   "pdl"            bit mask, programmatic dependent launch of 1 spmv | 2 x/r update | 4 direction update
+ *                    (default 7): a kernel's prologue overlaps the tail of the one before it
+ *   "trace"          n > 0: the loop kernels stamp %globaltimer into an 8-slot record per iteration for the
+ *                    first n iterations of a solve; read it with cgb200_read_trace()
  */
 CGB200_API int cgb200_set_option(cgb200_handle h, const char *key, long long value);
 CGB200_API int cgb200_get_option(cgb200_handle h, const char *key, long long *value);
@@ -117,6 +123,12 @@ CGB200_API int cgb200_last_timing(cgb200_handle h, double ms[4]);
  * (axpy.cl x2 + vdot.cl), 2 direction update (aypx.cl), 3 plain spmv.  Call it after a
  * cgb200_solve() with the same k; the next solve re-initialises the state it disturbs. */
 CGB200_API int cgb200_time_kernel(cgb200_handle h, int which, int k, int reps, double *ms_avg);
+
+/* Timeline of the last solve (option "trace"): out[it*8 + e], nanoseconds of the GPU's global timer, e =
+ * 0 spmv starts, 1 all blocks of spmv done, 2 d.q known (after the all-reduce when sharded), 3 x/r update
+ * starts, 4 all its blocks done, 5 delta known, 6 direction update starts, 7 halo entries of the peers
+ * have arrived (sharded).  0 = not recorded. */
+CGB200_API int cgb200_read_trace(cgb200_handle h, unsigned long long *out, int iterations);
 
 /* Facts about a handle, for benches and tests:
  * [0] n [1] nnz [2] dtype [3] lanes_per_row [4] persistent grid of the SpMV kernel

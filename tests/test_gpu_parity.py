@@ -580,3 +580,73 @@ def test_graph_and_plain_launch_paths_agree(gpu):
         x1, i1 = M.solve(b, max_iterations=50)
         assert M.info()["graph_launches"] == 7
     assert np.array_equal(x0, x1)                 # deterministic: same kernels, same order
+
+
+# ---------------------------------------------------------------------------------------
+# power-law tiles, programmatic dependent launch, the kernels' own timeline
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dname", ["f32", "f64", "c64", "c128"])
+def test_spmv_long_rows_among_short_ones_are_walked_by_a_warp(gpu, dname):
+    """Rows of 20..900 non-zeros scattered among rows of 0..8 (the shape of BASELINE config 5): with
+    defer_len they leave the thread-per-row pass and are walked by a whole warp; same sums either way."""
+    dt = DT[dname]
+    rng = np.random.default_rng(11)
+    n = 9000
+    lens = rng.integers(0, 9, n)
+    long_rows = rng.choice(n, 300, replace=False)
+    lens[long_rows] = rng.integers(17, 900, long_rows.size)
+    lens[long_rows[:8]] = [17, 18, 31, 32, 33, 64, 255, 257]
+    cols = np.concatenate([rng.choice(n, l, replace=False) for l in lens]).astype(np.intc)
+    vals = rand(rng, cols.size, dt)
+    indptr = np.zeros(n + 1, np.intc)
+    np.cumsum(lens, out=indptr[1:])
+    x = rand(rng, n, dt)
+    wide = np.complex128 if np.dtype(dt).kind == "c" else np.float64
+    exact = sp.csr_matrix((vals.astype(wide), cols, indptr), shape=(n, n)) @ x.astype(wide)
+    tol = 2e-5 if dname in ("f32", "c64") else 1e-13
+    alpha = np.sum(x.astype(wide) ** 2) / np.sum(x.astype(wide) * exact)
+    with gpu.Matrix(vals, indptr, cols) as M:
+        assert M.get_option("defer_len") == 16
+        for defer in (0, 1, 4, 16, 64):
+            M.set_option("defer_len", defer)
+            assert rel(M.spmv(x), exact) < tol, defer
+            xs, _ = M.solve(x, max_iterations=1)              # fused d.q of the deferred rows
+            assert rel(xs, alpha * x.astype(wide)) < tol, defer
+
+
+@pytest.mark.parametrize("k", [1, 4])
+def test_programmatic_dependent_launch_changes_nothing(gpu, k):
+    """pdl = 0 (plain stream order) and pdl = 7 (every loop kernel's prologue overlaps the previous tail)
+    run the same arithmetic in the same order: bit-identical iterates, graphs or not."""
+    A, b = system("helm", 40, np.complex128)
+    rng = np.random.default_rng(3)
+    B = np.concatenate([b] + [rand(rng, A.shape[0], np.complex128) for _ in range(k - 1)])
+    out = {}
+    with gpu.Matrix.from_scipy(A) as M:
+        M.set_option("solver", 1)
+        assert M.get_option("pdl") == 7
+        for pdl in (0, 7, 1, 2, 4):
+            for graph in (0, 1):
+                M.set_option("pdl", pdl)
+                M.set_option("use_graph", graph)
+                out[(pdl, graph)] = M.solve(B, k=k, max_iterations=64)[0]
+        x_tol, info = M.solve(B, k=k, max_iterations=2000, tol=1e-10)
+        assert info.flags == 0
+    for key, x in out.items():
+        assert np.array_equal(x, out[(0, 0)]), key
+
+
+def test_trace_timeline(gpu):
+    A, b = system("poisson", 64, np.float64)
+    with gpu.Matrix.from_scipy(A) as M:
+        M.set_option("solver", 1)
+        M.set_option("trace", 32)
+        M.solve(b, max_iterations=32)
+        tr = M.read_trace(32).astype(np.int64)
+        M.set_option("trace", 0)
+        x, _ = M.solve(b, max_iterations=32)
+    ev = tr[:, :7]
+    assert (ev > 0).all()
+    assert (np.diff(ev, axis=1) >= 0).all()              # events of one iteration are in order
+    assert (ev[1:, 0] >= ev[:-1, 6]).all()               # the next SpMV starts after the direction update started
+    assert (tr[:, 7] == 0).all()                         # no halo on one GPU
