@@ -42,3 +42,30 @@ def cg(A, b, x=None, tol=1e-5, maxit=1000, stop=False, history=None):
         beta = delta_new / delta_old                 # :539
         d = r + beta * d                             # :542
     return (x, it) if stop else x
+
+
+def cg_abs_tol(A, b, tol=1e-5, x=None, max_it=None):
+    """The OTHER numpy CG of the reference: the drivers' local `CG` (/root/reference/p_h-PY_C-CL.py:1338-1369,
+    used by as_prec when UseCG == 5, :1916-1923).  Same recurrence as `cg` above, but it ignores `maxit`
+    (the loop bound is 2*b.size, :1349) and stops on the ABSOLUTE residual sqrt(|r.r|) < tol (:1364-1367).
+    Same numpy operations in the same order, so results are bit-identical to the driver's
+    (oracle/run_reference_driver.py asserts that when it makes tests/golden/asprec_*.npz).
+    Returns (x, iterations performed)."""
+    if x is None:
+        x = np.zeros(b.size, dtype=complex)                  # :1346-1347
+    r = b - A.dot(x)                                         # :1349
+    d = None
+    rho_prev = None
+    it = 0
+    for i in range(2 * b.size if max_it is None else max_it):   # :1350
+        rho = np.dot(r, r)                                   # :1352-1353 (z = r, no preconditioner)
+        d = r if i == 0 else r + (rho / rho_prev) * d        # :1355-1359
+        q = A.dot(d)                                         # :1360
+        alpha = rho / np.dot(d, q)                           # :1361
+        x = x + alpha * d                                    # :1362
+        r = r - alpha * q                                    # :1363
+        it = i + 1
+        if np.sqrt(abs(np.dot(r, r))) < tol:                 # :1364-1367
+            break
+        rho_prev = rho                                       # :1368
+    return x, it

@@ -650,3 +650,66 @@ def test_trace_timeline(gpu):
     assert (np.diff(ev, axis=1) >= 0).all()              # events of one iteration are in order
     assert (ev[1:, 0] >= ev[:-1, 6]).all()               # the next SpMV starts after the direction update started
     assert (tr[:, 7] == 0).all()                         # no halo on one GPU
+
+
+# ---------------------------------------------------------------------------------------
+# the caller: as_prec (p_h-PY_C-CL.py:1842-1995) -- fixtures recorded from the reference driver itself
+# (oracle/run_reference_driver.py), SURVEY.md 8(f) rank 1
+# ---------------------------------------------------------------------------------------
+ASPREC = ["asprec_2_12.npz", "asprec_3_16.npz"]
+
+
+def _asprec(golden_dir, name):
+    z = np.load(os.path.join(golden_dir, name))
+    n = int(z["n"])
+    return z, sp.csr_matrix((z["data"], z["indices"], z["indptr"]), shape=(n, n))
+
+
+@pytest.mark.parametrize("name", ASPREC)
+def test_as_prec_numpy_cg_variant_in_double(gpu, cpu_ref, golden_dir, name):
+    """UseCG == 5: the reference solves every subdomain with its numpy CG in complex128 until |r| < 1e-5.
+    The device, given the same systems and the iteration counts the reference needed, must land on the
+    reference's own x.  The operators are indefinite: the C oracle (device summation order, double) is itself
+    up to 6e-9 from the numpy result, so the bar is 10x the oracle's own distance (and never looser than 1e-7).
+    With the reference's stopping rule (absolute |r| < tol -> relative tol / |r0|) the iteration count is +-1."""
+    z, A = _asprec(golden_dir, name)
+    with gpu.Matrix.from_scipy(A) as M:
+        for p in range(z["z"].shape[0]):
+            b, ref, it = z["z"][p], z["x_numpy_cg"][p], int(z["numpy_cg_iters"][p])
+            x, _ = M.solve(b, max_iterations=it)
+            xo, _, _ = cpu_ref.cg(A.data, A.indptr, A.indices, b, iters=it)
+            noise = rel(xo, ref)
+            assert rel(x, ref) < min(1e-7, max(1e-10, 10 * noise)), (p, rel(x, ref), noise)
+            r0 = np.sqrt(abs(np.dot(b, b)))                       # unconjugated, as the driver's dot(r, r)
+            _, info = M.solve(b, max_iterations=4 * it, tol=float(z["numpy_cg_tol"]) / r0)
+            assert abs(int(info.iterations[0]) - it) <= 1, (p, info.iterations, it)
+
+
+@pytest.mark.parametrize("name", ASPREC)
+def test_as_prec_multi_rhs_call_through_the_cl_module(gpu, cpu_ref, golden_dir, name, monkeypatch):
+    """UseCG == 2: ONE pcl.CG call with all subdomains as right-hand sides, the exact arrays as_prec built
+    (csingle / intc, recorded from the driver), through the drop-in `cl` module."""
+    monkeypatch.syspath_prepend(os.path.join(ROOT, "conjugate-gradient-pyopencl_b200"))
+    import sys
+    sys.modules.pop("cl", None)
+    import cl as pcl
+    z, A = _asprec(golden_dir, name)
+    k, size, its = int(z["cl_args_n_rhs"]), int(z["cl_args_size"]), int(z["cl_args_n_iterations"])
+    ctx, queue = pcl.initialize_cl_environment()
+    kernels = pcl.load_and_build_kernels(ctx, k)
+    x = z["cl_args_x_in"].copy()
+    out = pcl.CG(ctx, queue, kernels, size, int(z["cl_args_nnz"]), z["cl_args_a_values"], z["cl_args_b_values"],
+                 z["cl_args_a_pointers"], z["cl_args_a_cols"], x, k, its)
+    assert out is x
+    ref, wide = oracle_pair(cpu_ref, "c64", z["cl_args_a_values"], z["cl_args_a_pointers"], z["cl_args_a_cols"],
+                            z["cl_args_b_values"], k=k, iters=its)
+    check_parity(x, ref, wide, "c64")
+    # and the single-RHS variants (UseCG == 1 / 4): one call per subdomain gives the same columns
+    for p in range(k):
+        xp = np.zeros(size, np.csingle)
+        pcl.CG(ctx, queue, kernels, size, int(z["cl_args_nnz"]), z["cl_args_a_values"],
+               np.ascontiguousarray(z["cl_args_b_values"][p * size:(p + 1) * size]), z["cl_args_a_pointers"],
+               z["cl_args_a_cols"], xp, 1, its)
+        check_parity(xp, ref[p * size:(p + 1) * size], wide[p * size:(p + 1) * size], "c64")
+    gpu._lib.lib().cgb200_clear_cache()
+    sys.modules.pop("cl", None)

@@ -120,3 +120,72 @@ def test_c_oracle_edge_shapes(cpu_ref):
         assert np.linalg.norm(A @ x - b) <= 1e-10 * np.linalg.norm(b)
         y = cpu_ref.spmv(A.data, A.indptr, A.indices, b)
         assert np.allclose(y, A @ b, rtol=1e-13, atol=1e-13)
+
+
+# ---------------------------------------------------------------------------------------
+# the reference driver's own subdomain solves (oracle/run_reference_driver.py ran p_h-PY_C-CL.py unmodified)
+# ---------------------------------------------------------------------------------------
+ASPREC = ["asprec_2_12.npz", "asprec_3_16.npz"]
+
+
+def _asprec(golden_dir, name):
+    import scipy.sparse as sp
+    z = np.load(os.path.join(golden_dir, name))
+    n = int(z["n"])
+    return z, sp.csr_matrix((z["data"], z["indices"], z["indptr"]), shape=(n, n))
+
+
+@pytest.mark.parametrize("name", ASPREC)
+def test_driver_numpy_cg_restatement_is_bit_identical_to_the_reference_run(golden_dir, name):
+    """x_numpy_cg is what the reference driver's CG (p_h-PY_C-CL.py:1338-1369) returned inside as_prec when the
+    driver itself ran here; oracle/np_cg.cg_abs_tol must reproduce every bit, and the iteration counts."""
+    import np_cg
+    z, A = _asprec(golden_dir, name)
+    assert (abs(A - A.T) > 0).nnz == 0 and abs(A - A.conj().T).max() > 0.1      # complex-symmetric, not Hermitian
+    for p in range(z["z"].shape[0]):
+        x, it = np_cg.cg_abs_tol(A, z["z"][p], tol=float(z["numpy_cg_tol"]))
+        assert np.array_equal(x, z["x_numpy_cg"][p])
+        assert it == int(z["numpy_cg_iters"][p])
+
+
+@pytest.mark.parametrize("name", ASPREC)
+def test_c_oracle_on_the_driver_subdomain_systems(cpu_ref, golden_dir, name):
+    """The C restatement (device summation order) against the reference-run result at the same iteration count.
+    These subdomain operators are indefinite; after ~100 COCG iterations two summation orders of the same
+    double arithmetic are 4e-13 .. 6e-9 apart (measured), so the bar here is 1e-7, not 1e-10."""
+    z, A = _asprec(golden_dir, name)
+    for p in range(z["z"].shape[0]):
+        x, _, _ = cpu_ref.cg(A.data, A.indptr, A.indices, z["z"][p], iters=int(z["numpy_cg_iters"][p]))
+        ref = z["x_numpy_cg"][p]
+        assert np.linalg.norm(x - ref) / np.linalg.norm(ref) < 1e-7
+
+
+@pytest.mark.parametrize("name", ASPREC)
+def test_as_prec_builds_the_block_the_abi_expects(golden_dir, name):
+    """What as_prec hands to pcl.CG in its multi-RHS variant (p_h-PY_C-CL.py:1924-1937): csingle / intc arrays,
+    RHS p at offset p*size, x0 = 0, the SAME matrix for every subdomain."""
+    z, A = _asprec(golden_dir, name)
+    k, size = int(z["cl_args_n_rhs"]), int(z["cl_args_size"])
+    assert size == A.shape[0] and int(z["cl_args_nnz"]) == A.nnz and k == z["z"].shape[0]
+    assert z["cl_args_a_values"].dtype == np.csingle and z["cl_args_b_values"].dtype == np.csingle
+    assert z["cl_args_a_pointers"].dtype == np.intc and z["cl_args_a_cols"].dtype == np.intc
+    assert np.array_equal(z["cl_args_a_values"], A.data.astype(np.csingle))
+    assert np.array_equal(z["cl_args_b_values"].reshape(k, size), z["z"].astype(np.csingle))
+    assert not z["cl_args_x_in"].any()
+    g = z["gmres_iterations"]                   # variants 0 (exact), 1, 2 (CGMaxIT fixed, single), 5 (numpy CG to 1e-5)
+    assert len(g) == 4 and g[0] == g[3] and g[1] == g[2] >= g[0]
+
+
+@pytest.mark.reference
+def test_reference_driver_still_produces_the_committed_fixture(golden_dir, tmp_path):
+    """Build container only: run the unmodified driver again and compare with the committed fixture."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    old = dict(np.load(os.path.join(golden_dir, "asprec_2_12.npz")))
+    env = dict(os.environ, OMP_NUM_THREADS="2")
+    subprocess.check_call([sys.executable, os.path.join(root, "oracle", "run_reference_driver.py"), "2", "12", "40",
+                           "--out", str(tmp_path)], env=env, stdout=subprocess.DEVNULL)
+    new = np.load(os.path.join(str(tmp_path), "asprec_2_12.npz"))
+    for key in ("data", "indices", "indptr", "z", "x_numpy_cg", "numpy_cg_iters", "cl_args_b_values", "gmres_iterations"):
+        assert np.array_equal(old[key], new[key]), key
