@@ -5,6 +5,7 @@
 Outputs (all git-ignored, all travel to the GPU box with the snapshot):
     conjugate-gradient-pyopencl_b200/liboclcg.so   the library the package loads
     build/liboclcg.so                              where p_h-PY_C-CL.py:38 looks for it
+    build/oclcgex                                  the example executable (main.c), from csrc/oclcgex.c
     liboclcg.so                                    where p_helmholtz.py:29 looks for it
 """
 import os
@@ -55,7 +56,23 @@ def build(force=False, verbose=False):
         os.makedirs(os.path.dirname(dst), exist_ok=True)
         if not os.path.exists(dst) or os.path.getmtime(dst) < os.path.getmtime(LIB):
             shutil.copy2(LIB, dst)
+    build_example()
     return LIB
+
+
+EXE = os.path.join(ROOT, "build", "oclcgex")
+
+
+def build_example(force=False):
+    """build/oclcgex -- the reference's example executable (main.c; CMakeLists.txt:16), linked against
+    build/liboclcg.so (found at run time through $ORIGIN)."""
+    src = os.path.join(CSRC, "oclcgex.c")
+    if not force and os.path.exists(EXE) and os.path.getmtime(EXE) >= max(os.path.getmtime(src), os.path.getmtime(LIB)):
+        return EXE
+    gcc = shutil.which("gcc") or "/usr/bin/gcc"
+    subprocess.check_call([gcc, "-O2", "-std=c11", "-Wall", "-o", EXE, src, "-L" + os.path.join(ROOT, "build"),
+                           "-loclcg", "-lm", "-Wl,-rpath,$ORIGIN"])
+    return EXE
 
 
 if __name__ == "__main__":

@@ -70,6 +70,7 @@ struct cgb200_ctx {
     int sm_count = 0;
     int max_row = 0;
     double mean_row = 0;
+    int irregular = 0;           // row lengths vary wildly inside a tile (power-law graphs), see upload_matrix
     // CSR-stream schedule (k = 1): tiles of whole rows / chunks of long rows
     void *d_tiles = nullptr, *d_long = nullptr, *d_chunk_sum = nullptr;
     int ntiles = 0, nlong = 0, nslots = 0;
@@ -81,6 +82,9 @@ struct cgb200_ctx {
     int pdl = 7;                 // programmatic dependent launch of the loop kernels: 1 spmv, 2 update_xr, 4 update_d
     int trace_iters = 0;         // > 0: the kernels stamp a timeline of that many iterations into d_trace
     unsigned long long *d_trace = nullptr;
+    int pdl_early = 1;           // the trigger follows the wait at once (0: dependents start when the blocks exit)
+    int vec_carveout = -1;       // >= 0: preferred shared-memory carveout (percent) of the vector kernels
+    int auto_irregular = 1;      // spmv_variant 0 picks the per-non-zero balanced kernel for irregular matrices
     int defer_len = 16;          // rows longer than this (per lane) are walked by a whole warp, see spmv_tma_rows_kernel
     int coop = 0;
     // workspace (for ws_k right-hand sides)
@@ -215,6 +219,7 @@ template <typename T> struct Engine {
         s.partial = (T *)c->partial;
         s.hist = hist_cap > 0 ? c->d_hist : nullptr;
         s.hist_cap = hist_cap;
+        s.pdl_early = c->pdl_early;
         s.trace = c->trace_iters > 0 ? c->d_trace : nullptr;
         s.trace_cap = c->trace_iters;
         (void)tol;
@@ -345,17 +350,17 @@ template <typename T> struct Engine {
     }
     template <int S, bool DOT>
     static int spmv_tma(cgb200_ctx *c, const T *x, T *y, const CgScalars<T> &sc) {
-        using C = StreamCfg<T>;
         using K = TmaCfg<T, S>;
         auto kern = spmv_tma_kernel<T, S, DOT>;
         const size_t smem = K::SMEM_BYTES;
         const void *key = (const void *)kern;
         if (c->occ.find(key) == c->occ.end())
             CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        const int grid = persistent_grid(c, kern, C::THREADS, smem, c->ntiles);
+        const int grid = persistent_grid(c, kern, K::NT, smem, c->ntiles);
         c->spmv_grid_last = grid;
-        kern<<<grid, C::THREADS, smem, c->stream>>>(c->ntiles, (const SpmvTile *)c->d_tiles, (const T *)c->d_vals,
-                                                    c->d_rowptr, c->d_cols, x, y, (T *)c->d_chunk_sum, sc);
+        CU(launch_kernel(kern, dim3(grid), dim3(K::NT), smem, c->stream, DOT && (c->pdl & 1), c->ntiles,
+                         (const SpmvTile *)c->d_tiles, (const T *)c->d_vals, (const int *)c->d_rowptr,
+                         (const int *)c->d_cols, x, y, (T *)c->d_chunk_sum, sc));
         c->launches++;
         if (c->nlong > 0) {
             combine_long_rows_kernel<T><<<(c->nlong + 127) / 128, 128, 0, c->stream>>>(
@@ -411,7 +416,9 @@ template <typename T> struct Engine {
     template <bool DOT>
     static int spmv(cgb200_ctx *c, int k, const T *x, T *y, const CgScalars<T> &sc) {
         if (k == 1) {
-            switch (c->d_tiles ? c->spmv_variant : 1) {
+            int variant = c->d_tiles ? c->spmv_variant : 1;
+            if (variant == 0 && c->irregular && c->auto_irregular && !sc.peer) variant = 3;
+            switch (variant) {
             case 1: return spmv1<DOT>(c, x, y, sc);
             case 2: return spmv_stream<DOT>(c, x, y, sc);
             case 4: return spmv_tma<3, DOT>(c, x, y, sc);
@@ -454,6 +461,7 @@ template <typename T> struct Engine {
     template <int V>
     static int launch_update_xr(cgb200_ctx *c, int k, const VecGeom &g, const CgScalars<T> &sc) {
         auto kern = update_xr_kernel<T, V>;
+        if (c->vec_carveout >= 0) cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, c->vec_carveout);
         const size_t smem = (size_t)g.block * V * sizeof(T);
         const int grid = persistent_grid(c, kern, g.block, smem, (long long)((g.npacks + g.block - 1) / g.block));
         CU(launch_kernel(kern, dim3(grid), dim3(g.block), smem, c->stream, (c->pdl & 2) != 0, g.npacks, g.nelem, k, g.kv,
@@ -464,6 +472,7 @@ template <typename T> struct Engine {
     template <int V>
     static int launch_update_d(cgb200_ctx *c, int k, const VecGeom &g, const CgScalars<T> &sc) {
         auto kern = update_d_kernel<T, V>;
+        if (c->vec_carveout >= 0) cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, c->vec_carveout);
         const int grid = persistent_grid(c, kern, g.block, 0, (long long)((g.npacks + g.block - 1) / g.block));
         CU(launch_kernel(kern, dim3(grid), dim3(g.block), 0, c->stream, (c->pdl & 4) != 0, g.npacks, g.nelem, k, g.kv,
                          (const T *)c->r, (T *)c->d, sc));
@@ -869,13 +878,18 @@ static int upload_matrix(cgb200_ctx *c, const void *aValues, const int *aPointer
     if (rp[0] != 0 || rp[n] != (int)nnz)
         return fail(CGB200_ERR_ARG, "aPointers[0]=%d aPointers[n]=%d but nnz=%lld", rp[0], rp[n], nnz);
     int mx = 0;
+    long long in_long_rows = 0;
     for (int i = 0; i < n; i++) {
         const int len = rp[i + 1] - rp[i];
         if (len < 0) return fail(CGB200_ERR_ARG, "aPointers not monotone at row %d", i);
         mx = std::max(mx, len);
+        if (len > 32) in_long_rows += len;
     }
     c->max_row = mx;
     c->mean_row = (double)nnz / n;
+    // the share of the non-zeros that sits in rows of more than 32 entries, next to a short mean row: the rows of
+    // a tile then differ wildly in length and the per-non-zero balanced kernel is the faster schedule
+    c->irregular = (nnz > 0 && c->mean_row < 32.0 && (double)in_long_rows > 0.05 * (double)nnz) ? 1 : 0;
     drop_graph(c);
     void **old[] = {&c->d_tiles, &c->d_long, &c->d_chunk_sum};
     for (void **b : old) {
@@ -1031,6 +1045,9 @@ static int *option_slot(cgb200_handle c, const char *key) {
     if (!strcmp(key, "solver")) return &c->solver;
     if (!strcmp(key, "defer_len")) return &c->defer_len;
     if (!strcmp(key, "pdl")) return &c->pdl;
+    if (!strcmp(key, "auto_irregular")) return &c->auto_irregular;
+    if (!strcmp(key, "pdl_early")) return &c->pdl_early;
+    if (!strcmp(key, "vec_carveout")) return &c->vec_carveout;
     if (!strcmp(key, "trace")) return &c->trace_iters;
     return nullptr;
 }

@@ -157,6 +157,7 @@ template <typename T> struct CgScalars {
     const double *tol;  // in device memory, so that one captured graph serves every tolerance
     T *rr;              // [k] this device's part of r.r when `defer` is set
     PeerComm *peer;     // non-NULL: the dot products are all-reduced inside the kernels through peer memory
+    int pdl_early;      // 1: let the next kernel's blocks become resident as soon as this one has started
     unsigned long long *trace;   // optional timeline, [trace_cap][8] globaltimer stamps (TR_*)
     int trace_cap;
     int defer;          // row-block sharded solve: the dot products are only partial sums here; the
@@ -606,31 +607,41 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
         if (++spins > (1u << 22)) __trap();
 }
 
+// The shape of a staged tile, shared by both TMA-fed kernels (the schedule is built once per matrix).
+struct RowTileCfg {
+    static constexpr int NT = 128;        // max rows per tile (= threads per block of the row-direct kernel)
+    static constexpr int TILE = 1024;     // staged non-zeros per tile
+    static constexpr int CAP = TILE - 4;  // non-zeros per tile (aligned windows may start 3 entries early)
+};
+
 template <typename T, int S> struct TmaCfg {
-    using C = StreamCfg<T>;
-    static constexpr int TILE = C::TILE;
+    static constexpr int NT = 256;                              // threads per block
+    static constexpr int TILE = RowTileCfg::TILE;
+    static constexpr int NPT = TILE / NT;                       // gathers in flight per thread
     static constexpr size_t VALS_BYTES = (size_t)TILE * sizeof(T);
     static constexpr size_t COLS_BYTES = (size_t)TILE * sizeof(int);
-    static constexpr size_t ROWS_BYTES = (size_t)(C::RMAX + 8) * sizeof(int);
+    static constexpr size_t ROWS_BYTES = (size_t)(RowTileCfg::NT + 8) * sizeof(int);
     static constexpr size_t STAGE_BYTES = VALS_BYTES + COLS_BYTES + ROWS_BYTES;
     static constexpr size_t BAR_BYTES = 128;
     static constexpr size_t PROD_BYTES = (size_t)TILE * sizeof(T);
-    static constexpr size_t RED_BYTES = (size_t)C::THREADS * sizeof(T);
+    static constexpr size_t RED_BYTES = (size_t)NT * sizeof(T);
     static constexpr size_t SMEM_BYTES = BAR_BYTES + PROD_BYTES + RED_BYTES + S * STAGE_BYTES;
     static_assert(STAGE_BYTES % 16 == 0 && PROD_BYTES % 16 == 0 && RED_BYTES % 16 == 0, "16-byte aligned stages");
 };
 
+// Balanced in both phases, for matrices whose row lengths vary wildly inside a tile (power-law graphs):
+//   1. thread t takes non-zeros t, t + 256, ... of the tile whatever rows they belong to: every gather of
+//      the tile is in flight at once (ONE L2 round trip per tile instead of one per 8 entries of the
+//      longest row), shared-memory reads are conflict-free, products go to shared memory;
+//   2. row sums out of shared memory, where a round costs ~30 cycles instead of an L2 round trip: a
+//      group of lpr lanes per row, and rows much longer than the rest are summed by a whole warp.
 template <typename T, int S, bool DOT>
 __global__ void __launch_bounds__(256)
 spmv_tma_kernel(int ntiles, const SpmvTile *__restrict__ tiles, const T *__restrict__ vals,
                 const int *__restrict__ rowptr, const int *__restrict__ cols, const T *__restrict__ x,
                 T *__restrict__ y, T *__restrict__ chunk_sum, CgScalars<T> sc) {
-    using C = StreamCfg<T>;
     using K = TmaCfg<T, S>;
-    constexpr int VPT = C::VPT, NT = C::THREADS, NPT = C::TILE / NT;
-    if (DOT) {
-        if (*sc.n_active == 0) return;
-    }
+    constexpr int VPT = VecW<T>::value, NT = K::NT, NPT = K::NPT;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem_raw);
     T *prod = reinterpret_cast<T *>(smem_raw + K::BAR_BYTES);
@@ -639,6 +650,7 @@ spmv_tma_kernel(int ntiles, const SpmvTile *__restrict__ tiles, const T *__restr
     const int t = threadIdx.x;
     const int count = ((int)blockIdx.x < ntiles) ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
     T dot[1] = {Sc<T>::zero()};
+    const unsigned long long stream_policy = l2_evict_first_policy();
 
     if (t == 0) {
         for (int s = 0; s < S; s++) mbar_init(&bars[s], 1);
@@ -662,10 +674,10 @@ spmv_tma_kernel(int ntiles, const SpmvTile *__restrict__ tiles, const T *__restr
         const bool has_nnz = tl.p1 > tl.p0;
         mbar_arrive_expect_tx(bar, (has_nnz ? vbytes + cbytes : 0u) + rbytes);
         if (has_nnz) {
-            bulk_g2s(st, vals + vb, vbytes, bar);
-            bulk_g2s(st + K::VALS_BYTES, cols + cb, cbytes, bar);
+            bulk_g2s_hint(st, vals + vb, vbytes, bar, stream_policy);
+            bulk_g2s_hint(st + K::VALS_BYTES, cols + cb, cbytes, bar, stream_policy);
         }
-        if (rbytes) bulk_g2s(st + K::VALS_BYTES + K::COLS_BYTES, rowptr + rb, rbytes, bar);
+        if (rbytes) bulk_g2s_hint(st + K::VALS_BYTES + K::COLS_BYTES, rowptr + rb, rbytes, bar, stream_policy);
     };
 
     if (t == 0)
@@ -673,6 +685,17 @@ spmv_tma_kernel(int ntiles, const SpmvTile *__restrict__ tiles, const T *__restr
 
     SpmvTile tl_next = {0, 0, 0, 0};
     if (count > 0) tl_next = tiles[blockIdx.x];
+
+    pdl_wait();        // the matrix is not the previous kernel's output; x and the scalars are
+    if (sc.pdl_early) pdl_trigger();
+    if (DOT) {
+        if (*sc.n_active == 0) {
+            if (t == 0)
+                for (int i = 0; i < S && i < count; i++) mbar_wait(&bars[i], 0u);
+            return;
+        }
+    }
+
     for (int i = 0; i < count; i++) {
         const SpmvTile tl = tl_next;
         if (i + 1 < count) tl_next = tiles[blockIdx.x + (size_t)(i + 1) * gridDim.x];
@@ -682,9 +705,20 @@ spmv_tma_kernel(int ntiles, const SpmvTile *__restrict__ tiles, const T *__restr
         const int *cols_s = reinterpret_cast<const int *>(st + K::VALS_BYTES);
         const int *rp_s = reinterpret_cast<const int *>(st + K::VALS_BYTES + K::COLS_BYTES);
         const int vb = tl.p0 - (tl.p0 % VPT), cb = tl.p0 & ~3;
+
+        // who sums which row in phase 2 (known from the descriptor alone, so x[row] for the fused dot can be
+        // requested before the stage has even arrived)
+        const int rows = tl.r1 >= 0 ? tl.r1 - tl.r0 : 0;
+        int lpr = 1;
+        while (lpr < 32 && rows * lpr * 2 <= NT) lpr *= 2;
+        const int rr = t / lpr, lane = t % lpr;
+        const bool valid = rr < rows;
+        T xr = Sc<T>::zero();
+        if (DOT && valid && lane == 0) xr = __ldg(x + tl.r0 + rr);
+
         mbar_wait(&bars[s], (unsigned)((i / S) & 1));
 
-        // ---- 1. products: columns from the stage, gather x, multiply, into `prod`
+        // ---- 1. products: every gather of the tile issued before the first multiply
         int cc[NPT];
 #pragma unroll
         for (int u = 0; u < NPT; u++) {
@@ -704,34 +738,45 @@ spmv_tma_kernel(int ntiles, const SpmvTile *__restrict__ tiles, const T *__restr
 
         if (tl.r1 >= 0) {
             // ---- 2. row sums
-            const int rows = tl.r1 - tl.r0;
             const int rb = tl.r0 & ~3;
-            int lpr = 1;
-            while (lpr < 32 && rows * lpr * 2 <= NT) lpr *= 2;
-            const int g = t / lpr, lane = t % lpr, groups = NT / lpr;
-            for (int rr0 = 0; rr0 < rows; rr0 += groups) {
-                const int rr = rr0 + g;
-                const bool valid = rr < rows;
-                T sum = Sc<T>::zero();
-                T xr = Sc<T>::zero();
-                if (valid) {
-                    if (DOT && lane == 0) xr = __ldg(x + tl.r0 + rr);
-                    const int lo = rp_s[tl.r0 + rr - rb] - tl.p0;
-                    const int hi = rp_s[tl.r0 + rr + 1 - rb] - tl.p0;
-                    for (int j = lo + lane; j < hi; j += lpr) sum = Sc<T>::add(sum, prod[j]);
+            int lo = 0, hi = 0;
+            if (valid) {
+                lo = rp_s[tl.r0 + rr - rb] - tl.p0;
+                hi = rp_s[tl.r0 + rr + 1 - rb] - tl.p0;
+            }
+            const bool deferred = valid && lpr < 32 && (hi - lo) > 16 * lpr;
+            T sum = Sc<T>::zero();
+            if (valid && !deferred)
+                for (int j = lo + lane; j < hi; j += lpr) sum = Sc<T>::add(sum, prod[j]);
+            for (int off = lpr >> 1; off > 0; off >>= 1) {
+                if constexpr (Sc<T>::cplx) {
+                    sum.x += __shfl_xor_sync(0xffffffffu, sum.x, off);
+                    sum.y += __shfl_xor_sync(0xffffffffu, sum.y, off);
+                } else {
+                    sum += __shfl_xor_sync(0xffffffffu, sum, off);
                 }
-                for (int off = lpr >> 1; off > 0; off >>= 1) {
+            }
+            unsigned pending = __ballot_sync(0xffffffffu, deferred && lane == 0);
+            while (pending) {
+                const int src = __ffs(pending) - 1;
+                pending &= pending - 1;
+                const int rlo = __shfl_sync(0xffffffffu, lo, src), rhi = __shfl_sync(0xffffffffu, hi, src);
+                T part = Sc<T>::zero();
+                for (int j = rlo + (t & 31); j < rhi; j += 32) part = Sc<T>::add(part, prod[j]);
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) {
                     if constexpr (Sc<T>::cplx) {
-                        sum.x += __shfl_xor_sync(0xffffffffu, sum.x, off);
-                        sum.y += __shfl_xor_sync(0xffffffffu, sum.y, off);
+                        part.x += __shfl_xor_sync(0xffffffffu, part.x, off);
+                        part.y += __shfl_xor_sync(0xffffffffu, part.y, off);
                     } else {
-                        sum += __shfl_xor_sync(0xffffffffu, sum, off);
+                        part += __shfl_xor_sync(0xffffffffu, part, off);
                     }
                 }
-                if (valid && lane == 0) {
-                    y[tl.r0 + rr] = sum;
-                    if (DOT) dot[0] = Sc<T>::fma(xr, sum, dot[0]);
-                }
+                if ((t & 31) == src) sum = part;
+            }
+            if (valid && lane == 0) {
+                y[tl.r0 + rr] = sum;
+                if (DOT) dot[0] = Sc<T>::fma(xr, sum, dot[0]);
             }
         } else {
             // ---- 2'. chunk of a long row: one sum for the whole tile
@@ -770,12 +815,6 @@ spmv_tma_kernel(int ntiles, const SpmvTile *__restrict__ tiles, const T *__restr
 // block-wide barrier per tile (to recycle the stage), all shared memory spent on stages,
 // i.e. on bytes in flight.
 // ---------------------------------------------------------------------------
-struct RowTileCfg {
-    static constexpr int NT = 128;        // threads per block = max rows per tile
-    static constexpr int TILE = 1024;     // staged non-zeros per tile
-    static constexpr int CAP = TILE - 4;  // non-zeros per tile (aligned windows may start 3 entries early)
-};
-
 template <typename T, int S> struct RowTmaCfg {
     static constexpr size_t VALS_BYTES = (size_t)RowTileCfg::TILE * sizeof(T);
     static constexpr size_t COLS_BYTES = (size_t)RowTileCfg::TILE * sizeof(int);
@@ -843,7 +882,7 @@ spmv_tma_rows_kernel(int ntiles, int ntiles_interior, int defer_len, const SpmvT
 
     // Everything above touched the matrix only.  The vectors and scalars are the previous kernel's output.
     pdl_wait();
-    pdl_trigger();
+    if (sc.pdl_early) pdl_trigger();
     if (DOT) {
         if (*sc.n_active == 0) {
             // nothing to do, but the copies already in flight must land before this block's shared memory is released
@@ -1033,7 +1072,7 @@ spmm_kernel(int n, int k, const T *__restrict__ vals, const int *__restrict__ ro
             const int *__restrict__ cols, const T *__restrict__ x, T *__restrict__ y,
             CgScalars<T> sc) {
     pdl_wait();
-    pdl_trigger();
+    if (sc.pdl_early) pdl_trigger();
     if (DOT) {
         if (*sc.n_active == 0) return;
     }
@@ -1176,7 +1215,7 @@ __global__ void __launch_bounds__(256)
 update_xr_kernel(size_t npacks, size_t nelem, int k, int kv, const T *__restrict__ d,
                  const T *__restrict__ q, T *__restrict__ x, T *__restrict__ r, CgScalars<T> sc) {
     pdl_wait();
-    pdl_trigger();
+    if (sc.pdl_early) pdl_trigger();
     if (*sc.n_active == 0) return;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     T *smem = reinterpret_cast<T *>(smem_raw);
@@ -1256,7 +1295,7 @@ __global__ void __launch_bounds__(256)
 update_d_kernel(size_t npacks, size_t nelem, int k, int kv, const T *__restrict__ r,
                 T *__restrict__ d, CgScalars<T> sc) {
     pdl_wait();
-    pdl_trigger();
+    if (sc.pdl_early) pdl_trigger();
     if (*sc.n_active == 0) return;
     using P = Pack<T, V>;
     const int t = threadIdx.x;

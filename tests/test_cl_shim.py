@@ -70,3 +70,28 @@ def test_oclcgex_cli_arguments(tmp_path, capsys):
     scipy.io.mmwrite(str(tmp_path / "sym.mtx"), sp.tril(A), symmetry="symmetric")
     B = oclcgex.load_csr(str(tmp_path / "sym.mtx"))
     assert abs(B - A).max() == 0 and B.has_sorted_indices
+
+
+def _native_oclcgex():
+    import cg_b200.build as B
+    B.build()
+    return B.EXE
+
+
+def test_native_oclcgex_arguments_and_matrix_market_errors(tmp_path):
+    """build/oclcgex (csrc/oclcgex.c), the compiled twin of main.c: usage (main.c:15-18), unreadable file
+    (main.c:21-24), a complex file with <is complex> = 0 -- all before any device work."""
+    import subprocess
+    import scipy.io, scipy.sparse as sp
+    exe = _native_oclcgex()
+    r = subprocess.run([exe, "a", "b"], capture_output=True, text=True)
+    assert r.returncode == 1 and "Usage: ./CG <input matrix file>" in r.stderr
+    r = subprocess.run([exe, str(tmp_path / "missing.mtx"), "1", "1", "10"], capture_output=True, text=True)
+    assert r.returncode == 1 and "Could not read matrix" in r.stdout
+    (tmp_path / "junk.mtx").write_text("%%MatrixMarket matrix array real general\n2 2\n1\n2\n3\n4\n")
+    r = subprocess.run([exe, str(tmp_path / "junk.mtx"), "1", "0", "10"], capture_output=True, text=True)
+    assert r.returncode == 1 and "Could not read matrix" in r.stdout          # dense `array` files are not sparse matrices
+    A = sp.csr_matrix(np.array([[4.0 + 1j, -1], [-1, 4.0]]))
+    scipy.io.mmwrite(str(tmp_path / "c.mtx"), A)
+    r = subprocess.run([exe, str(tmp_path / "c.mtx"), "1", "0", "10"], capture_output=True, text=True)
+    assert r.returncode == 1 and "matrix is complex" in r.stdout

@@ -713,3 +713,25 @@ def test_as_prec_multi_rhs_call_through_the_cl_module(gpu, cpu_ref, golden_dir, 
         check_parity(xp, ref[p * size:(p + 1) * size], wide[p * size:(p + 1) * size], "c64")
     gpu._lib.lib().cgb200_clear_cache()
     sys.modules.pop("cl", None)
+
+
+def test_native_oclcgex_executable(gpu, tmp_path):
+    """build/oclcgex <mtx> <nRHS> <isComplex> <nIter>: main.c's flow in C -- Matrix Market (symmetric storage,
+    complex and real, pattern) -> full CSR -> b = 5(r+1) -> cg() / cgd() from liboclcg.so."""
+    import subprocess
+    import scipy.io
+    import cg_b200.build as B
+    import cg_b200.problems as P
+    B.build()
+    A = P.helmholtz_fe(24)
+    scipy.io.mmwrite(str(tmp_path / "helm.mtx"), sp.tril(A), symmetry="symmetric")
+    r = subprocess.run([B.EXE, str(tmp_path / "helm.mtx"), "2", "1", "400", "--double"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    res = [float(l.split()[4]) for l in r.stdout.splitlines() if l.startswith("rhs")]
+    assert len(res) == 2 and max(res) < 1e-8, r.stdout
+    r = subprocess.run([B.EXE, str(tmp_path / "helm.mtx"), "3", "1", "60"], capture_output=True, text=True)
+    res = [float(l.split()[4]) for l in r.stdout.splitlines() if l.startswith("rhs")]
+    assert r.returncode == 0 and len(res) == 3 and max(res) < 1e-3, r.stdout + r.stderr
+    scipy.io.mmwrite(str(tmp_path / "poisson.mtx"), P.poisson2d(20))
+    r = subprocess.run([B.EXE, str(tmp_path / "poisson.mtx"), "1", "0", "100"], capture_output=True, text=True)
+    assert r.returncode == 0 and float(r.stdout.split()[4]) < 1e-4, r.stdout + r.stderr
