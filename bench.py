@@ -170,6 +170,20 @@ def measured_peak():
         return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md); MEASURED_PEAKS.json absent"
 
 
+def measured_traffic(workload, kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel`, from the latest committed
+    `ncu --set full` capture (profiles/rNN_traffic.json); only the default workload has one."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json")))
+    if workload != "c4" or not files:
+        return None, None
+    try:
+        ent = json.load(open(files[-1])).get(kernel)
+        return (float(ent["traffic"]), ent["source"]) if ent else (None, None)
+    except Exception:
+        return None, None
+
+
 def calibrate(cpu_ref, A, B, k):
     """Seconds per CG iteration of the oracle on this host (after one warm call)."""
     cpu_ref.lib().cpu_ref_set_threads(os.cpu_count() or 1)      # torchrun exports OMP_NUM_THREADS=1
@@ -571,13 +585,15 @@ def main():
                    "sample": f"{iters} CG iterations of the same system on the host "
                              f"(oracle/cpu_ref.c, OpenMP, {threads} threads of {os.cpu_count()} cpus), {dt:.1f} s"}
         dom = max(kernels, key=lambda nm: kernels[nm]["ms"])
+        traffic, traffic_src = measured_traffic(args.workload if (dtype, k) == (wl["dtype"], wl["k"]) else None, dom)
         line = {
             "metric": "CG iters/sec", "value": value, "unit": "iterations/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": dtype, "data": "synthetic",
             "config": config_of(args, wl, A, k, dtype, world),
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["gbs"], "peak": peak, "unit": "GB/s",
-                         "frac": kernels[dom]["frac"], "traffic": None, "peak_source": peak_src,
+                         "frac": kernels[dom]["frac"], "traffic": traffic, "traffic_source": traffic_src,
+                         "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": kernels[dom]["algorithmic_bytes"],
                          "ms_per_launch": kernels[dom]["ms"]},
             "kernels": kernels,

@@ -17,6 +17,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <set>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -70,6 +71,9 @@ struct cgb200_ctx {
     int sm_count = 0;
     int max_row = 0;
     double mean_row = 0;
+    int grid_nx = 0, grid_ny = 0;   // lexicographic grid strides detected in the column offsets (0: none), see detect_grid
+    void *d_runs = nullptr;        // row schedule of spmm_sched_kernel for sched_R row groups per block
+    int sched_R = 0, sched_units = 0, spmm_schedule = 1;
     int irregular = 0;           // row lengths vary wildly inside a tile (power-law graphs), see upload_matrix
     // CSR-stream schedule (k = 1): tiles of whole rows / chunks of long rows
     void *d_tiles = nullptr, *d_long = nullptr, *d_chunk_sum = nullptr;
@@ -79,7 +83,9 @@ struct cgb200_ctx {
     uint64_t rowptr_hash = 0;
     // options
     int opt_lpr = 0, graph_chunk = 16, use_graph = 1, blocks_per_sm = 0, spmv_variant = 0, solver = 0;
-    int pdl = 7;                 // programmatic dependent launch of the loop kernels: 1 spmv, 2 update_xr, 4 update_d
+    int pdl = 1;                 // programmatic dependent launch of the loop kernels: 1 spmv, 2 update_xr, 4 update_d
+                                 // (measured: 2 hurts -- blocks of the x/r update that become resident beside SpMV blocks inherit
+                                 //  the SpMV's shared-memory carve-out, i.e. a small L1, and stream slower for the whole kernel)
     int trace_iters = 0;         // > 0: the kernels stamp a timeline of that many iterations into d_trace
     unsigned long long *d_trace = nullptr;
     int pdl_early = 1;           // the trigger follows the wait at once (0: dependents start when the blocks exit)
@@ -390,11 +396,58 @@ template <typename T> struct Engine {
         }
         return 0;
     }
+    // Row schedule for grids (see spmm_sched_kernel): patches of PY x PZ lines, cut into runs of XS rows.
+    static int build_row_schedule(cgb200_ctx *c, int R) {
+        if (c->d_runs && c->sched_R == R) return 0;
+        if (c->d_runs) cudaFree(c->d_runs);
+        c->d_runs = nullptr;
+        c->sched_R = R;
+        c->sched_units = 0;
+        const long long nx = c->grid_nx, ny = c->grid_ny, n = c->n;
+        const long long nz = (n + nx * ny - 1) / (nx * ny);
+        int PY = R, PZ = 1;
+        if (nz > 1) {
+            PY = 1;
+            while (PY * PY < R) PY *= 2;
+            PZ = std::max(1, R / PY);
+        }
+        const int XS = 16;
+        std::vector<RowRun> runs;
+        for (long long z0 = 0; z0 < nz; z0 += PZ)
+            for (long long y0 = 0; y0 < ny; y0 += PY)
+                for (long long x0 = 0; x0 < nx; x0 += XS) {
+                    for (int g = 0; g < R; g++) {
+                        const long long yy = y0 + g % PY, zz = z0 + g / PY;
+                        RowRun rr = {0, 0};
+                        if (g < PY * PZ && yy < ny && zz < nz) {
+                            const long long start = x0 + nx * (yy + ny * zz);
+                            const long long len = std::min<long long>(std::min<long long>(XS, nx - x0), n - start);
+                            if (len > 0) rr = RowRun{(int)start, (int)len};
+                        }
+                        runs.push_back(rr);
+                    }
+                }
+        c->sched_units = (int)(runs.size() / R);
+        CU(cudaMalloc(&c->d_runs, std::max<size_t>(1, runs.size()) * sizeof(RowRun)));
+        CU(cudaMemcpy(c->d_runs, runs.data(), runs.size() * sizeof(RowRun), cudaMemcpyHostToDevice));
+        return 0;
+    }
     template <int V, int G, bool DOT>
     static int launch_spmm(cgb200_ctx *c, int k, const T *x, T *y, const CgScalars<T> &sc) {
-        auto kern = spmm_kernel<T, V, G, DOT>;
         const int block = 256;
         const size_t smem = (size_t)block * V * sizeof(T);
+        if (c->spmm_schedule && c->grid_nx > 0) {
+            auto kern = spmm_sched_kernel<T, V, G, DOT>;
+            TRY(build_row_schedule(c, block / G));
+            const int grid = persistent_grid(c, kern, block, smem, c->sched_units);
+            c->spmv_grid_last = grid;
+            CU(launch_kernel(kern, dim3(grid), dim3(block), smem, c->stream, DOT && (c->pdl & 1), c->n, k, c->sched_units,
+                             (const RowRun *)c->d_runs, (const T *)c->d_vals, (const int *)c->d_rowptr,
+                             (const int *)c->d_cols, x, y, sc));
+            c->launches++;
+            return 0;
+        }
+        auto kern = spmm_kernel<T, V, G, DOT>;
         const long long work = ((long long)c->n + (block / G) - 1) / (block / G);
         const int grid = persistent_grid(c, kern, block, smem, work);
         c->spmv_grid_last = grid;
@@ -860,6 +913,42 @@ static uint64_t hash_bytes(const void *ptr, size_t bytes, uint64_t seed) {
 }
 
 
+// Looks at the column offsets (col - row) of a sample of rows.  A matrix assembled on a lexicographically
+// numbered grid has very few distinct ones: {+-1, +-NX} in 2-D, {+-1, +-NX, +-NX*NY} in 3-D.  The strides only
+// steer the ORDER in which the SpMM kernel visits rows (locality); nothing depends on them being right.
+static void detect_grid(cgb200_ctx *c, const std::vector<int> &rp) {
+    c->grid_nx = c->grid_ny = 0;
+    if (c->d_runs) cudaFree(c->d_runs);
+    c->d_runs = nullptr;
+    c->sched_R = 0;
+    const int n = c->n;
+    if (n < 4096 || c->max_row < 3 || c->max_row > 9) return;
+    std::set<long long> offs;
+    std::vector<int> buf((size_t)c->max_row);
+    const int samples = 257;
+    for (int s = 0; s < samples; s++) {
+        const int i = (int)((long long)s * (n - 1) / (samples - 1));
+        const int len = rp[i + 1] - rp[i];
+        if (len <= 0) continue;
+        if (cudaMemcpy(buf.data(), c->d_cols + rp[i], (size_t)len * sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) {
+            cudaGetLastError();
+            return;
+        }
+        for (int j = 0; j < len; j++) offs.insert((long long)buf[j] - i);
+        if (offs.size() > 9) return;
+    }
+    std::vector<long long> pos;
+    for (long long o : offs)
+        if (o > 0) pos.push_back(o);
+    if (pos.size() == 2 && pos[0] == 1 && pos[1] >= 8) {
+        c->grid_nx = (int)pos[1];
+        c->grid_ny = (int)((n + pos[1] - 1) / pos[1]);
+    } else if (pos.size() == 3 && pos[0] == 1 && pos[1] >= 8 && pos[2] % pos[1] == 0) {
+        c->grid_nx = (int)pos[1];
+        c->grid_ny = (int)(pos[2] / pos[1]);
+    }
+}
+
 // Copies the CSR arrays (host or device pointers) into the handle's buffers and (re)builds the
 // SpMV schedule when the sparsity pattern's row offsets changed.
 static int upload_matrix(cgb200_ctx *c, const void *aValues, const int *aPointers, const int *aCols) {
@@ -898,6 +987,7 @@ static int upload_matrix(cgb200_ctx *c, const void *aValues, const int *aPointer
     }
     TRY(DISPATCH(c, E::build_tiles(c, rp)));
     c->rowptr_hash = rh;
+    detect_grid(c, rp);
     return 0;
 }
 
@@ -1006,6 +1096,7 @@ int cgb200_destroy(cgb200_handle c) {
     free_workspace(c);
     if (c->d_hist) cudaFree(c->d_hist);
     if (c->d_trace) cudaFree(c->d_trace);
+    if (c->d_runs) cudaFree(c->d_runs);
     if (c->d_tiles) cudaFree(c->d_tiles);
     if (c->d_long) cudaFree(c->d_long);
     if (c->d_chunk_sum) cudaFree(c->d_chunk_sum);
@@ -1046,6 +1137,7 @@ static int *option_slot(cgb200_handle c, const char *key) {
     if (!strcmp(key, "defer_len")) return &c->defer_len;
     if (!strcmp(key, "pdl")) return &c->pdl;
     if (!strcmp(key, "auto_irregular")) return &c->auto_irregular;
+    if (!strcmp(key, "spmm_schedule")) return &c->spmm_schedule;
     if (!strcmp(key, "pdl_early")) return &c->pdl_early;
     if (!strcmp(key, "vec_carveout")) return &c->vec_carveout;
     if (!strcmp(key, "trace")) return &c->trace_iters;

@@ -1132,6 +1132,89 @@ spmm_kernel(int n, int k, const T *__restrict__ vals, const int *__restrict__ ro
 }
 
 // ---------------------------------------------------------------------------
+// SpMM with a row SCHEDULE, for matrices whose columns sit at a few fixed offsets from the diagonal
+// (finite-difference / finite-element grids numbered lexicographically).
+//
+// spmm_kernel hands consecutive rows to consecutive blocks, so the only reuse an SM's L1 sees is the
+// +-1 neighbour: of the 7 k-wide rows of x a 7-point row gathers, 5 come from L2, and at k = 32 the
+// kernel is bound by L2 -> SM traffic (5 x the vector), not by HBM.  Here a block instead owns a patch of
+// PY x PZ grid lines and marches along them: the R = PY*PZ row groups of the block work on rows
+// start_g + s at step s, so the x rows gathered as "+1" at one step are the centre of the next and the
+// "-1" of the one after, and the +-NX / +-NX*NY neighbours inside the patch are gathered by the same
+// block in the same step.  What still comes from L2 is the next slice (R rows) plus the patch faces:
+// 2 x the vector for a 4 x 4 patch instead of 5 x.  The schedule (RowRun per group per unit) is built on
+// the host from the detected strides; ANY schedule gives the same bits, rows are independent.
+// ---------------------------------------------------------------------------
+struct RowRun {
+    int start;   // first row of the run
+    int len;     // consecutive rows (0: idle group)
+};
+
+template <typename T, int V, int G, bool DOT>
+__global__ void __launch_bounds__(256)
+spmm_sched_kernel(int n, int k, int nunits, const RowRun *__restrict__ runs, const T *__restrict__ vals,
+                  const int *__restrict__ rowptr, const int *__restrict__ cols, const T *__restrict__ x,
+                  T *__restrict__ y, CgScalars<T> sc) {
+    pdl_wait();
+    if (sc.pdl_early) pdl_trigger();
+    if (DOT) {
+        if (*sc.n_active == 0) return;
+    }
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    T *smem = reinterpret_cast<T *>(smem_raw);
+    using P = Pack<T, V>;
+    const int t = threadIdx.x;
+    const int cp = t % G, grp = t / G;
+    const int kv = k / V;
+    const bool active = cp < kv;
+    const int R = blockDim.x / G;
+    T dot[V];
+#pragma unroll
+    for (int v = 0; v < V; v++) dot[v] = Sc<T>::zero();
+
+    for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
+        const RowRun run = runs[(size_t)u * R + grp];
+        if (!active) continue;
+        for (int s = 0; s < run.len; s++) {
+            const int row = run.start + s;
+            const int lo = __ldg(rowptr + row), hi = __ldg(rowptr + row + 1);
+            T acc[V];
+#pragma unroll
+            for (int v = 0; v < V; v++) acc[v] = Sc<T>::zero();
+#pragma unroll 4
+            for (int j = lo; j < hi; j++) {
+                const T a = __ldg(vals + j);
+                const int c = __ldg(cols + j);
+                const P xv = *reinterpret_cast<const P *>(x + (size_t)c * k + (size_t)cp * V);
+#pragma unroll
+                for (int v = 0; v < V; v++) acc[v] = Sc<T>::fma(a, xv.v[v], acc[v]);
+            }
+            P out;
+#pragma unroll
+            for (int v = 0; v < V; v++) out.v[v] = acc[v];
+            *reinterpret_cast<P *>(y + (size_t)row * k + (size_t)cp * V) = out;
+            if (DOT) {
+                const P xo = *reinterpret_cast<const P *>(x + (size_t)row * k + (size_t)cp * V);
+#pragma unroll
+                for (int v = 0; v < V; v++) dot[v] = Sc<T>::fma(xo.v[v], acc[v], dot[v]);
+            }
+        }
+    }
+
+    if (DOT) {
+        block_col_reduce<T, V>(dot, G, smem);
+        if (publish_and_arrive<T, V>(smem, kv, k, sc.partial, sc.ticket + TK_SPMV)) {
+            grid_col_reduce<T, V>(sc.partial, G, kv, k, smem);
+            if (t < kv) {
+#pragma unroll
+                for (int v = 0; v < V; v++) sc.dq[t * V + v] = smem[t * V + v];
+            }
+            if (t == 0) sc.ticket[TK_SPMV] = 0;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
 // Vector kernels.  The [n][k] array is walked as packs of V values; thread g of the
 // grid owns packs g, g + stride, ... with stride = gridDim*blockDim a multiple of
 // kv = k/V, so a thread always sees the same V columns: column(v) = (t % kv)*V + v.

@@ -75,7 +75,8 @@ CGB200_API int cgb200_set_stream(cgb200_handle h, void *cuda_stream);
  *                    0 auto (= 6)
  *                    1 CSR-vector: lanes_per_row lanes per row
  *                    2 CSR-stream: tiles of non-zeros, products staged in shared memory, plain loads
- *                    3/4/5 CSR-stream fed by TMA bulk copies through a 2/3/4-stage mbarrier ring
+ *                    3/4/5 CSR-stream fed by TMA bulk copies through a 2/3/4-stage mbarrier ring: every gather of a
+ *                          tile in flight at once, balanced row sums (the schedule for power-law matrices)
  *                    6/7/8/9 row-direct CSR-stream fed by TMA (2/3/4/6 stages, no product buffer)
  *   "solver"         0 auto: one cooperative launch for the whole solve when an iteration's working set
  *                      fits the L2 (2 grid barriers per iteration), else three kernels per iteration
@@ -87,7 +88,12 @@ CGB200_API int cgb200_set_stream(cgb200_handle h, void *cuda_stream);
  *   "defer_len"      rows with more than this many non-zeros per lane are walked by a whole warp (default 16,
  *                    0 off): keeps a tile of a power-law matrix from waiting for its longest row
  *   "pdl"            bit mask, programmatic dependent launch of 1 spmv | 2 x/r update | 4 direction update
- *                    (default 7): a kernel's prologue overlaps the tail of the one before it
+ *                    (default 1): the SpMV's prologue -- barriers, first matrix tiles by TMA -- overlaps the tail
+ *                    of the direction update
+ *   "pdl_early"      1 (default): a kernel lets its dependents become resident as soon as it has started
+ *   "auto_irregular" 1 (default): spmv_variant 0 picks variant 3 for matrices whose row lengths vary wildly
+ *   "spmm_schedule"  1 (default): k > 1 on a matrix with grid structure (few fixed column offsets) visits rows
+ *                    patch by patch for L1 reuse of the gathered rows (spmm_sched_kernel)
  *   "trace"          n > 0: the loop kernels stamp %globaltimer into an 8-slot record per iteration for the
  *                    first n iterations of a solve; read it with cgb200_read_trace()
  */

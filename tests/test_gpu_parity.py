@@ -624,7 +624,7 @@ def test_programmatic_dependent_launch_changes_nothing(gpu, k):
     out = {}
     with gpu.Matrix.from_scipy(A) as M:
         M.set_option("solver", 1)
-        assert M.get_option("pdl") == 7
+        assert M.get_option("pdl") == 1
         for pdl in (0, 7, 1, 2, 4):
             for graph in (0, 1):
                 M.set_option("pdl", pdl)
@@ -735,3 +735,37 @@ def test_native_oclcgex_executable(gpu, tmp_path):
     scipy.io.mmwrite(str(tmp_path / "poisson.mtx"), P.poisson2d(20))
     r = subprocess.run([B.EXE, str(tmp_path / "poisson.mtx"), "1", "0", "100"], capture_output=True, text=True)
     assert r.returncode == 0 and float(r.stdout.split()[4]) < 1e-4, r.stdout + r.stderr
+
+
+@pytest.mark.parametrize("dname", ["f64", "c64"])
+@pytest.mark.parametrize("kind,k", [("lap3d", 32), ("lap3d", 8), ("lap3d", 3), ("lap3d", 2), ("poisson", 4), ("poisson", 32)])
+def test_spmm_row_schedule_on_grids(gpu, cpu_ref, dname, kind, k):
+    """k > 1 on a matrix with grid structure: rows are visited patch by patch (spmm_sched_kernel).  Rows are
+    independent, so y has the same bits as with the plain row order; the CG iterate (whose dot products are
+    summed in a different block order) agrees with the oracle as usual.  Grids whose size is not a multiple of
+    the patch, more row groups than patch lines, a matrix without grid structure."""
+    import cg_b200.problems as P
+    dt = DT[dname]
+    A = (P.laplace3d(21) if kind == "lap3d" else P.poisson2d(83)).astype(dt)
+    A.sort_indices()
+    n = A.shape[0]
+    rng = np.random.default_rng(k)
+    X = np.concatenate([rand(rng, n, dt) for _ in range(k)])
+    with gpu.Matrix.from_scipy(A) as M:
+        assert M.get_option("spmm_schedule") == 1
+        M.set_option("solver", 1)                 # three kernels per iteration: the SpMM kernel fused with d.q
+        y1 = M.spmv(X, k=k)
+        x1, _ = M.solve(X, k=k, max_iterations=25)
+        M.set_option("spmm_schedule", 0)
+        y0 = M.spmv(X, k=k)
+    assert np.array_equal(y0, y1)
+    exact = np.concatenate([A @ X[c * n:(c + 1) * n] for c in range(k)])
+    assert rel(y1, exact) < (2e-6 if dname == "c64" else 1e-14)
+    ref, wide = oracle_pair(cpu_ref, dname, A.data, A.indptr, A.indices, X, k=k, iters=25)
+    check_parity(x1, ref, wide, dname)
+    # no grid structure (random columns): the plain order is used, same answers
+    B = (A + sp.random(n, n, density=2.0 / n, random_state=1, format="csr").astype(dt)).tocsr()
+    B.sort_indices()
+    with gpu.Matrix.from_scipy(B) as M:
+        yb = M.spmv(X, k=k)
+    assert rel(yb, np.concatenate([B @ X[c * n:(c + 1) * n] for c in range(k)])) < (2e-6 if dname == "c64" else 1e-13)
