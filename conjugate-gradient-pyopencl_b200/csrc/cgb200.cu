@@ -73,7 +73,7 @@ struct cgb200_ctx {
     double mean_row = 0;
     int grid_nx = 0, grid_ny = 0;   // lexicographic grid strides detected in the column offsets (0: none), see detect_grid
     void *d_runs = nullptr;        // row schedule of spmm_sched_kernel for sched_R row groups per block
-    int sched_R = 0, sched_units = 0, spmm_schedule = 1;
+    int sched_R = 0, sched_units = 0, spmm_schedule = 0;   // measured slower than the plain row order: off
     int irregular = 0;           // row lengths vary wildly inside a tile (power-law graphs), see upload_matrix
     // CSR-stream schedule (k = 1): tiles of whole rows / chunks of long rows
     void *d_tiles = nullptr, *d_long = nullptr, *d_chunk_sum = nullptr;
@@ -90,6 +90,7 @@ struct cgb200_ctx {
     unsigned long long *d_trace = nullptr;
     int pdl_early = 1;           // the trigger follows the wait at once (0: dependents start when the blocks exit)
     int vec_carveout = -1;       // >= 0: preferred shared-memory carveout (percent) of the vector kernels
+    int l2_keep = 0;             // d, q, r tagged evict-last in L2: 0 off, 1 on, -1 auto by size
     int auto_irregular = 1;      // spmv_variant 0 picks the per-non-zero balanced kernel for irregular matrices
     int defer_len = 16;          // rows longer than this (per lane) are walked by a whole warp, see spmv_tma_rows_kernel
     int coop = 0;
@@ -226,6 +227,8 @@ template <typename T> struct Engine {
         s.hist = hist_cap > 0 ? c->d_hist : nullptr;
         s.hist_cap = hist_cap;
         s.pdl_early = c->pdl_early;
+        // 0 off, 1 on, -1 auto: on when d, q, r (3 vectors) take at most half of a 126 MB L2
+        s.l2_keep = c->l2_keep >= 0 ? c->l2_keep : ((double)c->n * k * sizeof(T) * 3.0 <= 63e6 ? 1 : 0);
         s.trace = c->trace_iters > 0 ? c->d_trace : nullptr;
         s.trace_cap = c->trace_iters;
         (void)tol;
@@ -1137,6 +1140,7 @@ static int *option_slot(cgb200_handle c, const char *key) {
     if (!strcmp(key, "defer_len")) return &c->defer_len;
     if (!strcmp(key, "pdl")) return &c->pdl;
     if (!strcmp(key, "auto_irregular")) return &c->auto_irregular;
+    if (!strcmp(key, "l2_keep")) return &c->l2_keep;
     if (!strcmp(key, "spmm_schedule")) return &c->spmm_schedule;
     if (!strcmp(key, "pdl_early")) return &c->pdl_early;
     if (!strcmp(key, "vec_carveout")) return &c->vec_carveout;

@@ -157,6 +157,7 @@ template <typename T> struct CgScalars {
     const double *tol;  // in device memory, so that one captured graph serves every tolerance
     T *rr;              // [k] this device's part of r.r when `defer` is set
     PeerComm *peer;     // non-NULL: the dot products are all-reduced inside the kernels through peer memory
+    int l2_keep;        // 1: d, q and r are tagged evict-last in L2 (the system's vectors fit the L2)
     int pdl_early;      // 1: let the next kernel's blocks become resident as soon as this one has started
     unsigned long long *trace;   // optional timeline, [trace_cap][8] globaltimer stamps (TR_*)
     int trace_cap;
@@ -281,6 +282,50 @@ template <typename P> __device__ __forceinline__ void st_stream_bytes(P *p, cons
         unsigned v;
         memcpy(&v, &val, 4);
         __stcs(reinterpret_cast<unsigned *>(p), v);
+    }
+}
+// Loads / stores of 4, 8 or 16 bytes that carry an L2 eviction policy (createpolicy): the working vectors
+// d, q, r of a system that fits the 126 MB L2 are tagged evict-last so that the matrix stream (evict-first)
+// and x (streamed) leave them resident from kernel to kernel and from iteration to iteration.
+__device__ __forceinline__ unsigned long long l2_policy(bool keep) {
+    unsigned long long pol;
+    if (keep) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+template <typename P> __device__ __forceinline__ P ld_hint_bytes(const P *p, unsigned long long pol) {
+    P out;
+    if constexpr (sizeof(P) == 16) {
+        unsigned long long a, b;
+        asm volatile("ld.global.L2::cache_hint.v2.b64 {%0, %1}, [%2], %3;" : "=l"(a), "=l"(b) : "l"(p), "l"(pol));
+        unsigned long long v[2] = {a, b};
+        memcpy(&out, v, 16);
+    } else if constexpr (sizeof(P) == 8) {
+        unsigned long long a;
+        asm volatile("ld.global.L2::cache_hint.b64 %0, [%1], %2;" : "=l"(a) : "l"(p), "l"(pol));
+        memcpy(&out, &a, 8);
+    } else {
+        static_assert(sizeof(P) == 4, "ld_hint_bytes: 4, 8 or 16 bytes");
+        unsigned a;
+        asm volatile("ld.global.L2::cache_hint.b32 %0, [%1], %2;" : "=r"(a) : "l"(p), "l"(pol));
+        memcpy(&out, &a, 4);
+    }
+    return out;
+}
+template <typename P> __device__ __forceinline__ void st_hint_bytes(P *p, const P &val, unsigned long long pol) {
+    if constexpr (sizeof(P) == 16) {
+        unsigned long long v[2];
+        memcpy(v, &val, 16);
+        asm volatile("st.global.L2::cache_hint.v2.b64 [%0], {%1, %2}, %3;" ::"l"(p), "l"(v[0]), "l"(v[1]), "l"(pol) : "memory");
+    } else if constexpr (sizeof(P) == 8) {
+        unsigned long long a;
+        memcpy(&a, &val, 8);
+        asm volatile("st.global.L2::cache_hint.b64 [%0], %1, %2;" ::"l"(p), "l"(a), "l"(pol) : "memory");
+    } else {
+        static_assert(sizeof(P) == 4, "st_hint_bytes: 4, 8 or 16 bytes");
+        unsigned a;
+        memcpy(&a, &val, 4);
+        asm volatile("st.global.L2::cache_hint.b32 [%0], %1, %2;" ::"l"(p), "r"(a), "l"(pol) : "memory");
     }
 }
 // Cross-block data (partials) must come from L2, never from a stale L1 line.
@@ -842,6 +887,7 @@ spmv_tma_rows_kernel(int ntiles, int ntiles_interior, int defer_len, const SpmvT
     const int count = ((int)blockIdx.x < ntiles) ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
     T dot[1] = {Sc<T>::zero()};
     const unsigned long long stream_policy = l2_evict_first_policy();
+    const unsigned long long keep = l2_policy(sc.l2_keep != 0);
 
     if (t == 0) {
         for (int s = 0; s < S; s++) mbar_init(&bars[s], 1);
@@ -998,7 +1044,7 @@ spmv_tma_rows_kernel(int ntiles, int ntiles_interior, int defer_len, const SpmvT
                 if (wl == src) sum = part;
             }
             if (valid && lane == 0) {
-                y[tl.r0 + rr] = sum;
+                st_hint_bytes(y + tl.r0 + rr, sum, keep);
                 if (DOT) dot[0] = Sc<T>::fma(xr, sum, dot[0]);
             }
         } else {
@@ -1305,6 +1351,7 @@ update_xr_kernel(size_t npacks, size_t nelem, int k, int kv, const T *__restrict
     using P = Pack<T, V>;
     const int t = threadIdx.x;
     if (sc.trace && blockIdx.x == 0 && t == 0) trace_mark<T>(sc, *sc.it, TR_XR_START);
+    const unsigned long long keep = l2_policy(sc.l2_keep != 0);
     T alpha[V], acc[V];
 #pragma unroll
     for (int v = 0; v < V; v++) {
@@ -1318,12 +1365,12 @@ update_xr_kernel(size_t npacks, size_t nelem, int k, int kv, const T *__restrict
     }
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t p = (size_t)blockIdx.x * blockDim.x + t; p < npacks; p += stride) {
-        const P dv = reinterpret_cast<const P *>(d)[p];
-        const P qv = reinterpret_cast<const P *>(q)[p];
+        const P dv = ld_hint_bytes(reinterpret_cast<const P *>(d) + p, keep);
+        const P qv = ld_hint_bytes(reinterpret_cast<const P *>(q) + p, keep);
         // x is touched by this kernel only, once per iteration: streamed (evict-first) in both directions so
         // that it never displaces r, d and q -- which three kernels share -- from the 126 MB L2
         P xv = ld_stream_bytes(reinterpret_cast<const P *>(x) + p);
-        P rv = reinterpret_cast<const P *>(r)[p];
+        P rv = ld_hint_bytes(reinterpret_cast<const P *>(r) + p, keep);
 #pragma unroll
         for (int v = 0; v < V; v++) {
             xv.v[v] = Sc<T>::fma(alpha[v], dv.v[v], xv.v[v]);
@@ -1331,7 +1378,7 @@ update_xr_kernel(size_t npacks, size_t nelem, int k, int kv, const T *__restrict
             acc[v] = Sc<T>::fma(rv.v[v], rv.v[v], acc[v]);
         }
         st_stream_bytes(reinterpret_cast<P *>(x) + p, xv);
-        reinterpret_cast<P *>(r)[p] = rv;
+        st_hint_bytes(reinterpret_cast<P *>(r) + p, rv, keep);
     }
     if (V > 1 && blockIdx.x == 0) {
         const size_t e = npacks * V + t;
@@ -1383,6 +1430,7 @@ update_d_kernel(size_t npacks, size_t nelem, int k, int kv, const T *__restrict_
     using P = Pack<T, V>;
     const int t = threadIdx.x;
     if (sc.trace && blockIdx.x == 0 && t == 0) trace_mark<T>(sc, *sc.it - 1, TR_D_START);
+    const unsigned long long keep = l2_policy(sc.l2_keep != 0);
     T beta[V];
 #pragma unroll
     for (int v = 0; v < V; v++) {
@@ -1395,11 +1443,11 @@ update_d_kernel(size_t npacks, size_t nelem, int k, int kv, const T *__restrict_
     }
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t p = (size_t)blockIdx.x * blockDim.x + t; p < npacks; p += stride) {
-        const P rv = reinterpret_cast<const P *>(r)[p];
-        P dv = reinterpret_cast<const P *>(d)[p];
+        const P rv = ld_hint_bytes(reinterpret_cast<const P *>(r) + p, keep);
+        P dv = ld_hint_bytes(reinterpret_cast<const P *>(d) + p, keep);
 #pragma unroll
         for (int v = 0; v < V; v++) dv.v[v] = Sc<T>::fma(beta[v], dv.v[v], rv.v[v]);
-        reinterpret_cast<P *>(d)[p] = dv;
+        st_hint_bytes(reinterpret_cast<P *>(d) + p, dv, keep);
     }
     if (V > 1 && blockIdx.x == 0) {
         const size_t e = npacks * V + t;

@@ -92,7 +92,9 @@ CGB200_API int cgb200_set_stream(cgb200_handle h, void *cuda_stream);
  *                    of the direction update
  *   "pdl_early"      1 (default): a kernel lets its dependents become resident as soon as it has started
  *   "auto_irregular" 1 (default): spmv_variant 0 picks variant 3 for matrices whose row lengths vary wildly
- *   "spmm_schedule"  1 (default): k > 1 on a matrix with grid structure (few fixed column offsets) visits rows
+ *   "l2_keep"        d, q and r tagged evict-last in L2 (matrix stream and x are evict-first): 0 off, 1 on,
+ *                    -1 by size (on when the three vectors fit half the L2)
+ *   "spmm_schedule"  0 (default) | 1: k > 1 on a matrix with grid structure (few fixed column offsets) visits rows
  *                    patch by patch for L1 reuse of the gathered rows (spmm_sched_kernel)
  *   "trace"          n > 0: the loop kernels stamp %globaltimer into an 8-slot record per iteration for the
  *                    first n iterations of a solve; read it with cgb200_read_trace()
