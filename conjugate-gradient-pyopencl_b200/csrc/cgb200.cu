@@ -74,6 +74,10 @@ struct cgb200_ctx {
     int grid_nx = 0, grid_ny = 0;   // lexicographic grid strides detected in the column offsets (0: none), see detect_grid
     void *d_runs = nullptr;        // row schedule of spmm_sched_kernel for sched_R row groups per block
     int sched_R = 0, sched_units = 0, spmm_schedule = 0;   // measured slower than the plain row order: off
+    // row-pattern dictionary (k = 1), see spmv_pattern_kernel
+    void *d_pat = nullptr, *d_pat_table = nullptr, *d_pat_build = nullptr, *d_plen = nullptr, *d_poff = nullptr, *d_pval = nullptr;
+    int *d_pat_chunks = nullptr;
+    int npat = 0, pat_ok = 0, pattern = 1, pat_chunks = 0, pat_chunks_interior = 0;
     int irregular = 0;           // row lengths vary wildly inside a tile (power-law graphs), see upload_matrix
     // CSR-stream schedule (k = 1): tiles of whole rows / chunks of long rows
     void *d_tiles = nullptr, *d_long = nullptr, *d_chunk_sum = nullptr;
@@ -285,6 +289,79 @@ template <typename T> struct Engine {
         default: return launch_spmv1<32, DOT>(c, x, y, sc);
         }
     }
+    // ---- row-pattern dictionary ------------------------------------------------
+    // Built on the device at every matrix upload (values are part of a pattern); a few passes over the CSR arrays.
+    static int build_patterns(cgb200_ctx *c) {
+        c->pat_ok = 0;
+        c->npat = 0;
+        if (!c->pattern || c->n < 1 || c->max_row > PAT_MAXLEN || c->max_row < 1) return 0;
+        const int n = c->n;
+        if (!c->d_pat) {
+            CU(cudaMalloc(&c->d_pat, (size_t)n * sizeof(unsigned short) + 64));
+            CU(cudaMalloc(&c->d_pat_table, (size_t)PAT_TABLE_SLOTS * sizeof(PatSlot)));
+            CU(cudaMalloc(&c->d_pat_build, sizeof(PatBuild)));
+            CU(cudaMalloc(&c->d_plen, (size_t)PAT_MAXCOUNT * sizeof(int)));
+            CU(cudaMalloc(&c->d_poff, (size_t)PAT_MAXCOUNT * PAT_MAXLEN * sizeof(int)));
+            CU(cudaMalloc(&c->d_pval, (size_t)PAT_MAXCOUNT * PAT_MAXLEN * sizeof(T)));
+        }
+        CU(cudaMemsetAsync(c->d_pat_table, 0, (size_t)PAT_TABLE_SLOTS * sizeof(PatSlot), c->stream));
+        CU(cudaMemsetAsync(c->d_pat_build, 0, sizeof(PatBuild), c->stream));
+        const int grid = c->sm_count * 8;
+        pat_insert_kernel<T><<<grid, 256, 0, c->stream>>>(n, (const T *)c->d_vals, c->d_rowptr, c->d_cols,
+                                                          (PatSlot *)c->d_pat_table, (PatBuild *)c->d_pat_build);
+        pat_assign_kernel<T><<<grid, 256, 0, c->stream>>>(n, (const T *)c->d_vals, c->d_rowptr, c->d_cols,
+                                                          (const PatSlot *)c->d_pat_table, (PatBuild *)c->d_pat_build,
+                                                          (unsigned short *)c->d_pat);
+        pat_table_kernel<T><<<64, 256, 0, c->stream>>>((const T *)c->d_vals, c->d_rowptr, c->d_cols,
+                                                       (const PatSlot *)c->d_pat_table, (const PatBuild *)c->d_pat_build,
+                                                       (int *)c->d_plen, (int *)c->d_poff, (T *)c->d_pval);
+        PatBuild pb;
+        CU(cudaMemcpyAsync(&pb, c->d_pat_build, sizeof(pb), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        c->launches += 3;
+        if (pb.fail || pb.count < 1 || pb.count > PAT_MAXCOUNT) return 0;
+        c->npat = pb.count;
+        c->pat_ok = 1;
+        // chunk schedule: row-block shards visit the chunks that touch halo columns last
+        const int nchunks = (n + PAT_CHUNK - 1) / PAT_CHUNK;
+        c->pat_chunks = c->pat_chunks_interior = nchunks;
+        if (c->d_pat_chunks) cudaFree(c->d_pat_chunks);
+        c->d_pat_chunks = nullptr;
+        if (!c->row_boundary.empty()) {
+            std::vector<int> inner, outer;
+            for (int ch = 0; ch < nchunks; ch++) {
+                bool touches = false;
+                for (int r = ch * PAT_CHUNK; r < std::min(n, (ch + 1) * PAT_CHUNK) && !touches; r++) touches = c->row_boundary[r] != 0;
+                (touches ? outer : inner).push_back(ch);
+            }
+            c->pat_chunks_interior = (int)inner.size();
+            inner.insert(inner.end(), outer.begin(), outer.end());
+            CU(cudaMalloc(&c->d_pat_chunks, inner.size() * sizeof(int)));
+            CU(cudaMemcpy(c->d_pat_chunks, inner.data(), inner.size() * sizeof(int), cudaMemcpyHostToDevice));
+        }
+        return 0;
+    }
+    template <bool DOT>
+    static int spmv_pattern(cgb200_ctx *c, const T *x, T *y, const CgScalars<T> &sc) {
+        const int maxlen = std::max(1, c->max_row);
+        const size_t table_bytes = (size_t)c->npat * maxlen * (sizeof(T) + sizeof(int)) + (size_t)c->npat * sizeof(int);
+        const bool in_smem = table_bytes <= 32 * 1024;
+        const size_t smem = PAT_THREADS * sizeof(T) + (in_smem ? table_bytes : 0) + 16;
+        auto launch = [&](auto kern) -> int {
+            int grid = persistent_grid(c, kern, PAT_THREADS, smem, c->pat_chunks);
+            const int per = (c->pat_chunks + grid - 1) / grid;
+            grid = (c->pat_chunks + per - 1) / per;
+            c->spmv_grid_last = grid;
+            CU(launch_kernel(kern, dim3(grid), dim3(PAT_THREADS), smem, c->stream, DOT && (c->pdl & 1), c->n, c->pat_chunks,
+                             c->pat_chunks_interior, (const int *)c->d_pat_chunks, c->npat, maxlen,
+                             (const unsigned short *)c->d_pat, (const int *)c->d_plen, (const int *)c->d_poff,
+                             (const T *)c->d_pval, x, y, sc));
+            c->launches++;
+            return 0;
+        };
+        if (in_smem) return launch(spmv_pattern_kernel<T, DOT, true>);
+        return launch(spmv_pattern_kernel<T, DOT, false>);
+    }
     // ---- CSR-stream schedule -------------------------------------------------
     static int build_tiles(cgb200_ctx *c, const std::vector<int> &rp) {
         using C = StreamCfg<T>;
@@ -473,6 +550,7 @@ template <typename T> struct Engine {
     static int spmv(cgb200_ctx *c, int k, const T *x, T *y, const CgScalars<T> &sc) {
         if (k == 1) {
             int variant = c->d_tiles ? c->spmv_variant : 1;
+            if (variant == 0 && c->pat_ok && c->pattern) return spmv_pattern<DOT>(c, x, y, sc);
             if (variant == 0 && c->irregular && c->auto_irregular && !sc.peer) variant = 3;
             switch (variant) {
             case 1: return spmv1<DOT>(c, x, y, sc);
@@ -966,7 +1044,10 @@ static int upload_matrix(cgb200_ctx *c, const void *aValues, const int *aPointer
     CU(cudaMemcpyAsync(rp.data(), c->d_rowptr, ((size_t)n + 1) * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     const uint64_t rh = hash_bytes(rp.data(), rp.size() * sizeof(int), 7);
-    if (c->d_tiles && rh == c->rowptr_hash) return 0;       // same pattern: the tiles stand
+    if (c->d_tiles && rh == c->rowptr_hash) {               // same row offsets: the tiles stand,
+        TRY(DISPATCH(c, E::build_patterns(c)));             // the row patterns (values!) may not
+        return 0;
+    }
     if (rp[0] != 0 || rp[n] != (int)nnz)
         return fail(CGB200_ERR_ARG, "aPointers[0]=%d aPointers[n]=%d but nnz=%lld", rp[0], rp[n], nnz);
     int mx = 0;
@@ -991,6 +1072,7 @@ static int upload_matrix(cgb200_ctx *c, const void *aValues, const int *aPointer
     TRY(DISPATCH(c, E::build_tiles(c, rp)));
     c->rowptr_hash = rh;
     detect_grid(c, rp);
+    TRY(DISPATCH(c, E::build_patterns(c)));
     return 0;
 }
 
@@ -1100,6 +1182,8 @@ int cgb200_destroy(cgb200_handle c) {
     if (c->d_hist) cudaFree(c->d_hist);
     if (c->d_trace) cudaFree(c->d_trace);
     if (c->d_runs) cudaFree(c->d_runs);
+    for (void *b : {c->d_pat, c->d_pat_table, c->d_pat_build, c->d_plen, c->d_poff, c->d_pval, (void *)c->d_pat_chunks})
+        if (b) cudaFree(b);
     if (c->d_tiles) cudaFree(c->d_tiles);
     if (c->d_long) cudaFree(c->d_long);
     if (c->d_chunk_sum) cudaFree(c->d_chunk_sum);
@@ -1141,6 +1225,8 @@ static int *option_slot(cgb200_handle c, const char *key) {
     if (!strcmp(key, "pdl")) return &c->pdl;
     if (!strcmp(key, "auto_irregular")) return &c->auto_irregular;
     if (!strcmp(key, "l2_keep")) return &c->l2_keep;
+    if (!strcmp(key, "pattern")) return &c->pattern;
+    if (!strcmp(key, "patterns")) return &c->npat;        // read-only: distinct row patterns found (0: CSR kernels in use)
     if (!strcmp(key, "spmm_schedule")) return &c->spmm_schedule;
     if (!strcmp(key, "pdl_early")) return &c->pdl_early;
     if (!strcmp(key, "vec_carveout")) return &c->vec_carveout;
@@ -1156,6 +1242,7 @@ int cgb200_set_option(cgb200_handle c, const char *key, long long value) {
         value != 16 && value != 32)
         return fail(CGB200_ERR_ARG, "lanes_per_row must be 0 or a power of two <= 32");
     if (!strcmp(key, "graph_chunk") && value < 1) return fail(CGB200_ERR_ARG, "graph_chunk must be >= 1");
+    if (!strcmp(key, "patterns")) return fail(CGB200_ERR_ARG, "'patterns' is read-only");
     if (!strcmp(key, "trace")) {
         if (value < 0 || value > (1 << 20)) return fail(CGB200_ERR_ARG, "trace: 0 .. 2^20 iterations");
         DeviceGuard guard(c->device);

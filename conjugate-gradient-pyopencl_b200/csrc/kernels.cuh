@@ -46,10 +46,8 @@ enum : int { TK_SPMV = 0, TK_UPDATE = 1, TK_INIT = 2 };
 // buffered by sequence parity) nor the halo regions can be overwritten while still in use.
 // ---------------------------------------------------------------------------
 constexpr int PEER_MAX = 8;
-struct PeerSlot {              // 32 bytes
-    double re, im;
-    unsigned long long seq;
-    unsigned long long pad;
+struct PeerSlot {              // 32 bytes: four self-validating words, (sequence number << 32) | 32 bits of payload
+    unsigned long long w[4];   // re low, re high, im low, im high
 };
 struct PeerComm {
     int rank, world;
@@ -72,33 +70,61 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned 
 __device__ __forceinline__ void st_release_sys_u64(unsigned long long *p, unsigned long long v) {
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
 
 // Called by ALL threads of ONE block per GPU.  Returns the sum over the GPUs (same bits everywhere).
+//
+// Every 8-byte word a GPU stores into a peer carries the sequence number of the all-reduce in its upper
+// half and 32 bits of the value in its lower half (the scheme of NCCL's LL protocol): an aligned 8-byte
+// store is single-copy atomic, so a word whose tag matches IS the data -- no fence between "value" and
+// "flag", the cost is one NVLink one-way trip instead of a store, a system-scope release (a round trip)
+// and a second store.
 template <typename T> __device__ __forceinline__ T peer_allreduce(PeerComm *pc, T local) {
+    __shared__ double s_val[2][PEER_MAX];
     __shared__ double s_sum[2];
+    constexpr int NW = Sc<T>::cplx ? 4 : 2;
     const int t = threadIdx.x;
     const unsigned long long seq = pc->seq + 1;
+    const unsigned long long tag = (seq & 0xffffffffull) << 32;
     const int parity = (int)(seq & 1);
     if (t < pc->world) {
-        // value, then the sequence number with release semantics: whoever acquires the number sees the value
-        PeerSlot *dst = pc->slots[t] + (size_t)parity * pc->world + pc->rank;
         double v[2] = {0.0, 0.0};
         Sc<T>::to_double2(local, v);
-        dst->re = v[0];
-        dst->im = v[1];
-        st_release_sys_u64(&dst->seq, seq);
+        PeerSlot *dst = pc->slots[t] + (size_t)parity * pc->world + pc->rank;
+#pragma unroll
+        for (int i = 0; i < NW; i++) {
+            const unsigned long long bits = (unsigned long long)__double_as_longlong(v[i >> 1]);
+            st_relaxed_sys_u64(&dst->w[i], tag | ((i & 1) ? (bits >> 32) : (bits & 0xffffffffull)));
+        }
         const PeerSlot *src = pc->slots[pc->rank] + (size_t)parity * pc->world + t;
+        unsigned long long w[4] = {0, 0, 0, 0};
         unsigned long long spins = 0;
-        while (ld_acquire_sys_u64(&src->seq) != seq)
+        for (;;) {
+            bool ok = true;
+#pragma unroll
+            for (int i = 0; i < NW; i++) {
+                w[i] = ld_relaxed_sys_u64(&src->w[i]);
+                ok = ok && ((w[i] & 0xffffffff00000000ull) == tag);
+            }
+            if (ok) break;
             if (++spins > (1ull << 31)) __trap();
+        }
+        s_val[0][t] = __longlong_as_double((long long)(((w[1] & 0xffffffffull) << 32) | (w[0] & 0xffffffffull)));
+        s_val[1][t] = NW == 4 ? __longlong_as_double((long long)(((w[3] & 0xffffffffull) << 32) | (w[2] & 0xffffffffull))) : 0.0;
     }
     __syncthreads();
     if (t == 0) {
         double re = 0.0, im = 0.0;
-        for (int p = 0; p < pc->world; p++) {
-            const volatile PeerSlot *src = pc->slots[pc->rank] + (size_t)parity * pc->world + p;
-            re += src->re;
-            im += src->im;
+        for (int p = 0; p < pc->world; p++) {      // rank order: the same bits on every GPU
+            re += s_val[0][p];
+            im += s_val[1][p];
         }
         s_sum[0] = re;
         s_sum[1] = im;
@@ -387,11 +413,28 @@ __device__ __forceinline__ void grid_col_reduce(const T *partial, int group, int
 #pragma unroll
     for (int v = 0; v < V; v++) acc[v] = Sc<T>::zero();
     if (cp < kv) {
-        for (int b = t / group; b < (int)gridDim.x; b += blockDim.x / group) {
+        // 8 blocks' partials per round with every load issued before the first add (one L2 round trip per
+        // round instead of one per partial); the order of the adds is unchanged: b ascending
+        constexpr int UB = 8;
+        const int step = blockDim.x / group;
+        for (int b0 = t / group; b0 < (int)gridDim.x; b0 += UB * step) {
+            T part[UB][V];
 #pragma unroll
-            for (int v = 0; v < V; v++)
-                if (cp * V + v < k)
-                    acc[v] = Sc<T>::add(acc[v], ld_cg(partial + (size_t)b * k + cp * V + v));
+            for (int u = 0; u < UB; u++) {
+                const int b = b0 + u * step;
+#pragma unroll
+                for (int v = 0; v < V; v++)
+                    part[u][v] = (b < (int)gridDim.x && cp * V + v < k) ? ld_cg(partial + (size_t)b * k + cp * V + v)
+                                                                         : Sc<T>::zero();
+            }
+#pragma unroll
+            for (int u = 0; u < UB; u++) {
+                if (b0 + u * step < (int)gridDim.x) {
+#pragma unroll
+                    for (int v = 0; v < V; v++)
+                        if (cp * V + v < k) acc[v] = Sc<T>::add(acc[v], part[u][v]);
+                }
+            }
         }
     }
     __syncthreads();
@@ -681,7 +724,7 @@ template <typename T, int S> struct TmaCfg {
 //   2. row sums out of shared memory, where a round costs ~30 cycles instead of an L2 round trip: a
 //      group of lpr lanes per row, and rows much longer than the rest are summed by a whole warp.
 template <typename T, int S, bool DOT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 6)      // 6 blocks per SM (the shared-memory limit at S = 2): 6 tiles in flight
 spmv_tma_kernel(int ntiles, const SpmvTile *__restrict__ tiles, const T *__restrict__ vals,
                 const int *__restrict__ rowptr, const int *__restrict__ cols, const T *__restrict__ x,
                 T *__restrict__ y, T *__restrict__ chunk_sum, CgScalars<T> sc) {
@@ -1105,6 +1148,227 @@ __global__ void combine_long_rows_kernel(int nlong, const LongRow *__restrict__ 
     T s = Sc<T>::zero();
     for (int c = 0; c < lr.nslots; c++) s = Sc<T>::add(s, chunk_sum[lr.slot0 + c]);
     y[lr.row] = s;
+}
+
+// ---------------------------------------------------------------------------
+// Row-pattern dictionary ("pattern CSR"), k = 1.
+//
+// Matrices assembled on uniform grids with constant coefficients -- the Poisson / Laplace configs, the
+// Helmholtz FE operators the reference's drivers build with a constant wave number (local_rect, helm_fe),
+// i.e. the subdomain matrices as_prec really solves with -- consist of a handful of distinct ROWS when a
+// row is written as the list of (column - row, value) pairs: interior, faces, edges, corners.  At set-up
+// the rows are hashed on the device, the distinct patterns are collected into a small table, and every
+// row keeps only a 16-bit pattern number.  The SpMV then moves 2 bytes per ROW instead of 12..20 bytes
+// per NON-ZERO: what is left is one read of x and one write of y.  The arithmetic is the CSR kernel's:
+// the same products added in the same (CSR) order with the same FMAs.
+// The CSR arrays stay resident (k > 1, irregular rows and matrices with too many patterns use them).
+// ---------------------------------------------------------------------------
+constexpr int PAT_MAXLEN = 32;          // longest row a pattern may have
+constexpr int PAT_MAXCOUNT = 4096;      // most distinct patterns
+constexpr int PAT_TABLE_SLOTS = 1 << 15;
+constexpr unsigned long long PAT_EMPTY = 0ull;
+
+struct PatSlot {
+    unsigned long long hash;   // PAT_EMPTY: free
+    int row;                   // representative row
+    int id;                    // pattern number
+};
+struct PatBuild {
+    int count;                 // distinct patterns so far
+    int fail;                  // 1: too many patterns / a row too long / a hash collision -> stay with CSR
+};
+
+template <typename T> __device__ __forceinline__ bool pat_same_bits(const T &a, const T &b) {
+    unsigned long long x[2] = {0, 0}, y[2] = {0, 0};
+    memcpy(x, &a, sizeof(T));
+    memcpy(y, &b, sizeof(T));
+    return x[0] == y[0] && x[1] == y[1];
+}
+__device__ __forceinline__ unsigned long long pat_mix(unsigned long long h, unsigned long long v) {
+    h ^= v + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
+    h *= 0xD6E8FEB86659FD93ull;
+    return h ^ (h >> 32);
+}
+
+template <typename T>
+__device__ __forceinline__ unsigned long long pat_hash_row(int row, int lo, int hi, const T *vals, const int *cols) {
+    unsigned long long h = pat_mix(0x5bd1e995ull, (unsigned long long)(hi - lo));
+    for (int j = lo; j < hi; j++) {
+        h = pat_mix(h, (unsigned long long)(long long)(cols[j] - row));
+        unsigned long long bits[2] = {0, 0};
+        memcpy(bits, vals + j, sizeof(T));
+        h = pat_mix(h, bits[0]);
+        if (sizeof(T) > 8) h = pat_mix(h, bits[1]);
+    }
+    return h == PAT_EMPTY ? 1ull : h;
+}
+
+// pass 1: claim a table slot for every distinct hash
+template <typename T>
+__global__ void pat_insert_kernel(int n, const T *__restrict__ vals, const int *__restrict__ rowptr,
+                                  const int *__restrict__ cols, PatSlot *table, PatBuild *pb) {
+    for (int row = blockIdx.x * blockDim.x + threadIdx.x; row < n; row += gridDim.x * blockDim.x) {
+        const int lo = rowptr[row], hi = rowptr[row + 1];
+        if (hi - lo > PAT_MAXLEN) {
+            pb->fail = 1;
+            return;
+        }
+        if (*reinterpret_cast<volatile int *>(&pb->fail)) return;
+        const unsigned long long h = pat_hash_row<T>(row, lo, hi, vals, cols);
+        unsigned slot = (unsigned)(h >> 17) & (PAT_TABLE_SLOTS - 1);
+        for (int probe = 0; probe < PAT_TABLE_SLOTS; probe++) {
+            unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(&table[slot].hash);   // fast path: no atomic
+            if (cur == PAT_EMPTY) cur = atomicCAS(&table[slot].hash, PAT_EMPTY, h);
+            if (cur == PAT_EMPTY) {            // this thread created the pattern
+                const int id = atomicAdd(&pb->count, 1);
+                table[slot].row = row;
+                table[slot].id = id;
+                if (id >= PAT_MAXCOUNT) pb->fail = 1;
+                break;
+            }
+            if (cur == h) break;
+            slot = (slot + 1) & (PAT_TABLE_SLOTS - 1);
+            if (*reinterpret_cast<volatile int *>(&pb->fail)) break;
+        }
+    }
+}
+
+// pass 2: every row looks its pattern up, checks entry by entry that it really IS the representative's
+// pattern (a 64-bit hash collision must not merge two different rows), and keeps the number
+template <typename T>
+__global__ void pat_assign_kernel(int n, const T *__restrict__ vals, const int *__restrict__ rowptr,
+                                  const int *__restrict__ cols, const PatSlot *__restrict__ table, PatBuild *pb,
+                                  unsigned short *__restrict__ pat) {
+    if (pb->fail) return;
+    for (int row = blockIdx.x * blockDim.x + threadIdx.x; row < n; row += gridDim.x * blockDim.x) {
+        const unsigned long long h = pat_hash_row<T>(row, rowptr[row], rowptr[row + 1], vals, cols);
+        unsigned slot = (unsigned)(h >> 17) & (PAT_TABLE_SLOTS - 1);
+        while (table[slot].hash != h) slot = (slot + 1) & (PAT_TABLE_SLOTS - 1);
+        const int rep = table[slot].row;
+        const int lo = rowptr[row], hi = rowptr[row + 1], rlo = rowptr[rep];
+        bool same = (hi - lo) == (rowptr[rep + 1] - rlo);
+        for (int j = 0; same && j < hi - lo; j++) {
+            same = (cols[lo + j] - row) == (cols[rlo + j] - rep) && pat_same_bits<T>(vals[lo + j], vals[rlo + j]);
+        }
+        if (!same) pb->fail = 1;
+        pat[row] = (unsigned short)table[slot].id;
+    }
+}
+
+// pass 3: the pattern table itself, [count][PAT_MAXLEN] offsets and values (+ lengths), from the representatives
+template <typename T>
+__global__ void pat_table_kernel(const T *__restrict__ vals, const int *__restrict__ rowptr, const int *__restrict__ cols,
+                                 const PatSlot *__restrict__ table, const PatBuild *pb, int *__restrict__ p_len,
+                                 int *__restrict__ p_off, T *__restrict__ p_val) {
+    if (pb->fail) return;
+    for (int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < PAT_TABLE_SLOTS; slot += gridDim.x * blockDim.x) {
+        if (table[slot].hash == PAT_EMPTY) continue;
+        const int id = table[slot].id, rep = table[slot].row;
+        const int lo = rowptr[rep], len = rowptr[rep + 1] - lo;
+        p_len[id] = len;
+        for (int j = 0; j < PAT_MAXLEN; j++) {
+            p_off[id * PAT_MAXLEN + j] = j < len ? cols[lo + j] - rep : 0;
+            p_val[id * PAT_MAXLEN + j] = j < len ? vals[lo + j] : Sc<T>::zero();
+        }
+    }
+}
+
+// y = A x from the pattern dictionary, fused with the partial sums of x.y.
+// A block owns chunks of PAT_CHUNK consecutive rows (chunk c of the schedule `chunks`, or c itself when the
+// schedule is NULL): consecutive threads take consecutive rows, so each of a row's gathers x[row + offset] is
+// one coalesced 256-byte load per warp, and the +-NX neighbours of a chunk's rows are the chunk's own rows
+// a little earlier / later (L1 hits).  Row-block shards list the chunks that touch halo columns last
+// ([nchunks_interior, nchunks)) and wait for the peers' entries only there.
+constexpr int PAT_THREADS = 256;
+constexpr int PAT_CHUNK = 1024;
+
+template <typename T, bool DOT, bool SMEM_TABLE>
+__global__ void __launch_bounds__(PAT_THREADS)
+spmv_pattern_kernel(int n, int nchunks, int nchunks_interior, const int *__restrict__ chunks, int npat, int maxlen,
+                    const unsigned short *__restrict__ pat, const int *__restrict__ p_len, const int *__restrict__ p_off,
+                    const T *__restrict__ p_val, const T *__restrict__ x, T *__restrict__ y, CgScalars<T> sc) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    T *red = reinterpret_cast<T *>(smem_raw);                                  // [PAT_THREADS]
+    T *s_val = red + PAT_THREADS;                                              // [npat][maxlen]   (SMEM_TABLE)
+    int *s_off = reinterpret_cast<int *>(s_val + (SMEM_TABLE ? npat * maxlen : 0));
+    int *s_len = s_off + (SMEM_TABLE ? npat * maxlen : 0);
+    const int t = threadIdx.x;
+    if (SMEM_TABLE) {        // the table is part of the matrix: not the previous kernel's output
+        for (int i = t; i < npat * maxlen; i += PAT_THREADS) {
+            const int id = i / maxlen, j = i - id * maxlen;
+            s_val[i] = p_val[id * PAT_MAXLEN + j];
+            s_off[i] = p_off[id * PAT_MAXLEN + j];
+        }
+        for (int i = t; i < npat; i += PAT_THREADS) s_len[i] = p_len[i];
+        __syncthreads();
+    }
+    pdl_wait();
+    if (sc.pdl_early) pdl_trigger();
+    if (DOT) {
+        if (*sc.n_active == 0) return;
+    }
+    int trace_it = -1;
+    if (DOT && sc.trace) {
+        trace_it = *sc.it;
+        if (blockIdx.x == 0 && t == 0) trace_mark<T>(sc, trace_it, TR_SPMV_START);
+    }
+    const unsigned long long keep = l2_policy(sc.l2_keep != 0);
+    T dot[1] = {Sc<T>::zero()};
+    bool halo_ready = !(sc.peer && sc.peer->world > 1);
+    const int stride = SMEM_TABLE ? maxlen : PAT_MAXLEN;
+    const T *tv = SMEM_TABLE ? s_val : p_val;
+    const int *to = SMEM_TABLE ? s_off : p_off;
+    const int *tl = SMEM_TABLE ? s_len : p_len;
+
+    // contiguous share of the chunk list per block (neighbouring chunks share their +-NX neighbours in L1 / L2)
+    const int per = (nchunks + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int c_begin = (int)blockIdx.x * per, c_end = min(nchunks, c_begin + per);
+    for (int ci = c_begin; ci < c_end; ci++) {
+        if (!halo_ready && ci >= nchunks_interior) {
+            if (t == 0) {
+                peer_wait_halo(sc.peer);
+                trace_mark<T>(sc, trace_it, TR_HALO_READY);
+            }
+            __syncthreads();
+            halo_ready = true;
+        }
+        const int chunk = chunks ? chunks[ci] : ci;
+        const int row_end = min(n, (chunk + 1) * PAT_CHUNK);
+        for (int row = chunk * PAT_CHUNK + t; row < row_end; row += PAT_THREADS) {
+            const int id = pat[row];
+            const int len = tl[id];
+            const T *pv = tv + id * stride;
+            const int *po = to + id * stride;
+            const T xr = DOT ? __ldg(x + row) : Sc<T>::zero();
+            T sum = Sc<T>::zero();
+            constexpr int UB = 8;
+            for (int j0 = 0; j0 < len; j0 += UB) {      // every gather of a batch issued before the first FMA
+                T xv[UB];
+#pragma unroll
+                for (int u = 0; u < UB; u++) xv[u] = __ldg(x + row + ((j0 + u < len) ? po[j0 + u] : 0));
+#pragma unroll
+                for (int u = 0; u < UB; u++)
+                    if (j0 + u < len) sum = Sc<T>::fma(pv[j0 + u], xv[u], sum);
+            }
+            st_hint_bytes(y + row, sum, keep);
+            if (DOT) dot[0] = Sc<T>::fma(xr, sum, dot[0]);
+        }
+    }
+
+    if (DOT) {
+        block_col_reduce<T, 1>(dot, 1, red);
+        if (publish_and_arrive<T, 1>(red, 1, 1, sc.partial, sc.ticket + TK_SPMV)) {
+            if (t == 0) trace_mark<T>(sc, trace_it, TR_SPMV_ALL_DONE);
+            grid_col_reduce<T, 1>(sc.partial, 1, 1, 1, red);
+            T total = red[0];
+            if (sc.peer) total = peer_allreduce<T>(sc.peer, red[0]);
+            if (t == 0) {
+                sc.dq[0] = total;
+                sc.ticket[TK_SPMV] = 0;
+                trace_mark<T>(sc, trace_it, TR_SPMV_END);
+            }
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------

@@ -769,3 +769,73 @@ def test_spmm_row_schedule_on_grids(gpu, cpu_ref, dname, kind, k):
     with gpu.Matrix.from_scipy(B) as M:
         yb = M.spmv(X, k=k)
     assert rel(yb, np.concatenate([B @ X[c * n:(c + 1) * n] for c in range(k)])) < (2e-6 if dname == "c64" else 1e-13)
+
+
+# ---------------------------------------------------------------------------------------
+# row-pattern dictionary (spmv_pattern_kernel)
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dname", ["f32", "f64", "c64", "c128"])
+@pytest.mark.parametrize("kind", ["poisson", "helm", "lap3d"])
+def test_pattern_dictionary_spmv_and_cg(gpu, cpu_ref, dname, kind):
+    """Grid matrices with constant coefficients have a handful of distinct rows as (column - row, value) lists:
+    the SpMV then runs from a 16-bit pattern number per row.  Same products, same order as the CSR kernel."""
+    import cg_b200.problems as P
+    dt = DT[dname]
+    if kind == "lap3d":
+        A = P.laplace3d(19).astype(dt)
+        b = np.ones(A.shape[0], dtype=dt)
+    else:
+        A, b = system(kind, 70, dt)
+    if kind == "helm" and dname in ("f32", "f64"):
+        pytest.skip("the real twin of the Helmholtz system has a random diagonal: no repeated rows (covered below)")
+    n = A.shape[0]
+    rng = np.random.default_rng(5)
+    x = rand(rng, n, dt)
+    wide = np.complex128 if np.dtype(dt).kind == "c" else np.float64
+    exact = A.astype(wide) @ x.astype(wide)
+    with gpu.Matrix.from_scipy(A) as M:
+        M.set_option("solver", 1)
+        npat = M.get_option("patterns")
+        assert 1 <= npat <= 64, npat
+        y1 = M.spmv(x)
+        x1, i1 = M.solve(b, max_iterations=60)
+        M.set_option("pattern", 0)
+        y0 = M.spmv(x)
+        x0, i0 = M.solve(b, max_iterations=60)
+    tol = 2e-6 if dname in ("f32", "c64") else 1e-14
+    assert rel(y1, exact) < tol and rel(y0, exact) < tol
+    ref, w = oracle_pair(cpu_ref, dname, A.data, A.indptr, A.indices, b, iters=60)
+    check_parity(x1, ref, w, dname)
+    check_parity(x0, ref, w, dname)
+
+
+def test_pattern_dictionary_falls_back_and_follows_updates(gpu, cpu_ref):
+    """No repeated rows (random values) -> the CSR kernels; new VALUES with the same sparsity pattern
+    (cgb200_update) -> the dictionary is rebuilt; a row longer than a pattern may be -> CSR."""
+    import cg_b200.problems as P
+    A = P.poisson2d(72).astype(np.float64)
+    n = A.shape[0]
+    rng = np.random.default_rng(9)
+    x = rng.standard_normal(n)
+    R = A.copy()
+    R.data = R.data * (1.0 + 0.1 * rng.random(R.nnz))            # every row different
+    with gpu.Matrix.from_scipy(R) as M:
+        assert M.get_option("patterns") == 0
+        assert rel(M.spmv(x), R @ x) < 1e-14
+        M.update(A.data, A.indptr, A.indices)                    # constant coefficients again
+        assert 1 <= M.get_option("patterns") <= 16
+        assert rel(M.spmv(x), A @ x) < 1e-14
+        B = A.copy()
+        B.data = B.data * 3.0
+        M.update(B.data, B.indptr, B.indices)                    # same pattern COUNT, other values
+        assert rel(M.spmv(x), B @ x) < 1e-14
+        M.update(R.data, R.indptr, R.indices)
+        assert M.get_option("patterns") == 0
+        assert rel(M.spmv(x), R @ x) < 1e-14
+    L = sp.lil_matrix(A)
+    L[5, :40] = 0.25                                             # one row of 40+ entries
+    L = L.tocsr()
+    L.sort_indices()
+    with gpu.Matrix.from_scipy(L) as M:
+        assert M.get_option("patterns") == 0
+        assert rel(M.spmv(x), L @ x) < 1e-14

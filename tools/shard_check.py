@@ -47,6 +47,12 @@ for name, A, b, tolv in (("lap3d24", P.laplace3d(24), np.ones(24 ** 3), 1e-10),
         en = float(np.linalg.norm(x - xn) / np.linalg.norm(xn))
         log(name, "peer-memory vs NCCL collectives:", en)
         assert en < 1e-12, en
+    M.set_option("pattern", 0)                       # CSR kernels instead of the row-pattern dictionary
+    xc, _ = M.solve(b[rb:re].astype(A.dtype), max_iterations=60)
+    M.set_option("pattern", 1)
+    ec = float(np.linalg.norm(x - xc) / np.linalg.norm(xc))
+    log(name, "pattern dictionary vs CSR kernels:", ec)
+    assert ec < 1e-11, ec
     log(name, "plain solve done; graph solve")
     M.set_option("use_graph", 1)
     xg, _ = M.solve(b[rb:re].astype(A.dtype), max_iterations=60)
