@@ -159,7 +159,20 @@ static cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, 
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
-    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+    // CGB200_SYNC_DEBUG=1: wait after every launch and name the kernel (by its parameter list) a fault surfaces in
+    static const bool sync_debug = getenv("CGB200_SYNC_DEBUG") && atoi(getenv("CGB200_SYNC_DEBUG")) != 0;
+    if (sync_debug && e == cudaSuccess) {
+        cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+        cudaStreamIsCapturing(stream, &st);
+        if (st == cudaStreamCaptureStatusNone) {
+            e = cudaStreamSynchronize(stream);
+            if (e != cudaSuccess)
+                fprintf(stderr, "cgb200: fault in the kernel launched by %s (grid %u, block %u, smem %zu): %s\n", __PRETTY_FUNCTION__,
+                        grid.x, block.x, smem, cudaGetErrorString(e));
+        }
+    }
+    return e;
 }
 
 // persistent grid for `kernel` with `block` threads and `smem` bytes, capped by `work_blocks`
@@ -320,6 +333,10 @@ template <typename T> struct Engine {
         CU(cudaStreamSynchronize(c->stream));
         c->launches += 3;
         if (pb.fail || pb.count < 1 || pb.count > PAT_MAXCOUNT) return 0;
+        {   // the table is staged in shared memory by every block: at most 40 KB of it
+            const int stride = c->max_row <= 8 ? 8 : (c->max_row <= 16 ? 16 : 32);
+            if ((size_t)pb.count * stride * (sizeof(T) + sizeof(int)) + (size_t)pb.count * sizeof(int) > 40 * 1024) return 0;
+        }
         c->npat = pb.count;
         c->pat_ok = 1;
         // chunk schedule: row-block shards visit the chunks that touch halo columns last
@@ -343,24 +360,28 @@ template <typename T> struct Engine {
     }
     template <bool DOT>
     static int spmv_pattern(cgb200_ctx *c, const T *x, T *y, const CgScalars<T> &sc) {
-        const int maxlen = std::max(1, c->max_row);
-        const size_t table_bytes = (size_t)c->npat * maxlen * (sizeof(T) + sizeof(int)) + (size_t)c->npat * sizeof(int);
-        const bool in_smem = table_bytes <= 32 * 1024;
-        const size_t smem = PAT_THREADS * sizeof(T) + (in_smem ? table_bytes : 0) + 16;
+        const int stride = c->max_row <= 8 ? 8 : (c->max_row <= 16 ? 16 : 32);
+        const size_t smem = PAT_THREADS * sizeof(T) + (size_t)c->npat * stride * (sizeof(T) + sizeof(int)) +
+                            (size_t)c->npat * sizeof(int) + 16;
         auto launch = [&](auto kern) -> int {
             int grid = persistent_grid(c, kern, PAT_THREADS, smem, c->pat_chunks);
             const int per = (c->pat_chunks + grid - 1) / grid;
             grid = (c->pat_chunks + per - 1) / per;
             c->spmv_grid_last = grid;
             CU(launch_kernel(kern, dim3(grid), dim3(PAT_THREADS), smem, c->stream, DOT && (c->pdl & 1), c->n, c->pat_chunks,
-                             c->pat_chunks_interior, (const int *)c->d_pat_chunks, c->npat, maxlen,
-                             (const unsigned short *)c->d_pat, (const int *)c->d_plen, (const int *)c->d_poff,
-                             (const T *)c->d_pval, x, y, sc));
+                             c->pat_chunks_interior, (const int *)c->d_pat_chunks, c->npat, (const unsigned short *)c->d_pat,
+                             (const int *)c->d_plen, (const int *)c->d_poff, (const T *)c->d_pval, x, y, sc));
             c->launches++;
             return 0;
         };
-        if (in_smem) return launch(spmv_pattern_kernel<T, DOT, true>);
-        return launch(spmv_pattern_kernel<T, DOT, false>);
+        if (sc.peer) {
+            if (stride == 8) return launch(spmv_pattern_kernel<T, DOT, 8, true>);
+            if (stride == 16) return launch(spmv_pattern_kernel<T, DOT, 16, true>);
+            return launch(spmv_pattern_kernel<T, DOT, 32, true>);
+        }
+        if (stride == 8) return launch(spmv_pattern_kernel<T, DOT, 8, false>);
+        if (stride == 16) return launch(spmv_pattern_kernel<T, DOT, 16, false>);
+        return launch(spmv_pattern_kernel<T, DOT, 32, false>);
     }
     // ---- CSR-stream schedule -------------------------------------------------
     static int build_tiles(cgb200_ctx *c, const std::vector<int> &rp) {
@@ -1263,6 +1284,18 @@ int cgb200_get_option(cgb200_handle c, const char *key, long long *value) {
     int *slot = option_slot(c, key);
     if (!slot) return fail(CGB200_ERR_ARG, "unknown option '%s'", key);
     *value = *slot;
+    return CGB200_OK;
+}
+
+// Debug aid: the row-pattern dictionary as it sits in device memory (which: 0 pattern number per row [n] u16,
+// 1 lengths, 2 offsets, 3 values of the pattern table).
+CGB200_API int cgb200_debug_read_patterns(cgb200_handle c, int which, void *out, size_t bytes) {
+    if (!c || !out) return fail(CGB200_ERR_ARG, "NULL argument");
+    DeviceGuard guard(c->device);
+    const void *src = which == 0 ? c->d_pat : which == 1 ? c->d_plen : which == 2 ? c->d_poff : c->d_pval;
+    if (!src) return fail(CGB200_ERR_ARG, "no pattern dictionary");
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaMemcpy(out, src, bytes, cudaMemcpyDeviceToHost));
     return CGB200_OK;
 }
 

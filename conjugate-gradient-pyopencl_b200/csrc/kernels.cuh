@@ -1282,90 +1282,92 @@ __global__ void pat_table_kernel(const T *__restrict__ vals, const int *__restri
 constexpr int PAT_THREADS = 256;
 constexpr int PAT_CHUNK = 1024;
 
-template <typename T, bool DOT, bool SMEM_TABLE>
+// PEER: the row-block sharded flavour (halo wait, all-reduce of d.q through peer memory); the single-GPU
+// engine runs the PEER = false instantiation, which contains none of that code.
+// STRIDE: entries per pattern in the shared-memory copy of the table (8, 16 or 32 >= the longest row).
+template <typename T, bool DOT, int STRIDE, bool PEER>
 __global__ void __launch_bounds__(PAT_THREADS)
-spmv_pattern_kernel(int n, int nchunks, int nchunks_interior, const int *__restrict__ chunks, int npat, int maxlen,
+spmv_pattern_kernel(int n, int nchunks, int nchunks_interior, const int *__restrict__ chunks, int npat,
                     const unsigned short *__restrict__ pat, const int *__restrict__ p_len, const int *__restrict__ p_off,
                     const T *__restrict__ p_val, const T *__restrict__ x, T *__restrict__ y, CgScalars<T> sc) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     T *red = reinterpret_cast<T *>(smem_raw);                                  // [PAT_THREADS]
-    T *s_val = red + PAT_THREADS;                                              // [npat][maxlen]   (SMEM_TABLE)
-    int *s_off = reinterpret_cast<int *>(s_val + (SMEM_TABLE ? npat * maxlen : 0));
-    int *s_len = s_off + (SMEM_TABLE ? npat * maxlen : 0);
+    T *s_val = red + PAT_THREADS;                                              // [npat][STRIDE]
+    int *s_off = reinterpret_cast<int *>(s_val + npat * STRIDE);               // [npat][STRIDE]
+    int *s_len = s_off + npat * STRIDE;                                        // [npat]
     const int t = threadIdx.x;
-    if (SMEM_TABLE) {        // the table is part of the matrix: not the previous kernel's output
-        for (int i = t; i < npat * maxlen; i += PAT_THREADS) {
-            const int id = i / maxlen, j = i - id * maxlen;
-            s_val[i] = p_val[id * PAT_MAXLEN + j];
-            s_off[i] = p_off[id * PAT_MAXLEN + j];
-        }
-        for (int i = t; i < npat; i += PAT_THREADS) s_len[i] = p_len[i];
-        __syncthreads();
+    // the table is part of the matrix, not the previous kernel's output: staged before the grid dependency wait
+    for (int i = t; i < npat * STRIDE; i += PAT_THREADS) {
+        const int id = i / STRIDE, j = i % STRIDE;
+        s_val[i] = p_val[id * PAT_MAXLEN + j];
+        s_off[i] = p_off[id * PAT_MAXLEN + j];
     }
+    for (int i = t; i < npat; i += PAT_THREADS) s_len[i] = p_len[i];
+    __syncthreads();
     pdl_wait();
     if (sc.pdl_early) pdl_trigger();
     if (DOT) {
         if (*sc.n_active == 0) return;
     }
-    int trace_it = -1;
-    if (DOT && sc.trace) {
-        trace_it = *sc.it;
-        if (blockIdx.x == 0 && t == 0) trace_mark<T>(sc, trace_it, TR_SPMV_START);
-    }
+    // (the iteration number is re-read at every mark: *sc.it only changes in the x/r update)
+    if (DOT && sc.trace && blockIdx.x == 0 && t == 0) trace_mark<T>(sc, *sc.it, TR_SPMV_START);
     const unsigned long long keep = l2_policy(sc.l2_keep != 0);
     T dot[1] = {Sc<T>::zero()};
-    bool halo_ready = !(sc.peer && sc.peer->world > 1);
-    const int stride = SMEM_TABLE ? maxlen : PAT_MAXLEN;
-    const T *tv = SMEM_TABLE ? s_val : p_val;
-    const int *to = SMEM_TABLE ? s_off : p_off;
-    const int *tl = SMEM_TABLE ? s_len : p_len;
+    bool halo_ready = true;
+    if constexpr (PEER) halo_ready = !(sc.peer && sc.peer->world > 1);
 
     // contiguous share of the chunk list per block (neighbouring chunks share their +-NX neighbours in L1 / L2)
     const int per = (nchunks + (int)gridDim.x - 1) / (int)gridDim.x;
     const int c_begin = (int)blockIdx.x * per, c_end = min(nchunks, c_begin + per);
     for (int ci = c_begin; ci < c_end; ci++) {
-        if (!halo_ready && ci >= nchunks_interior) {
-            if (t == 0) {
-                peer_wait_halo(sc.peer);
-                trace_mark<T>(sc, trace_it, TR_HALO_READY);
+        if constexpr (PEER) {
+            if (!halo_ready && ci >= nchunks_interior) {
+                if (t == 0) {
+                    peer_wait_halo(sc.peer);
+                    if (DOT && sc.trace) trace_mark<T>(sc, *sc.it, TR_HALO_READY);
+                }
+                __syncthreads();
+                halo_ready = true;
             }
-            __syncthreads();
-            halo_ready = true;
         }
         const int chunk = chunks ? chunks[ci] : ci;
         const int row_end = min(n, (chunk + 1) * PAT_CHUNK);
         for (int row = chunk * PAT_CHUNK + t; row < row_end; row += PAT_THREADS) {
             const int id = pat[row];
-            const int len = tl[id];
-            const T *pv = tv + id * stride;
-            const int *po = to + id * stride;
-            const T xr = DOT ? __ldg(x + row) : Sc<T>::zero();
+            const int len = s_len[id];
+            const T *pv = s_val + id * STRIDE;
+            const int *po = s_off + id * STRIDE;
+            const T *xrow = x + row;
             T sum = Sc<T>::zero();
-            constexpr int UB = 8;
-            for (int j0 = 0; j0 < len; j0 += UB) {      // every gather of a batch issued before the first FMA
-                T xv[UB];
+            // padded entries have offset 0 and coefficient 0: a batch needs no bounds test
 #pragma unroll
-                for (int u = 0; u < UB; u++) xv[u] = __ldg(x + row + ((j0 + u < len) ? po[j0 + u] : 0));
+            for (int j0 = 0; j0 < STRIDE; j0 += 8) {
+                if (j0 < len) {
+                    T xv[8];
 #pragma unroll
-                for (int u = 0; u < UB; u++)
-                    if (j0 + u < len) sum = Sc<T>::fma(pv[j0 + u], xv[u], sum);
+                    for (int u = 0; u < 8; u++) xv[u] = __ldg(xrow + po[j0 + u]);
+#pragma unroll
+                    for (int u = 0; u < 8; u++) sum = Sc<T>::fma(pv[j0 + u], xv[u], sum);
+                }
             }
             st_hint_bytes(y + row, sum, keep);
-            if (DOT) dot[0] = Sc<T>::fma(xr, sum, dot[0]);
+            if (DOT) dot[0] = Sc<T>::fma(__ldg(xrow), sum, dot[0]);
         }
     }
 
     if (DOT) {
         block_col_reduce<T, 1>(dot, 1, red);
         if (publish_and_arrive<T, 1>(red, 1, 1, sc.partial, sc.ticket + TK_SPMV)) {
-            if (t == 0) trace_mark<T>(sc, trace_it, TR_SPMV_ALL_DONE);
+            if (t == 0 && sc.trace) trace_mark<T>(sc, *sc.it, TR_SPMV_ALL_DONE);
             grid_col_reduce<T, 1>(sc.partial, 1, 1, 1, red);
             T total = red[0];
-            if (sc.peer) total = peer_allreduce<T>(sc.peer, red[0]);
+            if constexpr (PEER) {
+                if (sc.peer) total = peer_allreduce<T>(sc.peer, red[0]);
+            }
             if (t == 0) {
                 sc.dq[0] = total;
                 sc.ticket[TK_SPMV] = 0;
-                trace_mark<T>(sc, trace_it, TR_SPMV_END);
+                if (sc.trace) trace_mark<T>(sc, *sc.it, TR_SPMV_END);
             }
         }
     }
