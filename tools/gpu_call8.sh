@@ -1,0 +1,23 @@
+#!/bin/bash
+set -u
+O=gpurun_out
+export PYTHONUNBUFFERED=1
+export CGB200_PROBLEM_CACHE=/tmp/cgb200_problems
+B="timeout 600 python bench.py --no-cpu-baseline --no-e2e --no-also --steps 3"
+run() { # name, args...
+    local name=$1; shift
+    $B "$@" > $O/$name.json 2> $O/$name.err || echo "$name FAILED rc=$?"
+    python - "$O/$name.json" "$name" <<'PY'
+import json, sys
+try:
+    l = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
+    print(sys.argv[2], round(l["value"], 1), "it/s", {k: (round(v["ms"] * 1e3, 1), round(v["frac"], 3)) for k, v in l["kernels"].items()},
+          "iter_us", round(l["iteration"]["ms"] * 1e3, 1), round(l["iteration"]["frac"], 3))
+except Exception as e:
+    print(sys.argv[2], "no line", e)
+PY
+}
+timeout 600 python -m pytest tests -m gpu -q -k "pattern or fused or golden or cg_fixed" > $O/pytest18.log 2>&1; tail -2 $O/pytest18.log
+run c4_rr --workload c4
+run slab_rr --workload c4slab8
+run c2_rr --workload c2
