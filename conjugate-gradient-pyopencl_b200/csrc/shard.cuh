@@ -325,6 +325,11 @@ int cgb200_shard_create(cgb200_shard *out, int rank, int world, const void *nccl
     int rc = cgb200_create(&sh->m, n_owned, nnz, aValues, aPointers, aColsLocal, dtype, device);
     if (rc < 0) return bail(rc);
     sh->m->extra_cols = n_halo;
+    // Programmatic dependent launch stays off in the sharded iteration: with it the graph-launched tolerance solve
+    // stopped one iteration later than the plain-launched one (measured on 2 and 4 GPUs), i.e. some kernel of the
+    // halo / all-reduce chain saw a value one step early.  The single-GPU gain (<= 4 % on small systems) is not
+    // worth an ordering that is not understood.
+    if (world > 1 && !getenv("CGB200_PDL")) sh->m->pdl = 0;
     if (row_boundary && world > 1) {
         // rebuild the SpMV schedule with the halo-touching tiles last
         sh->m->row_boundary.assign(row_boundary, row_boundary + n_owned);
