@@ -533,6 +533,14 @@ def main():
             kernels[name] = {"ms": kms, "algorithmic_bytes": nbytes, "gbs": nbytes / kms / 1e6,
                              "frac": nbytes / kms / 1e6 / peak}
         M.solve(b_dev, x=x_dev, k=k, max_iterations=2)          # restore a sane state
+        npat = M.get_option("patterns") if k == 1 else 0
+        if npat > 0:
+            # the SpMV ran from the row-pattern dictionary: "algorithmic_bytes" stays the CSR figure of SURVEY.md 8(d)
+            # (so frac can exceed 1); what the kernel really has to move is 2 bytes per row + x + y
+            moved = n * (2 + 2 * v_bytes)
+            kernels["spmv_dot"].update(format=f"row-pattern dictionary, {npat} distinct rows (DESIGN.md 4.3)",
+                                       moved_bytes=moved, moved_gbs=moved / kernels["spmv_dot"]["ms"] / 1e6,
+                                       moved_frac=moved / kernels["spmv_dot"]["ms"] / 1e6 / peak)
     it_ms = timing["iterations"] / ITERS_PER_STEP
 
     # ---- e2e through the exported cg / cgd symbol, pinned host buffers, matrix re-uploaded each step

@@ -37,6 +37,7 @@ SIGNATURES = {
     "cgb200_last_timing": (_i, [_vp, ctypes.POINTER(_d)]),
     "cgb200_info": (_i, [_vp, ctypes.POINTER(_ll)]),
     "cgb200_read_trace": (_i, [_vp, _vp, _i]),
+    "cgb200_debug_read_patterns": (_i, [_vp, _i, _vp, ctypes.c_size_t]),
     "cgb200_cg": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _i]),
     "cgb200_clear_cache": (_i, []),
     "cgb200_nccl_unique_id": (_i, [_vp]),

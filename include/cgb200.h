@@ -23,6 +23,8 @@
 #ifndef CGB200_H
 #define CGB200_H
 
+#include <stddef.h>
+
 #ifndef CGB200_API
 #define CGB200_API __attribute__((visibility("default")))
 #endif
@@ -137,6 +139,10 @@ CGB200_API int cgb200_time_kernel(cgb200_handle h, int which, int k, int reps, d
  * starts, 4 all its blocks done, 5 delta known, 6 direction update starts, 7 halo entries of the peers
  * have arrived (sharded).  0 = not recorded. */
 CGB200_API int cgb200_read_trace(cgb200_handle h, unsigned long long *out, int iterations);
+
+/* Debug aid: the row-pattern dictionary as it sits in device memory.  which: 0 the 16-bit pattern number of
+ * every row [n], 1 pattern lengths [patterns], 2 column offsets and 3 values [patterns][32]. */
+CGB200_API int cgb200_debug_read_patterns(cgb200_handle h, int which, void *out, size_t bytes);
 
 /* Facts about a handle, for benches and tests:
  * [0] n [1] nnz [2] dtype [3] lanes_per_row [4] persistent grid of the SpMV kernel
