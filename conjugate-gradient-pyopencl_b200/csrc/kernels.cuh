@@ -251,7 +251,13 @@ template <typename T> __global__ void update_bookkeep_kernel(int k, CgScalars<T>
 // over NVLink; the last block to finish for that destination raises the arrival flag there.
 template <typename T>
 __global__ void __launch_bounds__(256)
-halo_push_kernel(PeerComm *pc, const int *__restrict__ idx, const T *__restrict__ d) {
+halo_push_kernel(PeerComm *pc, const int *__restrict__ idx, const T *__restrict__ d, const int *n_active) {
+    // An exchange is identified by the all-reduce count (peer_wait_halo).  Once every column has converged the
+    // kernels of the loop return at once and no all-reduce happens any more: an exchange pushed then would carry
+    // the SAME number as the first exchange of the NEXT solve and let that solve's first SpMV run ahead of its
+    // halo (seen as a graph-launched tolerance solve stopping one iteration late).  So: nothing to push, nobody
+    // waits.  n_active == NULL: the exchange of the initialisation, always done.
+    if (n_active && *n_active == 0) return;
     const int p = blockIdx.y;
     const int lo = pc->send_off[p], hi = pc->send_off[p + 1];
     if (hi <= lo) return;

@@ -108,7 +108,7 @@ template <typename T> struct ShardEngine {
     static ncclDataType_t nccl_type() { return sizeof(typename Sc<T>::real) == 4 ? ncclFloat : ncclDouble; }
 
     // halo of v (v has n_owned + n_halo entries): pack what the peers need, one grouped send/recv
-    static int exchange(cgb200_shard_ctx *sh, T *v) {
+    static int exchange(cgb200_shard_ctx *sh, T *v, const int *n_active = nullptr) {
         cgb200_ctx *c = sh->m;
         if (sh->world == 1) return 0;
         if (sh->p2p) {
@@ -119,7 +119,7 @@ template <typename T> struct ShardEngine {
                 const int nb = std::max(1, std::min(32, (sh->max_send + 2047) / 2048));
                 CU(cudaEventRecord(sh->ev_fork, c->stream));
                 CU(cudaStreamWaitEvent(sh->side, sh->ev_fork, 0));
-                halo_push_kernel<T><<<dim3(nb, sh->world), 256, 0, sh->side>>>(sh->d_peer, sh->d_send_idx, v);
+                halo_push_kernel<T><<<dim3(nb, sh->world), 256, 0, sh->side>>>(sh->d_peer, sh->d_send_idx, v, n_active);
                 CU(cudaEventRecord(sh->ev_join, sh->side));
                 sh->push_pending = true;
                 c->launches++;
@@ -165,7 +165,7 @@ template <typename T> struct ShardEngine {
 
     static int iteration(cgb200_shard_ctx *sh, const typename E::VecGeom &g, const CgScalars<T> &sc) {
         cgb200_ctx *c = sh->m;
-        TRY(exchange(sh, (T *)c->d));
+        TRY(exchange(sh, (T *)c->d, sh->p2p ? sc.n_active : nullptr));
         TRY(E::template spmv<true>(c, 1, (const T *)c->d, (T *)c->q, sc));          // q = A d, local d.q -> sc.dq
         TRY(allreduce(sh, sc.dq, 1));
         if (g.V == 1) TRY(E::template launch_update_xr<1>(c, 1, g, sc));            // local r.r -> sc.rr
