@@ -611,6 +611,13 @@ def main():
             "solve_phases_ms": timing,
         }
         line["iteration"]["spmv_pct_of_nominal_8TBs"] = 100.0 * kernels["spmv_dot"]["gbs"] / 8000.0
+        if "format" in kernels["spmv_dot"]:
+            note = ("the SpMV runs from the row-pattern dictionary and moves fewer bytes than the CSR figure its "
+                    "'algorithmic_bytes' is (kernels.spmv_dot.moved_*): fractions above 1 are format compression, "
+                    "not bandwidth")
+            line["iteration"]["note"] = note
+            if dom == "spmv_dot":
+                line["roofline"]["note"] = note
         if world == 1 and not args.no_also and args.workload != "c2":
             line["also"] = {"c2_c128": also_single_gpu("c2", "c128", peak, tdt_of, stream)}
         print(json.dumps(line), flush=True)

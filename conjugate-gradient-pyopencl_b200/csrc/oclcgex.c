@@ -15,7 +15,8 @@
  * main.c allocates complex buffers whatever <is complex> says and is therefore only correct for 1; here
  * <is complex> = 0 on a real file runs the real path on real buffers.  Unlike main.c the relative residual
  * |b - A x| / |b| of every right-hand side is printed (computed here on the host, in double).
- * --double solves through cgd().
+ * --double solves through cgd().  `oclcgex <file> --dump-csr` prints the full-storage CSR matrix the file expands
+ * to (no device work): the Matrix Market reader can be checked without a GPU.
  */
 #include <complex.h>
 #include <ctype.h>
@@ -153,12 +154,25 @@ static int load_matrix_market(const char *path, csr_t *out) {
 }
 
 int main(int argc, char *argv[]) {
-    int use_double = 0, npos = 0;
+    int use_double = 0, npos = 0, dump = 0;
     char *pos[4];
     for (int i = 1; i < argc; i++) {
         if (!strcmp(argv[i], "--double")) use_double = 1;
+        else if (!strcmp(argv[i], "--dump-csr")) dump = 1;
         else if (npos < 4) pos[npos++] = argv[i];
         else npos++;
+    }
+    if (dump && npos == 1) {      /* the matrix as cg() would receive it, no device work: "n nnz" then "row col re im" */
+        csr_t m;
+        if (load_matrix_market(pos[0], &m)) {
+            printf("Could not read matrix\n");
+            return 1;
+        }
+        printf("%d %lld %d\n", m.n, m.nnz, m.is_complex);
+        for (int r = 0; r < m.n; r++)
+            for (int j = m.rowptr[r]; j < m.rowptr[r + 1]; j++)
+                printf("%d %d %.17g %.17g\n", r, m.colidx[j], creal(m.values[j]), cimag(m.values[j]));
+        return 0;
     }
     if (npos != 4) {      /* main.c:15-18 */
         fprintf(stderr, "Usage: ./CG <input matrix file> <number of RHS> <is complex> <number of iterations>\n");

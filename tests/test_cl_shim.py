@@ -95,3 +95,44 @@ def test_native_oclcgex_arguments_and_matrix_market_errors(tmp_path):
     scipy.io.mmwrite(str(tmp_path / "c.mtx"), A)
     r = subprocess.run([exe, str(tmp_path / "c.mtx"), "1", "0", "10"], capture_output=True, text=True)
     assert r.returncode == 1 and "matrix is complex" in r.stdout
+
+
+@pytest.mark.parametrize("field,symmetry", [("real", "general"), ("real", "symmetric"), ("complex", "symmetric"),
+                                            ("complex", "hermitian"), ("real", "skew-symmetric"), ("pattern", "symmetric"),
+                                            ("integer", "general")])
+def test_native_matrix_market_reader(tmp_path, field, symmetry):
+    """csrc/oclcgex.c reads the coordinate format itself (the reference uses BeBOP SMC, main.c:20-27): every
+    field / symmetry combination must expand to the same full-storage CSR matrix scipy's reader gives, with
+    sorted rows and summed duplicates -- what cg() then receives."""
+    import subprocess
+    import scipy.io, scipy.sparse as sp
+    exe = _native_oclcgex()
+    rng = np.random.default_rng(hash((field, symmetry)) % 2**32)
+    n = 9
+    L = sp.random(n, n, density=0.3, random_state=3, format="coo")
+    L = sp.tril(L, k=-1 if symmetry == "skew-symmetric" else 0).tocoo()
+    vals = rng.integers(1, 9, L.nnz).astype(float)
+    if field == "complex":
+        vals = vals + 1j * rng.integers(1, 9, L.nnz)
+        if symmetry == "hermitian":
+            vals = np.where(L.row == L.col, vals.real, vals)
+    path = tmp_path / "m.mtx"
+    with open(path, "w") as f:
+        f.write(f"%%MatrixMarket matrix coordinate {field} {symmetry}\n% a comment\n\n{n} {n} {L.nnz + (1 if symmetry == 'general' else 0)}\n")
+        for r, c, v in zip(L.row, L.col, vals):
+            f.write(f"{r + 1} {c + 1}" + ("" if field == "pattern" else (f" {v.real:g} {v.imag:g}" if field == "complex" else
+                                                                    (f" {int(v.real)}" if field == "integer" else f" {v.real:.17g}"))) + "\n")
+        if symmetry == "general":          # a duplicate entry: summed
+            f.write(f"{L.row[0] + 1} {L.col[0] + 1}" + (" 2" if field == "integer" else " 2.5") + "\n")
+    out = subprocess.run([exe, str(path), "--dump-csr"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    lines = out.stdout.split("\n")
+    hn, hnnz, hc = (int(v) for v in lines[0].split())
+    ent = np.array([[float(v) for v in l.split()] for l in lines[1:] if l.strip()]).reshape(-1, 4)
+    got = sp.csr_matrix((ent[:, 2] + 1j * ent[:, 3], (ent[:, 0].astype(int), ent[:, 1].astype(int))), shape=(n, n))
+    ref = sp.csr_matrix(scipy.io.mmread(str(path)))
+    ref.sum_duplicates()
+    assert hn == n and hnnz == ref.nnz == len(ent) and hc == (field == "complex")
+    assert abs(got - ref).max() == 0
+    rows, cols = ent[:, 0].astype(int), ent[:, 1].astype(int)
+    assert np.all(np.diff(rows) >= 0) and np.all((np.diff(cols) > 0) | (np.diff(rows) > 0))      # CSR order, no duplicates

@@ -1,6 +1,6 @@
 #!/bin/bash
 # One gpurun call of round 1 (session 2): tests, the effect of the new options, the ncu passes.
-# Usage (from the repo root on the GPU box): bash tools/gpu_call.sh
+# Usage (from the repo root on the GPU box): bash tools/experiments/r01_call1.sh
 set -u
 O=gpurun_out
 mkdir -p $O
