@@ -93,3 +93,42 @@ def test_product_does_not_touch_the_oracle():
                 assert "cpu_ref" not in src and "np_cg" not in src and "oracle/" not in src, f
     out = subprocess.check_output(["ldd", _lib.lib()._path], text=True)
     assert "cpu_ref" not in out
+
+
+def test_ctypes_signatures_match_the_header_prototypes():
+    """Every prototype of include/*.h against cg_b200._lib.SIGNATURES: the number of parameters and, per parameter,
+    pointer / 64-bit integer / int / double -- a ctypes table that drifted from the header corrupts the call silently."""
+    protos = {}
+    for h in ("clcg.h", "cgb200.h"):
+        src = open(os.path.join(ROOT, "include", h)).read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        src = "\n".join(l for l in src.splitlines() if not l.lstrip().startswith("#"))
+        for ret, name, params in re.findall(r"CGB200_API\s+([^;(]*?)\b(\w+)\s*\(([^;]*?)\)\s*;", src, flags=re.S):
+            params = " ".join(params.split())
+            protos[name] = (ret.strip(), [] if params in ("", "void") else [p.strip() for p in params.split(",")])
+
+    def kind(c_decl):
+        if "*" in c_decl or "[" in c_decl or re.search(r"\bcgb200_(handle|shard)\b", c_decl):
+            return "ptr"
+        if "long long" in c_decl or "size_t" in c_decl:
+            return "i64"
+        if "double" in c_decl:
+            return "f64"
+        return "i32"
+
+    def ckind(ct):
+        if ct in (ctypes.c_void_p, ctypes.c_char_p) or hasattr(ct, "contents") or isinstance(ct, type(ctypes.POINTER(ctypes.c_int))):
+            return "ptr"
+        if ct in (ctypes.c_longlong, ctypes.c_size_t, ctypes.c_ulonglong):
+            return "i64"
+        if ct is ctypes.c_double:
+            return "f64"
+        return "i32"
+
+    assert set(protos) == set(_lib.SIGNATURES)
+    for name, (ret, params) in protos.items():
+        res, args = _lib.SIGNATURES[name]
+        assert len(params) == len(args), (name, params, args)
+        for p, a in zip(params, args):
+            assert kind(p) == ckind(a), (name, p, a)
+        assert kind(ret + " ") == ckind(res), (name, ret, res)
