@@ -78,6 +78,7 @@ struct cgb200_ctx {
     void *d_pat = nullptr, *d_pat_table = nullptr, *d_pat_build = nullptr, *d_plen = nullptr, *d_poff = nullptr, *d_pval = nullptr;
     int *d_pat_chunks = nullptr;
     int npat = 0, pat_ok = 0, pattern = 1, pat_chunks = 0, pat_chunks_interior = 0;
+    int pattern_regs = 0;        // experiment: the last pattern kept in registers (spmv_pattern_regs_kernel), unmeasured
     int irregular = 0;           // row lengths vary wildly inside a tile (power-law graphs), see upload_matrix
     // CSR-stream schedule (k = 1): tiles of whole rows / chunks of long rows
     void *d_tiles = nullptr, *d_long = nullptr, *d_chunk_sum = nullptr;
@@ -374,6 +375,16 @@ template <typename T> struct Engine {
             c->launches++;
             return 0;
         };
+        if (c->pattern_regs && stride == 8 && !sc.peer && !c->d_pat_chunks) {      // experiment, see spmv_pattern_regs_kernel
+            auto kern = spmv_pattern_regs_kernel<T, DOT>;
+            const int grid = persistent_grid(c, kern, PAT_THREADS, smem, c->pat_chunks);
+            c->spmv_grid_last = grid;
+            CU(launch_kernel(kern, dim3(grid), dim3(PAT_THREADS), smem, c->stream, DOT && (c->pdl & 1), c->n, c->pat_chunks,
+                             c->npat, (const unsigned short *)c->d_pat, (const int *)c->d_plen, (const int *)c->d_poff,
+                             (const T *)c->d_pval, x, y, sc));
+            c->launches++;
+            return 0;
+        }
         if (sc.peer) {
             if (stride == 8) return launch(spmv_pattern_kernel<T, DOT, 8, true>);
             if (stride == 16) return launch(spmv_pattern_kernel<T, DOT, 16, true>);
@@ -1249,6 +1260,7 @@ static int *option_slot(cgb200_handle c, const char *key) {
     if (!strcmp(key, "auto_irregular")) return &c->auto_irregular;
     if (!strcmp(key, "l2_keep")) return &c->l2_keep;
     if (!strcmp(key, "pattern")) return &c->pattern;
+    if (!strcmp(key, "pattern_regs")) return &c->pattern_regs;
     if (!strcmp(key, "patterns")) return &c->npat;        // read-only: distinct row patterns found (0: CSR kernels in use)
     if (!strcmp(key, "spmm_schedule")) return &c->spmm_schedule;
     if (!strcmp(key, "pdl_early")) return &c->pdl_early;

@@ -1407,6 +1407,81 @@ spmv_pattern_kernel(int n, int nchunks, int nchunks_interior, const int *__restr
     }
 }
 
+// EXPERIMENT (option "pattern_regs", off: written after this round's GPU budget was spent, not yet run on hardware).
+// ncu on spmv_pattern_kernel (C4): L1TEX throughput 85 %, of which a third is the table look-up -- 17 shared-memory
+// reads per row (length, 8 offsets, 8 values) that return the same values for nearly every row of a warp -- and one
+// gather in nine is the padding entry.  Here a thread keeps the pattern it used last in registers and re-reads the
+// table only when the pattern number changes, and gathers exactly `len` entries.  Rows of <= 8 entries, one GPU.
+template <typename T, bool DOT>
+__global__ void __launch_bounds__(PAT_THREADS)
+spmv_pattern_regs_kernel(int n, int nchunks, int npat, const unsigned short *__restrict__ pat, const int *__restrict__ p_len,
+                         const int *__restrict__ p_off, const T *__restrict__ p_val, const T *__restrict__ x,
+                         T *__restrict__ y, CgScalars<T> sc) {
+    constexpr int STRIDE = 8;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    T *red = reinterpret_cast<T *>(smem_raw);                                  // [PAT_THREADS]
+    T *s_val = red + PAT_THREADS;                                              // [npat][STRIDE]
+    int *s_off = reinterpret_cast<int *>(s_val + npat * STRIDE);               // [npat][STRIDE]
+    int *s_len = s_off + npat * STRIDE;                                        // [npat]
+    const int t = threadIdx.x;
+    for (int i = t; i < npat * STRIDE; i += PAT_THREADS) {
+        const int id = i / STRIDE, j = i % STRIDE;
+        s_val[i] = p_val[id * PAT_MAXLEN + j];
+        s_off[i] = p_off[id * PAT_MAXLEN + j];
+    }
+    for (int i = t; i < npat; i += PAT_THREADS) s_len[i] = p_len[i];
+    __syncthreads();
+    pdl_wait();
+    if (sc.pdl_early) pdl_trigger();
+    if (DOT) {
+        if (*sc.n_active == 0) return;
+    }
+    const unsigned long long keep = l2_policy(sc.l2_keep != 0);
+    T dot[1] = {Sc<T>::zero()};
+    int cid = -1, clen = 0;
+    int coff[STRIDE];
+    T cval[STRIDE];
+#pragma unroll
+    for (int u = 0; u < STRIDE; u++) {
+        coff[u] = 0;
+        cval[u] = Sc<T>::zero();
+    }
+    for (int ci = (int)blockIdx.x; ci < nchunks; ci += (int)gridDim.x) {
+        const int row_end = min(n, (ci + 1) * PAT_CHUNK);
+        for (int row = ci * PAT_CHUNK + t; row < row_end; row += PAT_THREADS) {
+            const int id = pat[row];
+            if (id != cid) {             // rare: the interior pattern covers almost every row of a grid
+                cid = id;
+                clen = s_len[id];
+#pragma unroll
+                for (int u = 0; u < STRIDE; u++) {
+                    coff[u] = s_off[id * STRIDE + u];
+                    cval[u] = s_val[id * STRIDE + u];
+                }
+            }
+            const T *xrow = x + row;
+            T xv[STRIDE];
+#pragma unroll
+            for (int u = 0; u < STRIDE; u++) xv[u] = u < clen ? __ldg(xrow + coff[u]) : Sc<T>::zero();
+            T sum = Sc<T>::zero();
+#pragma unroll
+            for (int u = 0; u < STRIDE; u++) sum = Sc<T>::fma(cval[u], xv[u], sum);   // padding: coefficient 0, same result
+            st_hint_bytes(y + row, sum, keep);
+            if (DOT) dot[0] = Sc<T>::fma(__ldg(xrow), sum, dot[0]);
+        }
+    }
+    if (DOT) {
+        block_col_reduce<T, 1>(dot, 1, red);
+        if (publish_and_arrive<T, 1>(red, 1, 1, sc.partial, sc.ticket + TK_SPMV)) {
+            grid_col_reduce<T, 1>(sc.partial, 1, 1, 1, red);
+            if (t == 0) {
+                sc.dq[0] = red[0];
+                sc.ticket[TK_SPMV] = 0;
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------
 // SpMM, k right-hand sides in row-major [n][k]: G lanes per row, lane cp owns the
 // V-wide column pack cp (one 128-bit gather per non-zero per lane when

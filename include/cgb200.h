@@ -96,6 +96,9 @@ CGB200_API int cgb200_set_stream(cgb200_handle h, void *cuda_stream);
  *   "auto_irregular" 1 (default): spmv_variant 0 picks variant 3 for matrices whose row lengths vary wildly
  *   "l2_keep"        d, q and r tagged evict-last in L2 (matrix stream and x are evict-first): 0 off, 1 on,
  *                    -1 by size (on when the three vectors fit half the L2)
+ *   "pattern"        1 (default): k = 1 runs from the row-pattern dictionary when the matrix has <= 4096 distinct rows
+ *                    ("patterns", read-only, tells how many were found; 0 = CSR kernels in use)
+ *   "pattern_regs"   0 (default) | 1: EXPERIMENT, not yet run on hardware -- the last pattern kept in registers
  *   "spmm_schedule"  0 (default) | 1: k > 1 on a matrix with grid structure (few fixed column offsets) visits rows
  *                    patch by patch for L1 reuse of the gathered rows (spmm_sched_kernel)
  *   "trace"          n > 0: the loop kernels stamp %globaltimer into an 8-slot record per iteration for the
