@@ -14,6 +14,9 @@ Fixtures:
                       x after 10 / 50 / 200 iterations of helmFE_var.CG      (complex128)
   poisson32_f64.npz   Poisson(32), b=ones, x0=0, x after 10 / 40 / 120 its   (float64)
   helm16_varC.npz     helmFE_var(N=16, omega=7.3, C=U(0.5,1.5), rho=0.21) matrix only
+  helm32_pcg.npz      the same helm32 system through the reference's PCG (helmFE_var.py:546-586): no preconditioner
+                      and Jacobi (inverse diagonal as a sparse matrix, the `M.dot(r)` branch), tol 1e-4 / 1e-8:
+                      x and the iteration index it returned
   known_answers.json  iterations to sqrt(|delta_k|/|delta_0|) < tol for the two systems of
                       SURVEY.md 8(c), produced by oracle/np_cg.py (stop=True) after that
                       restatement was checked bit-identical to helmFE_var.CG here.
@@ -113,5 +116,26 @@ def main():
     print(json.dumps(ka, indent=1, sort_keys=True))
 
 
+def pcg_fixture():
+    """helm32_pcg.npz -- the reference's PCG, see the header."""
+    import warnings
+    import helmFE_var as H
+    import problems
+    A = problems.helmholtz_fe(32)
+    b = problems.rhs_a(32, 12.0)
+    dinv = 1.0 / A.diagonal()
+    Minv = scipy.sparse.csr_matrix(scipy.sparse.diags(dinv))
+    out = {}
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")          # PCG tests `type(M) is scipy.sparse.csr.csr_matrix`: a deprecated path
+        for name, M in (("none", None), ("jacobi", Minv)):
+            for tol in (1e-4, 1e-8):
+                x, i = H.PCG(A, b, M=M, tol=tol, maxit=500)
+                out[f"x_{name}_{tol:g}"] = x
+                out[f"i_{name}_{tol:g}"] = i
+    np.savez_compressed(os.path.join(OUT, "helm32_pcg.npz"), dinv=dinv, **out)
+
+
 if __name__ == "__main__":
     main()
+    pcg_fixture()

@@ -69,3 +69,37 @@ def cg_abs_tol(A, b, tol=1e-5, x=None, max_it=None):
             break
         rho_prev = rho                                       # :1368
     return x, it
+
+
+def pcg(A, b, M=None, x=None, tol=1e-6, maxit=1000):
+    """The reference's preconditioned CG (/root/reference/helmFE_var.py:546-586), restated for the day the engine
+    gets a preconditioner.  M: None (z = r, :557-558), a 1-D array of the INVERSE diagonal
+    -- what the reference applies as a sparse matrix with one entry per row, z = M.dot(r), :559-563 -- or a
+    callable (:566-567).  Unconjugated dots; stops when sqrt(|r.r|) < tol (:579-583).  Returns (x, i) like the
+    reference: i is the index of the last iteration performed."""
+    if M is not None and not callable(M):
+        import scipy.sparse as sp
+        M = sp.csr_matrix(sp.diags(np.asarray(M)))           # the same sparse product the reference performs
+    if x is None:
+        x = np.zeros(b.size, dtype=complex)                  # :553-554
+    r = b - A.dot(x)                                         # :556
+    p = None
+    rho_prev = None
+    i = 0
+    for i in range(maxit):                                   # :557
+        if M is None:
+            z = r
+        elif callable(M):
+            z = M(r)
+        else:
+            z = M.dot(r)                                     # :563 (nnz <= n: "z = M.dot(r)")
+        rho = np.dot(r, z)                                   # :568
+        p = z if i == 0 else z + (rho / rho_prev) * p        # :570-574
+        q = A.dot(p)                                         # :575
+        alpha = rho / np.dot(p, q)                           # :576
+        x = x + alpha * p                                    # :577
+        r = r - alpha * q                                    # :578
+        if np.sqrt(abs(np.dot(r, r))) < tol:                 # :579-583
+            break
+        rho_prev = rho                                       # :584
+    return x, i

@@ -189,3 +189,17 @@ def test_reference_driver_still_produces_the_committed_fixture(golden_dir, tmp_p
     new = np.load(os.path.join(str(tmp_path), "asprec_2_12.npz"))
     for key in ("data", "indices", "indptr", "z", "x_numpy_cg", "numpy_cg_iters", "cl_args_b_values", "gmres_iterations"):
         assert np.array_equal(old[key], new[key]), key
+
+
+@pytest.mark.parametrize("name", ["none", "jacobi"])
+@pytest.mark.parametrize("tol", [1e-4, 1e-8])
+def test_pcg_restatement_is_bit_identical_to_the_reference_pcg(golden_dir, name, tol):
+    """oracle/np_cg.pcg against what the reference's own PCG (helmFE_var.py:546-586) returned here for the helm32
+    system -- the oracle for the preconditioned solver of SURVEY.md 8(f) rank 2 (not built yet)."""
+    import cg_b200.problems as P
+    z = np.load(os.path.join(golden_dir, "helm32_pcg.npz"))
+    A, b = P.helmholtz_fe(32), P.rhs_a(32, 12.0)
+    x, i = np_cg.pcg(A, b, M=None if name == "none" else z["dinv"], tol=tol, maxit=500)
+    assert i == int(z[f"i_{name}_{tol:g}"])
+    assert np.array_equal(x, z[f"x_{name}_{tol:g}"])
+    assert int(z["i_jacobi_1e-08"]) < int(z["i_none_1e-08"])           # Jacobi helps a little on this operator
