@@ -93,6 +93,8 @@ CGB200_API int cgb200_set_stream(cgb200_handle h, void *cuda_stream);
  *                    (default 1): the SpMV's prologue -- barriers, first matrix tiles by TMA -- overlaps the tail
  *                    of the direction update
  *   "pdl_early"      1 (default): a kernel lets its dependents become resident as soon as it has started
+ *   "vec_carveout"   -1 (default: leave alone) | 0..100: preferred shared-memory carve-out of the vector kernels, the
+ *                    knob that showed why "pdl" = 2 hurts
  *   "auto_irregular" 1 (default): spmv_variant 0 picks variant 3 for matrices whose row lengths vary wildly
  *   "l2_keep"        d, q and r tagged evict-last in L2 (matrix stream and x are evict-first): 0 off, 1 on,
  *                    -1 by size (on when the three vectors fit half the L2)

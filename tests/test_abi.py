@@ -132,3 +132,12 @@ def test_ctypes_signatures_match_the_header_prototypes():
         for p, a in zip(params, args):
             assert kind(p) == ckind(a), (name, p, a)
         assert kind(ret + " ") == ckind(res), (name, ret, res)
+
+
+def test_every_option_key_is_documented_in_the_header():
+    """cgb200_set_option keys (the strcmp chain of option_slot) against the option list in include/cgb200.h."""
+    src = open(os.path.join(ROOT, "conjugate-gradient-pyopencl_b200", "csrc", "cgb200.cu")).read()
+    keys = set(re.findall(r'strcmp\(key, "(\w+)"\)', src))
+    header = open(os.path.join(ROOT, "include", "cgb200.h")).read()
+    assert len(keys) >= 15
+    assert not [k for k in keys if f'"{k}"' not in header]
