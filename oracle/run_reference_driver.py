@@ -195,7 +195,53 @@ def run(M_s, W_s, maxit):
     return record
 
 
+def run_multi_gpu_script(M_s=3, W_s=12, maxit=20, n_devices=2):
+    """The reference's multi-GPU driver (p_h-PY_C-CL-multi-GPU.py), unmodified, on `n_devices` pretend devices.
+
+    As shipped it only runs variant 2 (`cgs = [2]`, :3684); its RHS-split code -- distribute_workloads_on_devices
+    (:2123-2140), run at import, and distribute_computations_with_threads (:2142-2181), variant 6 -- is then driven
+    here with the very arrays as_prec built for variant 2: one thread per device calling this repo's
+    cl.conjugate_gradient_multi_gpu on its contiguous block of right-hand sides.  Columns are independent CGs, so
+    the stitched result must equal the single multi-RHS call bit for bit.  Returns a summary dict."""
+    record = {"cl_calls": [], "c_calls": 0, "numpy_cg_calls": [], "_open": {}}
+    install_stubs(record)
+    import cl as pcl
+    pcl.get_gpu_devices = lambda: [pcl.Device(i) for i in range(n_devices)]
+    script = os.path.join(REF, "p_h-PY_C-CL-multi-GPU.py")
+    argv, cwd = sys.argv, os.getcwd()
+    tmp = os.path.join("/tmp", f"refdrv_{os.getpid()}")
+    os.makedirs(tmp, exist_ok=True)
+    os.chdir(tmp)
+    sys.argv = [script, str(M_s), str(W_s), "2", str(maxit)]
+    try:
+        with redirect_stdout(io.StringIO()) as buf:
+            ns = runpy.run_path(script, run_name="__main__")
+    finally:
+        sys.argv = argv
+        os.chdir(cwd)
+    n_my = M_s * M_s
+    workloads = ns["workloads"]
+    ranges = sorted((w[0], w[1]) for w in workloads.values())
+    multi = [c for c in record["cl_calls"] if c["n_rhs"] == n_my]
+    assert multi, "variant 2 did not reach pcl.CG"
+    c2 = multi[0]
+    import cpu_ref
+    whole, _, _ = cpu_ref.cg(c2["a_values"], c2["a_pointers"], c2["a_cols"], c2["b_values"], x0=c2["x_in"], k=n_my,
+                             iters=c2["n_iterations"])
+    before = len(record["cl_calls"])
+    x = c2["x_in"].copy()
+    ns["distribute_computations_with_threads"](c2["size"], c2["nnz"], c2["a_values"], c2["b_values"], c2["a_pointers"],
+                                               c2["a_cols"], x, n_my, c2["n_iterations"], workloads)
+    split_calls = record["cl_calls"][before:]
+    return {"ranges": ranges, "n_my": n_my, "devices": sorted(d.ordinal for d in workloads),
+            "split_calls": sorted((c["n_rhs"]) for c in split_calls), "identical": bool(np.array_equal(x, whole)),
+            "gmres_iterations": [int(m) for m in re.findall(r"####it:\s*(\d+)", buf.getvalue())]}
+
+
 def main():
+    if "--multi-gpu" in sys.argv:
+        print(run_multi_gpu_script())
+        return
     out_dir = os.path.join(ROOT, "tests", "golden")
     if "--out" in sys.argv:
         i = sys.argv.index("--out")

@@ -203,3 +203,22 @@ def test_pcg_restatement_is_bit_identical_to_the_reference_pcg(golden_dir, name,
     assert i == int(z[f"i_{name}_{tol:g}"])
     assert np.array_equal(x, z[f"x_{name}_{tol:g}"])
     assert int(z["i_jacobi_1e-08"]) < int(z["i_none_1e-08"])           # Jacobi helps a little on this operator
+
+
+@pytest.mark.reference
+def test_reference_multi_gpu_script_splits_right_hand_sides_over_our_cl_module():
+    """Build container only: p_h-PY_C-CL-multi-GPU.py, unmodified, on two pretend devices.  Its own
+    distribute_workloads_on_devices / distribute_computations_with_threads (:2123-2181) drive this repo's
+    cl.conjugate_gradient_multi_gpu from one thread per device; the stitched result equals the single multi-RHS
+    call, and the ranges are what sharded.split_rhs computes."""
+    import ast
+    import subprocess
+    import sys
+    from cg_b200 import sharded
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.check_output([sys.executable, os.path.join(root, "oracle", "run_reference_driver.py"), "--multi-gpu"],
+                                  text=True, env=dict(os.environ, OMP_NUM_THREADS="2"))
+    res = ast.literal_eval(out.strip().splitlines()[-1])
+    assert res["identical"] is True
+    assert res["devices"] == [0, 1] and res["split_calls"] == [4, 5] and res["n_my"] == 9
+    assert [tuple(r) for r in res["ranges"]] == [tuple(r) for r in sharded.split_rhs(9, 2)]
