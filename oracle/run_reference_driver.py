@@ -152,8 +152,8 @@ def install_stubs(record):
         def __call__(self, *a):
             return self.fn(*a)
 
-    # only the driver's own literal (p_h-PY_C-CL.py:38) gets the stand-in
-    ctypes.CDLL = lambda name=None, *a, **k: FakeLib() if name == "./build/liboclcg.so" else real_cdll(name, *a, **k)
+    # only the drivers' own literals (p_h-PY_C-CL.py:38, p_helmholtz.py:29) get the stand-in
+    ctypes.CDLL = lambda name=None, *a, **k: FakeLib() if name in ("./build/liboclcg.so", "./liboclcg.so") else real_cdll(name, *a, **k)
 
 
 def profile_hook(record):
@@ -238,7 +238,36 @@ def run_multi_gpu_script(M_s=3, W_s=12, maxit=20, n_devices=2):
             "gmres_iterations": [int(m) for m in re.findall(r"####it:\s*(\d+)", buf.getvalue())]}
 
 
+def run_old_api_script(use_cg, M_s=2, W_s=12):
+    """p_helmholtz.py, the oldest of the three drivers, unmodified: `pcl.create_kernels(1)` at import (:31) and the
+    9-argument `pcl.CG(size, nnz, a, b, ptr, cols, x, n_rhs, maxit)` (:1839, :1873); its numpy CG is imported from
+    helmFE_var (:25).  Returns how often and with how many right-hand sides the hot path was called."""
+    record = {"cl_calls": [], "c_calls": 0, "numpy_cg_calls": [], "_open": {}}
+    install_stubs(record)
+    sys.path.insert(0, REF)                    # `from helmFE_var import CG`
+    script = os.path.join(REF, "p_helmholtz.py")
+    argv, cwd = sys.argv, os.getcwd()
+    tmp = os.path.join("/tmp", f"refdrv_{os.getpid()}")
+    os.makedirs(tmp, exist_ok=True)
+    os.chdir(tmp)
+    sys.argv = [script, str(M_s), str(W_s), str(use_cg)]
+    buf = io.StringIO()
+    try:
+        with redirect_stdout(buf):
+            runpy.run_path(script, run_name="__main__")
+    except SystemExit:
+        pass
+    finally:
+        sys.argv = argv
+        os.chdir(cwd)
+    return {"use_cg": use_cg, "cl_calls": len(record["cl_calls"]), "n_rhs": sorted({c["n_rhs"] for c in record["cl_calls"]}),
+            "c_calls": record["c_calls"], "gmres_iterations": [int(m) for m in re.findall(r"####it:\s*(\d+)", buf.getvalue())]}
+
+
 def main():
+    if "--old-api" in sys.argv:
+        print(run_old_api_script(int(sys.argv[sys.argv.index("--old-api") + 1])))
+        return
     if "--multi-gpu" in sys.argv:
         print(run_multi_gpu_script())
         return

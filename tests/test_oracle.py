@@ -222,3 +222,19 @@ def test_reference_multi_gpu_script_splits_right_hand_sides_over_our_cl_module()
     assert res["identical"] is True
     assert res["devices"] == [0, 1] and res["split_calls"] == [4, 5] and res["n_my"] == 9
     assert [tuple(r) for r in res["ranges"]] == [tuple(r) for r in sharded.split_rhs(9, 2)]
+
+
+@pytest.mark.reference
+@pytest.mark.parametrize("use_cg,n_rhs,calls", [(1, [1], 28), (2, [4], 7)])
+def test_oldest_reference_driver_runs_on_the_old_cl_api(use_cg, n_rhs, calls):
+    """Build container only: p_helmholtz.py, unmodified -- `pcl.create_kernels(1)` at import and the 9-argument
+    `pcl.CG(size, nnz, a, b, ptr, cols, x, n_rhs, maxit)` (:31, :1839, :1873) -- runs to the end of its GMRES
+    (7 iterations, as with exact subdomain solves) on this repo's cl.py."""
+    import ast
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.check_output([sys.executable, os.path.join(root, "oracle", "run_reference_driver.py"), "--old-api",
+                                   str(use_cg)], text=True, env=dict(os.environ, OMP_NUM_THREADS="2"))
+    res = ast.literal_eval(out.strip().splitlines()[-1])
+    assert res["n_rhs"] == n_rhs and res["cl_calls"] == calls and res["gmres_iterations"] == [7]
