@@ -20,6 +20,11 @@ RHS) and 5 (its own numpy CG) one after the other (p_h-PY_C-CL.py:3622).  A prof
   every call that reaches `pcl.CG(...)` (the arguments of the hot path exactly as as_prec builds them,
       p_h-PY_C-CL.py:1924-1937 and :1956-1969).
 
+Two more modes run the other two drivers the same way (no fixtures, they print a summary that tests check):
+    --multi-gpu        p_h-PY_C-CL-multi-GPU.py on two pretend devices; its own thread-per-device RHS split is then
+                       driven with the recorded arrays (run_multi_gpu_script)
+    --old-api <UseCG>  p_helmholtz.py: `pcl.create_kernels(1)`, 9-argument `pcl.CG`, `CDLL("./liboclcg.so")`
+
 tests/golden/asprec_<M_s>_<W_s>.npz then holds, for the first preconditioner application:
   data/indices/indptr   the subdomain matrix P[0] (complex128, from the driver's local_rect)
   z                     [n_my][size] the right-hand sides z[p] (complex128)
