@@ -17,6 +17,9 @@
  *   complex arithmetic                 kernel/complex/cmplx.h:4-25
  *   host orchestration, host partial sums, alpha/beta   clcg.c:253-419
  *
+ * Pinned: bit-identical (float, float complex; 1..4 right-hand sides) to the reference's own kernel sources
+ * executed by oracle/clref -- tests/test_oracle.py, tests/golden/clref_*.npz.
+ *
  * Deliberate differences (documented in DESIGN.md):
  *   - the out-of-bounds row-pointer read of spmv.cl:18-19 is not reproduced;
  *   - size < 256 (the reference prints "NOT SUPPORTED", clcg.c:123) is handled

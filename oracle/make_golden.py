@@ -17,6 +17,10 @@ Fixtures:
   helm32_pcg.npz      the same helm32 system through the reference's PCG (helmFE_var.py:546-586): no preconditioner
                       and Jacobi (inverse diagonal as a sparse matrix, the `M.dot(r)` branch), tol 1e-4 / 1e-8:
                       x and the iteration index it returned
+  clref_poisson32_f32.npz, clref_helm32_c64.npz
+                      the reference's OWN OpenCL kernels (oracle/clref: kernel/*/*.cl executed on the CPU inside
+                      clcg.c's launch sequence) on the two systems above in single precision: B (k right-hand
+                      sides) and x after 10 / 40 iterations for k = 1, after 25 iterations for k = 3
   known_answers.json  iterations to sqrt(|delta_k|/|delta_0|) < tol for the two systems of
                       SURVEY.md 8(c), produced by oracle/np_cg.py (stop=True) after that
                       restatement was checked bit-identical to helmFE_var.CG here.
@@ -136,6 +140,26 @@ def pcg_fixture():
     np.savez_compressed(os.path.join(OUT, "helm32_pcg.npz"), dinv=dinv, **out)
 
 
+def clref_fixtures():
+    """clref_*.npz -- results of the reference's own kernels, see the header."""
+    import clref
+    import problems
+    for name, A, b0, dt in (("poisson32_f32", problems.poisson2d(32), np.ones(1024), np.float32),
+                            ("helm32_c64", problems.helmholtz_fe(32), problems.rhs_a(32, 12.0), np.complex64)):
+        A = canon(A)
+        n = A.shape[0]
+        vals = A.data.astype(dt)
+        rng = np.random.default_rng(2024)
+        extra = [rng.standard_normal(n) + (1j * rng.standard_normal(n) if dt == np.complex64 else 0) for _ in range(2)]
+        B3 = np.concatenate([b0] + extra).astype(dt)
+        out = {"B3": B3}
+        for its in (10, 40):
+            out[f"x_k1_it{its}"] = clref.cg(vals, A.indptr, A.indices, B3[:n], k=1, iters=its)
+        out["x_k3_it25"] = clref.cg(vals, A.indptr, A.indices, B3, k=3, iters=25)
+        np.savez_compressed(os.path.join(OUT, f"clref_{name}.npz"), **out)
+
+
 if __name__ == "__main__":
     main()
     pcg_fixture()
+    clref_fixtures()

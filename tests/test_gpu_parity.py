@@ -839,3 +839,26 @@ def test_pattern_dictionary_falls_back_and_follows_updates(gpu, cpu_ref):
     with gpu.Matrix.from_scipy(L) as M:
         assert M.get_option("patterns") == 0
         assert rel(M.spmv(x), L @ x) < 1e-14
+
+
+@pytest.mark.parametrize("kind,dname", [("poisson32_f32", "f32"), ("helm32_c64", "c64")])
+def test_cg_against_results_of_the_reference_kernels(gpu, cpu_ref, golden_dir, kind, dname):
+    """tests/golden/clref_*.npz: x computed by the reference's OWN OpenCL kernels (executed on the CPU by oracle/clref
+    in the build container) for 1 and 3 right-hand sides.  The exported `cg` symbol against them, single precision:
+    1e-5 on the SPD system; on the indefinite Helmholtz operator no further from the double-precision recurrence than
+    10x the reference arithmetic's own distance (check_parity)."""
+    import cg_b200.problems as P
+    z = np.load(os.path.join(golden_dir, f"clref_{kind}.npz"))
+    A = (P.poisson2d(32) if kind == "poisson32_f32" else P.helmholtz_fe(32))
+    A.sort_indices()
+    dt = DT[dname]
+    n = A.shape[0]
+    vals = A.data.astype(dt)
+    wide_t = WIDE[dname]
+    for k, its, key in ((1, 10, "x_k1_it10"), (1, 40, "x_k1_it40"), (3, 25, "x_k3_it25")):
+        B = np.ascontiguousarray(z["B3"][:n * k])
+        x = np.zeros(n * k, dtype=dt)
+        gpu.cg(n, A.nnz, vals, B, A.indptr, A.indices, x, k, its)
+        wide, _, _ = cpu_ref.cg(vals.astype(wide_t), A.indptr, A.indices, B.astype(wide_t), k=k, iters=its)
+        check_parity(x, z[key], wide, dname)
+    gpu._lib.lib().cgb200_clear_cache()

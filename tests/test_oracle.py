@@ -238,3 +238,53 @@ def test_oldest_reference_driver_runs_on_the_old_cl_api(use_cg, n_rhs, calls):
                                    str(use_cg)], text=True, env=dict(os.environ, OMP_NUM_THREADS="2"))
     res = ast.literal_eval(out.strip().splitlines()[-1])
     assert res["n_rhs"] == n_rhs and res["cl_calls"] == calls and res["gmres_iterations"] == [7]
+
+
+# ---------------------------------------------------------------------------------------
+# the reference's own OpenCL kernels (oracle/clref: kernel/*/*.cl from /root/reference, executed on the CPU)
+# ---------------------------------------------------------------------------------------
+def _clref_system(kind):
+    import cg_b200.problems as P
+    if kind == "poisson32_f32":
+        return P.poisson2d(32), np.float32
+    return P.helmholtz_fe(32), np.complex64
+
+
+@pytest.mark.reference
+@pytest.mark.parametrize("kind", ["poisson32_f32", "helm32_c64"])
+@pytest.mark.parametrize("k", [1, 2, 3, 4])
+def test_c_oracle_is_bit_identical_to_the_reference_kernels(cpu_ref, kind, k):
+    """Build container only.  oracle/cpu_ref.c RESTATES the reference's kernels; oracle/clref EXECUTES them (the .cl
+    sources #included from /root/reference, work-items as fibers, barriers honoured, clcg.c's launch sequence and
+    host sums around them).  Same bits after 0, 1 and 12 iterations for 1..4 right-hand sides, real and complex --
+    the summation trees, the host partial sums and the complex arithmetic of the restatement are the reference's."""
+    import clref
+    A, dt = _clref_system(kind)
+    A.sort_indices()
+    n = A.shape[0]
+    rng = np.random.default_rng(100 + k)
+    B = np.concatenate([rng.standard_normal(n) + (1j * rng.standard_normal(n) if dt == np.complex64 else 0)
+                        for _ in range(k)]).astype(dt)
+    X0 = (0.1 * np.concatenate([rng.standard_normal(n) + (1j * rng.standard_normal(n) if dt == np.complex64 else 0)
+                                for _ in range(k)])).astype(dt)
+    vals = A.data.astype(dt)
+    for its, x0 in ((0, X0), (1, None), (12, X0)):
+        ref = clref.cg(vals, A.indptr, A.indices, B, x0=x0, k=k, iters=its)
+        mine, _, _ = cpu_ref.cg(vals, A.indptr, A.indices, B, x0=x0, k=k, iters=its)
+        assert np.array_equal(ref.view(np.uint8), mine.view(np.uint8)), (kind, k, its)
+
+
+@pytest.mark.parametrize("kind", ["poisson32_f32", "helm32_c64"])
+def test_c_oracle_reproduces_the_reference_kernel_fixtures(cpu_ref, golden_dir, kind):
+    """Runs everywhere (the GPU box included): tests/golden/clref_*.npz are results of the reference's own kernels
+    (oracle/make_golden.py::clref_fixtures); the C oracle must give the same bits."""
+    z = np.load(os.path.join(golden_dir, f"clref_{kind}.npz"))
+    A, dt = _clref_system(kind)
+    A.sort_indices()
+    n = A.shape[0]
+    vals = A.data.astype(dt)
+    for its in (10, 40):
+        x, _, _ = cpu_ref.cg(vals, A.indptr, A.indices, z["B3"][:n], k=1, iters=its)
+        assert np.array_equal(x.view(np.uint8), z[f"x_k1_it{its}"].view(np.uint8)), its
+    x, _, _ = cpu_ref.cg(vals, A.indptr, A.indices, z["B3"], k=3, iters=25)
+    assert np.array_equal(x.view(np.uint8), z["x_k3_it25"].view(np.uint8))
