@@ -39,7 +39,7 @@ def lib():
 
 
 def cg(vals, rowptr, cols, b, x0=None, k=1, iters=10):
-    """cg() of clcg.h:3-5 with the reference's kernels: float32 or complex64, n >= 256 and n % 8 == 0, k <= 4."""
+    """cg() of clcg.h:3-5 with the reference's kernels: float32 or complex64, n >= 256, k <= 4."""
     vals = np.ascontiguousarray(vals)
     dt = vals.dtype
     assert dt in (np.float32, np.complex64), "the reference has single precision only (main.c:49)"
@@ -51,5 +51,5 @@ def cg(vals, rowptr, cols, b, x0=None, k=1, iters=10):
     rc = lib().clref_cg(n, vals.size, vals.ctypes.data, b.ctypes.data, rowptr.ctypes.data, cols.ctypes.data,
                         x.ctypes.data, k, iters, int(dt.kind == "c"))
     if rc != 0:
-        raise ValueError(f"clref_cg: {rc} (-1: k not in 1..4, -2: n < 256 or n % 8 != 0)")
+        raise ValueError(f"clref_cg: {rc} (-1: k not in 1..4, -2: n < 256)")
     return x

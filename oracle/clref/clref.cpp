@@ -230,7 +230,7 @@ static int run_cg(int size, const void *aValues_, const void *b_, const int *aPo
                   int nIterations) {
     typedef typename K::val V;
     typedef typename Host<V>::T H;
-    if (size < WG_SIZE || size % (WG_SIZE / WAVE_SIZE) != 0) return -2;   // what the reference supports without reading out of bounds
+    if (size < WG_SIZE) return -2;       // "size less than 256 NOT SUPPORTED" (clcg.c:123): one odd-sized work-group there
     const V *aValues = (const V *)aValues_, *b = (const V *)b_;
     V *x = (V *)x_;
     const int workGroups = 1 + (size - 1) / WG_SIZE;                       // clcg.c:124
@@ -282,8 +282,8 @@ static int run_cg(int size, const void *aValues_, const void *b_, const int *aPo
 }
 
 extern "C" {
-// size must be >= 256 and a multiple of 8 (the cases the reference handles without its out-of-bounds read);
-// nRHS 1..4.  Same argument meaning as cg() (clcg.h:3-5).  Returns 0, -1 (nRHS not instantiated), -2 (size).
+// size must be >= 256 (clcg.c:123); when it is not a multiple of 8 the out-of-bounds row-offset read of
+// spmv.cl:18-19 lands in the padding added above (empty rows, never stored).  nRHS 1..4.  Same argument meaning as cg() (clcg.h:3-5).  Returns 0, -1 (nRHS not instantiated), -2 (size).
 int clref_cg(int size, int nonZeros, const float *aValues, const float *b, const int *aPointers, const int *aCols,
              float *x, int nRHS, int nIterations, int isComplex) {
     (void)nonZeros;

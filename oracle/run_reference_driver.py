@@ -31,6 +31,7 @@ tests/golden/asprec_<M_s>_<W_s>.npz then holds, for the first preconditioner app
   x_numpy_cg            [n_my][size] what the driver's numpy CG returned for them (tol 1e-5 on |r|)
   numpy_cg_iters        iterations that took (re-derived by the oracle restatement, checked to agree)
   cl_args_*             the arrays as_prec passed to pcl.CG in variant 2 (csingle / intc), n_rhs, n_iterations
+  cl_result_reference_kernels   x of that very call computed by the reference's own OpenCL kernels (oracle/clref)
   gmres_iterations      outer iterations per variant, as printed by the driver
 """
 import ctypes
@@ -299,6 +300,17 @@ def main():
         assert np.array_equal(x, c["x"]), "oracle/np_cg.py differs from the driver's CG"
         iters.append(it)
     c2 = multi[0]
+    # the same call -- the very arrays as_prec built -- through the reference's OWN OpenCL kernels (oracle/clref);
+    # the columns are independent CGs, so they go through in groups of <= 4 (the instantiated N_RHS values)
+    import clref
+    size = c2["size"]
+    x_kernels = np.zeros_like(c2["x_in"])
+    for c0 in range(0, n_my, 4):
+        kk = min(4, n_my - c0)
+        x_kernels[c0 * size:(c0 + kk) * size] = clref.cg(c2["a_values"], c2["a_pointers"], c2["a_cols"],
+                                                         c2["b_values"][c0 * size:(c0 + kk) * size],
+                                                         x0=c2["x_in"][c0 * size:(c0 + kk) * size], k=kk,
+                                                         iters=c2["n_iterations"])
     gm = [int(m) for m in re.findall(r"####it:\s*(\d+)", out)]          # one per variant 0, 1, 2, 5 (p_h-PY_C-CL.py:3622)
     dst = os.path.join(out_dir, f"asprec_{M_s}_{W_s}.npz")
     np.savez_compressed(
@@ -308,6 +320,7 @@ def main():
         cl_args_a_values=c2["a_values"], cl_args_b_values=c2["b_values"], cl_args_a_pointers=c2["a_pointers"],
         cl_args_a_cols=c2["a_cols"], cl_args_x_in=c2["x_in"], cl_args_n_rhs=c2["n_rhs"],
         cl_args_n_iterations=c2["n_iterations"], cl_args_size=c2["size"], cl_args_nnz=c2["nnz"],
+        cl_result_reference_kernels=x_kernels,
         cl_calls_total=len(rec["cl_calls"]), numpy_cg_calls_total=len(rec["numpy_cg_calls"]),
         gmres_iterations=np.array(gm))
     print("wrote", dst, "n =", A.shape[0], "nnz =", A.nnz, "n_my =", n_my, "numpy CG iterations", iters,

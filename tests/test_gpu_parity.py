@@ -704,6 +704,9 @@ def test_as_prec_multi_rhs_call_through_the_cl_module(gpu, cpu_ref, golden_dir, 
     ref, wide = oracle_pair(cpu_ref, "c64", z["cl_args_a_values"], z["cl_args_a_pointers"], z["cl_args_a_cols"],
                             z["cl_args_b_values"], k=k, iters=its)
     check_parity(x, ref, wide, "c64")
+    # the same call as computed by the reference's own OpenCL kernels (oracle/clref, stored in the fixture)
+    assert np.array_equal(ref.view(np.uint8), z["cl_result_reference_kernels"].view(np.uint8))
+    check_parity(x, z["cl_result_reference_kernels"], wide, "c64")
     # and the single-RHS variants (UseCG == 1 / 4): one call per subdomain gives the same columns
     for p in range(k):
         xp = np.zeros(size, np.csingle)

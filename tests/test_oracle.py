@@ -172,6 +172,12 @@ def test_as_prec_builds_the_block_the_abi_expects(golden_dir, name):
     assert np.array_equal(z["cl_args_a_values"], A.data.astype(np.csingle))
     assert np.array_equal(z["cl_args_b_values"].reshape(k, size), z["z"].astype(np.csingle))
     assert not z["cl_args_x_in"].any()
+    # ... and what the reference's own kernels return for exactly these arrays is what the C oracle returns
+    import cpu_ref as _cpu_ref
+    _cpu_ref.build()
+    mine, _, _ = _cpu_ref.cg(z["cl_args_a_values"], z["cl_args_a_pointers"], z["cl_args_a_cols"], z["cl_args_b_values"],
+                             x0=z["cl_args_x_in"], k=k, iters=int(z["cl_args_n_iterations"]))
+    assert np.array_equal(mine.view(np.uint8), z["cl_result_reference_kernels"].view(np.uint8))
     g = z["gmres_iterations"]                   # variants 0 (exact), 1, 2 (CGMaxIT fixed, single), 5 (numpy CG to 1e-5)
     assert len(g) == 4 and g[0] == g[3] and g[1] == g[2] >= g[0]
 
@@ -187,7 +193,8 @@ def test_reference_driver_still_produces_the_committed_fixture(golden_dir, tmp_p
     subprocess.check_call([sys.executable, os.path.join(root, "oracle", "run_reference_driver.py"), "2", "12", "40",
                            "--out", str(tmp_path)], env=env, stdout=subprocess.DEVNULL)
     new = np.load(os.path.join(str(tmp_path), "asprec_2_12.npz"))
-    for key in ("data", "indices", "indptr", "z", "x_numpy_cg", "numpy_cg_iters", "cl_args_b_values", "gmres_iterations"):
+    for key in ("data", "indices", "indptr", "z", "x_numpy_cg", "numpy_cg_iters", "cl_args_b_values", "gmres_iterations",
+                "cl_result_reference_kernels"):
         assert np.array_equal(old[key], new[key]), key
 
 
