@@ -295,3 +295,68 @@ def test_c_oracle_reproduces_the_reference_kernel_fixtures(cpu_ref, golden_dir, 
         assert np.array_equal(x.view(np.uint8), z[f"x_k1_it{its}"].view(np.uint8)), its
     x, _, _ = cpu_ref.cg(vals, A.indptr, A.indices, z["B3"], k=3, iters=25)
     assert np.array_equal(x.view(np.uint8), z["x_k3_it25"].view(np.uint8))
+
+
+# ---------------------------------------------------------------------------------------
+# randomised cross-checks of the oracles (hypothesis)
+# ---------------------------------------------------------------------------------------
+def _random_spd(n, density, seed, cplx):
+    """Diagonally dominant symmetric (complex-symmetric when cplx) CSR matrix with unsorted duplicates removed."""
+    import scipy.sparse as sp
+    rng = np.random.default_rng(seed)
+    L = sp.random(n, n, density=density, random_state=int(seed), format="csr")
+    L.data = rng.uniform(-1.0, 1.0, L.nnz) + (1j * rng.uniform(-1.0, 1.0, L.nnz) if cplx else 0)
+    S = L + L.T
+    d = np.asarray(abs(S).sum(axis=1)).ravel() + 1.0
+    A = (S + sp.diags(d + (0.2j if cplx else 0))).tocsr()
+    A.sum_duplicates()
+    A.sort_indices()
+    return A
+
+
+def test_randomised_double_oracles_agree():
+    """cpu_ref.c in double (device summation order) against np_cg (numpy order) on random diagonally dominant
+    systems, real and complex-symmetric, several right-hand sides: two orders of the same recurrence, 1e-10."""
+    from hypothesis import given, settings, strategies as st
+    import cpu_ref as cr
+    cr.build()
+
+    @settings(max_examples=12, deadline=None)
+    @given(n=st.integers(256, 700), k=st.integers(1, 4), seed=st.integers(0, 2**31 - 1), cplx=st.booleans(),
+           its=st.integers(1, 25))
+    def run(n, k, seed, cplx, its):
+        A = _random_spd(n, 6.0 / n, seed, cplx)
+        rng = np.random.default_rng(seed + 1)
+        dt = np.complex128 if cplx else np.float64
+        B = np.concatenate([rng.standard_normal(n) + (1j * rng.standard_normal(n) if cplx else 0) for _ in range(k)]).astype(dt)
+        x, _, _ = cr.cg(A.data.astype(dt), A.indptr, A.indices, B, k=k, iters=its)
+        for c in range(k):
+            ref = np_cg.cg(A.astype(dt), B[c * n:(c + 1) * n].astype(complex), maxit=its)
+            assert np.linalg.norm(x[c * n:(c + 1) * n] - ref) <= 1e-10 * np.linalg.norm(ref)
+
+    run()
+
+
+@pytest.mark.reference
+def test_randomised_single_oracle_is_bit_identical_to_the_reference_kernels():
+    """Build container only: random systems (row lengths 1..40, n not a multiple of 8 or 256, 1..4 right-hand
+    sides, real and complex) through the reference's own kernels (oracle/clref) and through oracle/cpu_ref.c."""
+    from hypothesis import given, settings, strategies as st
+    import clref
+    import cpu_ref as cr
+    cr.build()
+
+    @settings(max_examples=10, deadline=None)
+    @given(n=st.integers(256, 520), k=st.integers(1, 4), seed=st.integers(0, 2**31 - 1), cplx=st.booleans(),
+           its=st.integers(0, 6), dens=st.floats(2.0, 40.0))
+    def run(n, k, seed, cplx, its, dens):
+        A = _random_spd(n, dens / n, seed, cplx)
+        rng = np.random.default_rng(seed + 1)
+        dt = np.complex64 if cplx else np.float32
+        B = np.concatenate([rng.standard_normal(n) + (1j * rng.standard_normal(n) if cplx else 0) for _ in range(k)]).astype(dt)
+        vals = A.data.astype(dt)
+        ref = clref.cg(vals, A.indptr, A.indices, B, k=k, iters=its)
+        mine, _, _ = cr.cg(vals, A.indptr, A.indices, B, k=k, iters=its)
+        assert np.array_equal(ref.view(np.uint8), mine.view(np.uint8))
+
+    run()
