@@ -88,6 +88,17 @@ int cpu_ref_spmv(int dtype, int n, const void *aValues, const int *aPointers,
 }
 
 /* The reference's own entry point shape (clcg.h:3-5), served by the oracle. */
+int cpu_ref_pcg(int dtype, int n, const void *aValues, const void *b, const int *aPointers, const int *aCols,
+                void *x, const void *dinv, int k, int nIterations, double *rr_hist) {
+    switch (dtype) {
+    case 0: return cpu_ref_pcg_f32(n, aValues, b, aPointers, aCols, x, dinv, k, nIterations, rr_hist);
+    case 1: return cpu_ref_pcg_f64(n, aValues, b, aPointers, aCols, x, dinv, k, nIterations, rr_hist);
+    case 2: return cpu_ref_pcg_c64(n, aValues, b, aPointers, aCols, x, dinv, k, nIterations, rr_hist);
+    case 3: return cpu_ref_pcg_c128(n, aValues, b, aPointers, aCols, x, dinv, k, nIterations, rr_hist);
+    }
+    return -2;
+}
+
 float *cpu_ref_cg_legacy(int size, int nonZeros, const float *aValues, const float *b,
                          const int *aPointers, const int *aCols, float *x,
                          int nRHS, int nIterations, int isComplex) {

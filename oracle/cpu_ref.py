@@ -69,6 +69,30 @@ def cg(vals, rowptr, cols, b, x0=None, k=1, iters=100, tol=0.0, want_hist=False)
     return x, its, hist
 
 
+def pcg(vals, rowptr, cols, b, dinv, x0=None, k=1, iters=100, want_hist=False):
+    """Jacobi-preconditioned CG in the device's arrangement (cpu_ref_impl.h::cpu_ref_pcg): exactly `iters` iterations.
+    dinv: the n inverse diagonal entries.  Returns (x, r.r history or None)."""
+    vals = np.ascontiguousarray(vals)
+    dt = vals.dtype
+    n = rowptr.size - 1
+    b = np.ascontiguousarray(b, dtype=dt)
+    dinv = np.ascontiguousarray(dinv, dtype=dt)
+    x = np.zeros(n * k, dtype=dt) if x0 is None else np.array(x0, dtype=dt, copy=True, order="C")
+    rowptr = np.ascontiguousarray(rowptr, dtype=np.intc)
+    cols = np.ascontiguousarray(cols, dtype=np.intc)
+    ncomp = 2 if dt.kind == "c" else 1
+    hist = np.zeros((iters + 1, k, ncomp)) if want_hist else None
+    L = lib()
+    L.cpu_ref_pcg.argtypes = [ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 6 + [ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+    L.cpu_ref_pcg.restype = ctypes.c_int
+    rc = L.cpu_ref_pcg(_CODES[dt], n, _p(vals), _p(b), _p(rowptr), _p(cols), _p(x), _p(dinv), k, iters, _p(hist))
+    if rc:
+        raise RuntimeError(f"cpu_ref_pcg failed: {rc}")
+    if hist is not None:
+        hist = hist[..., 0] + 1j * hist[..., 1] if ncomp == 2 else hist[..., 0]
+    return x, hist
+
+
 def spmv(vals, rowptr, cols, x, k=1):
     vals = np.ascontiguousarray(vals)
     dt = vals.dtype

@@ -263,6 +263,67 @@ int FN(cpu_ref_cg)(int n, int nnz, const void *aValues, const void *bValues,
     return 0;
 }
 
+/*
+ * Jacobi-preconditioned CG -- the oracle for SURVEY.md 8(f) rank 2 (not yet on the device).  The recurrence of the
+ * reference's PCG (helmFE_var.py:546-586: z = M r, rho = r.z, p = z + (rho/rho_prev) p, alpha = rho / p.q) arranged
+ * as the device will run it, with the kernels and summation orders above:
+ *     q = A x0 ; r = b - q ; z = dinv o r ; d = z ; rho = r.z
+ *     loop:  q = A d ; alpha = rho / d.q ; x += alpha d ; r -= alpha q ; z = dinv o r ; rho' = r.z ;
+ *            d = z + (rho'/rho) d
+ * dinv: n values (the inverse diagonal), shared by the k right-hand sides.  Exactly nIterations iterations;
+ * rr_hist (optional, (nIterations+1)*k*NCOMP doubles): r.r after the initialisation and after every iteration,
+ * the quantity the reference's PCG stops on (sqrt|r.r| < tol, :579-583).
+ */
+int FN(cpu_ref_pcg)(int n, const void *aValues, const void *bValues, const int *aPointers, const int *aCols,
+                    void *xInOut, const void *dinv_, int k, int nIterations, double *rr_hist) {
+    const VAL *av = (const VAL *)aValues, *b = (const VAL *)bValues, *dinv = (const VAL *)dinv_;
+    VAL *x = (VAL *)xInOut;
+    const size_t len = (size_t)n * k;
+    const int wgs = 1 + (n - 1) / CPU_REF_WG;
+    VAL *r = malloc(len * sizeof(VAL)), *d = malloc(len * sizeof(VAL)), *q = malloc(len * sizeof(VAL));
+    VAL *z = malloc(len * sizeof(VAL)), *part = malloc((size_t)wgs * k * sizeof(VAL));
+    VAL *rho = malloc(k * sizeof(VAL)), *rhoNew = malloc(k * sizeof(VAL)), *dq = malloc(k * sizeof(VAL));
+    VAL *alpha = malloc(k * sizeof(VAL)), *beta = malloc(k * sizeof(VAL)), *rr = malloc(k * sizeof(VAL));
+    if (!r || !d || !q || !z || !part || !rho || !rhoNew || !dq || !alpha || !beta || !rr) return -1;
+#define PCG_APPLY_M()                                                            \
+    for (int c = 0; c < k; c++)                                                  \
+        for (int i = 0; i < n; i++) z[(size_t)c * n + i] = VMUL(dinv[i], r[(size_t)c * n + i]);
+#define PCG_RR(slot)                                                             \
+    if (rr_hist) {                                                               \
+        for (int c = 0; c < k; c++) rr[c] = VZERO();                             \
+        FN(vdot)(n, r, r, k, part, rr);                                          \
+        for (int c = 0; c < k; c++) FN(store_hist)(rr_hist + ((size_t)(slot) * k + c) * NCOMP, rr[c]); \
+    }
+    FN(spmv)(n, av, aPointers, aCols, x, q, k);
+    FN(vsubv)(len, b, q, r);
+    PCG_APPLY_M();
+    memcpy(d, z, len * sizeof(VAL));
+    for (int c = 0; c < k; c++) rho[c] = VZERO();
+    FN(vdot)(n, r, z, k, part, rho);
+    PCG_RR(0);
+    for (int it = 0; it < nIterations; it++) {
+        FN(spmv)(n, av, aPointers, aCols, d, q, k);
+        for (int c = 0; c < k; c++) dq[c] = VZERO();
+        FN(vdot)(n, d, q, k, part, dq);
+        for (int c = 0; c < k; c++) alpha[c] = VDIV(rho[c], dq[c]);
+        FN(axpy)(n, d, x, alpha, 1, k);
+        FN(axpy)(n, q, r, alpha, 0, k);
+        PCG_APPLY_M();
+        for (int c = 0; c < k; c++) rhoNew[c] = VZERO();
+        FN(vdot)(n, r, z, k, part, rhoNew);
+        for (int c = 0; c < k; c++) {
+            beta[c] = VDIV(rhoNew[c], rho[c]);
+            rho[c] = rhoNew[c];
+        }
+        PCG_RR(it + 1);
+        FN(aypx)(n, z, d, beta, k);          /* d = beta d + z */
+    }
+#undef PCG_APPLY_M
+#undef PCG_RR
+    free(r); free(d); free(q); free(z); free(part); free(rho); free(rhoNew); free(dq); free(alpha); free(beta); free(rr);
+    return 0;
+}
+
 /* y = A x with the reference's summation order; exported for kernel-level parity tests. */
 int FN(cpu_ref_spmv)(int n, const void *aValues, const int *aPointers, const int *aCols,
                      const void *x, void *y, int k) {

@@ -360,3 +360,23 @@ def test_randomised_single_oracle_is_bit_identical_to_the_reference_kernels():
         assert np.array_equal(ref.view(np.uint8), mine.view(np.uint8))
 
     run()
+
+
+def test_c_pcg_oracle_against_the_reference_pcg_fixture(cpu_ref, golden_dir):
+    """oracle/cpu_ref.c::cpu_ref_pcg (Jacobi, device summation order) after exactly the iterations the reference's
+    PCG needed (helm32_pcg.npz: results of helmFE_var.PCG itself): same x to 1e-9 (two summation orders of an
+    indefinite problem), and its r.r history crosses the reference's tolerance at the reference's iteration."""
+    import cg_b200.problems as P
+    z = np.load(os.path.join(golden_dir, "helm32_pcg.npz"))
+    A, b = P.helmholtz_fe(32), P.rhs_a(32, 12.0)
+    for tol in (1e-4, 1e-8):
+        i_ref = int(z[f"i_jacobi_{tol:g}"])
+        x, hist = cpu_ref.pcg(A.data, A.indptr, A.indices, b, z["dinv"], iters=i_ref + 1, want_hist=True)
+        ref = z[f"x_jacobi_{tol:g}"]
+        assert np.linalg.norm(x - ref) <= 1e-9 * np.linalg.norm(ref)
+        res = np.sqrt(np.abs(hist[:, 0]))
+        assert res[i_ref + 1] < tol <= res[i_ref]
+    # without a preconditioner (dinv = 1) it is the plain CG oracle, bit for bit
+    x1, _ = cpu_ref.pcg(A.data, A.indptr, A.indices, b, np.ones(A.shape[0]), iters=30)
+    x0, _, _ = cpu_ref.cg(A.data, A.indptr, A.indices, b, iters=30)
+    assert np.array_equal(x1, x0)
