@@ -34,10 +34,11 @@ enum : int { TK_SPMV = 0, TK_UPDATE = 1, TK_INIT = 2 };
 // themselves through NVLink-mapped pointers (CUDA IPC), instead of separate NCCL launches.
 //
 //   all-reduce of a dot product   the last block of spmv_dot / update_xr stores its GPU's
-//       partial sum (+ a sequence number) straight into a slot in EVERY peer's memory, then
-//       waits until all peers' slots of the same sequence number have arrived in its own
-//       memory and adds them up in rank order -- every GPU gets the bit-identical sum, in
-//       about one NVLink round trip, inside the kernel that produced the partial.
+//       partial sum straight into a slot in EVERY peer's memory -- 8-byte words that carry the
+//       sequence number next to 32 bits of payload, so no fence separates "value" from "flag" --,
+//       then waits until all peers' words of the same sequence number have arrived in its own
+//       memory and adds them up in rank order: every GPU gets the bit-identical sum, in about
+//       one NVLink one-way trip, inside the kernel that produced the partial.
 //   halo of d                     halo_push_kernel writes the entries a peer needs directly
 //       into that peer's d vector and then raises a flag there; the peer's SpMV waits for
 //       the flags after it has already started streaming its matrix tiles.
@@ -52,7 +53,7 @@ struct PeerSlot {              // 32 bytes: four self-validating words, (sequenc
 struct PeerComm {
     int rank, world;
     unsigned long long seq;                     // all-reduces completed on this GPU
-    unsigned long long halo_seq;                // halo exchanges started on this GPU
+    unsigned long long halo_seq;                // (unused since an exchange is numbered by the all-reduce count)
     PeerSlot *slots[PEER_MAX];                  // slots[p]: rank p's [2][world] slot array (peer mapped; [rank] is local)
     unsigned long long *halo_flag[PEER_MAX];    // halo_flag[p]: rank p's [world] arrival flags
     void *d_peer[PEER_MAX];                     // rank p's direction vector [owned | halo]
