@@ -206,6 +206,26 @@ def cpu_sample(A, B, k, target_s, max_iters):
     return iters, dt, cpu_ref.threads()
 
 
+def numpy_sample(A, B, k, target_s):
+    """oracle/np_cg.cg (the restatement of helmFE_var.CG, numpy/scipy, one thread) on the first right-hand side,
+    for about target_s seconds: iterations/s of ONE column, scaled to k columns solved one after the other."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import np_cg
+    from threadpoolctl import threadpool_limits
+    n = A.shape[0]
+    b = np.ascontiguousarray(B[:n]).astype(complex if np.iscomplexobj(B) else float)
+    with threadpool_limits(limits=1):                           # "single thread" includes the BLAS behind np.dot
+        t0 = time.perf_counter()
+        np_cg.cg(A, b, x=np.zeros(n, dtype=b.dtype), maxit=1)
+        per_it = max(time.perf_counter() - t0, 1e-6) / 2.0      # initial residual + one iteration
+        iters = int(max(2, min(ITERS_PER_STEP, target_s / per_it)))
+        t0 = time.perf_counter()
+        np_cg.cg(A, b, x=np.zeros(n, dtype=b.dtype), maxit=iters)
+        dt = time.perf_counter() - t0
+    return {"value": iters / dt, "unit": "iterations/s", "cores": 1,
+            "sample": f"{iters} iterations of oracle/np_cg.cg (numpy/scipy) on one right-hand side, {dt:.1f} s"}
+
+
 def run_reference(args, wl, dtype, k, rank, world):
     """--impl reference: the reference's CPU implementation of the path = the oracle port (the OpenCL
     original cannot run in this image: no ICD); rank 0 only."""
@@ -592,6 +612,10 @@ def main():
             cpu = {"value": iters * k / dt, "unit": "iterations/s", "cores": threads, "kind": "port",
                    "sample": f"{iters} CG iterations of the same system on the host "
                              f"(oracle/cpu_ref.c, OpenMP, {threads} threads of {os.cpu_count()} cpus), {dt:.1f} s"}
+            try:        # second point of BASELINE.md section 3: the reference's numpy CG recurrence, one thread
+                cpu["numpy_single_thread"] = numpy_sample(A, B, k, 6.0)
+            except Exception as e:      # never let a reporting extra break the line
+                cpu["numpy_single_thread"] = {"error": str(e)[:100]}
         dom = max(kernels, key=lambda nm: kernels[nm]["ms"])
         traffic, traffic_src = measured_traffic(args.workload if (dtype, k) == (wl["dtype"], wl["k"]) else None, dom)
         line = {
