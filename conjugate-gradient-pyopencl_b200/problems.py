@@ -216,6 +216,18 @@ def powerlaw_spd(n: int = 5_000_000, nnz_target: int = 50_000_000, alpha: float 
     return _canonical(A)
 
 
+def row_patterns(A: sp.csr_matrix) -> int:
+    """Number of distinct rows of A written as lists of (column - row, value bits) -- what the engine's row-pattern
+    dictionary finds on the device.  Host-side restatement for tests and for choosing workloads."""
+    A = A.tocsr()
+    ip, ix, d = A.indptr, A.indices, A.data
+    seen = set()
+    for i in range(A.shape[0]):
+        lo, hi = ip[i], ip[i + 1]
+        seen.add(((ix[lo:hi].astype(np.int64) - i).tobytes(), d[lo:hi].tobytes()))
+    return len(seen)
+
+
 def csr_arrays(A: sp.csr_matrix, dtype: str):
     """(values, rowptr, cols) as contiguous arrays of the ABI types for dtype name `dtype`."""
     np_t = DTYPES[dtype][0]

@@ -89,3 +89,23 @@ def test_byte_model():
     assert abs(bs / 1e6 - 184.4) < 0.1 and abs(bi / 1e6 - 335.4) < 0.1
     bs, bi = P.algorithmic_bytes(2097152, 14581760, 32, "f64")
     assert abs(bs / 1e9 - 1.257) < 0.001 and abs(bi / 1e9 - 6.089) < 0.001
+
+
+def test_constant_coefficient_grid_operators_have_a_handful_of_distinct_rows(golden_dir):
+    """Why the row-pattern dictionary applies to the reference's own workload: as lists of
+    (column - row, value) the rows of the BASELINE grid operators, and of the subdomain matrices the unmodified
+    driver built (`local_rect`, recorded in tests/golden/asprec_*.npz), come in 9 (2-D) or 27 (3-D) kinds --
+    in double and after the drivers' cast to csingle alike; a power-law matrix has as many kinds as rows."""
+    import os
+    import scipy.sparse as sp
+    import cg_b200.problems as P
+    assert P.row_patterns(P.poisson2d(40)) == 9
+    assert P.row_patterns(P.laplace3d(12)) == 27
+    assert P.row_patterns(P.helmholtz_fe(48)) == 9
+    for name in ("asprec_2_12.npz", "asprec_3_16.npz"):
+        z = np.load(os.path.join(golden_dir, name))
+        n = int(z["n"])
+        A = sp.csr_matrix((z["data"], z["indices"], z["indptr"]), shape=(n, n))
+        assert P.row_patterns(A) == 9 and P.row_patterns(A.astype(np.complex64)) == 9
+    R = P.powerlaw_spd(n=3000, nnz_target=30000, max_row=400)
+    assert P.row_patterns(R) == R.shape[0]
