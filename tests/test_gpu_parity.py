@@ -800,6 +800,7 @@ def test_pattern_dictionary_spmv_and_cg(gpu, cpu_ref, dname, kind):
     with gpu.Matrix.from_scipy(A) as M:
         M.set_option("solver", 1)
         npat = M.get_option("patterns")
+        assert npat == P.row_patterns(A), (npat, P.row_patterns(A))      # the device finds the rows the host finds
         assert 1 <= npat <= 64, npat
         y1 = M.spmv(x)
         x1, i1 = M.solve(b, max_iterations=60)
