@@ -16,7 +16,9 @@ they do not: the kernels of the loop return at once.  The model shows that
     NEXT solve on a flag raised by a stale, post-convergence push -- the bug seen on hardware as a tolerance solve that
     stopped one iteration late (DESIGN.md section 6);
   * with `halo_push_kernel` returning at once when no column is active, every wait is satisfied by the push of the
-    same logical exchange, in every interleaving tried.
+    same logical exchange, in every interleaving tried;
+  * no push ever lands in a halo region its receiver is still reading (the two all-reduces of an iteration are the
+    barrier that guarantees it).
 """
 import random
 
@@ -32,6 +34,8 @@ class Rank:
         self.flag = [0] * world            # flag[p]: raised by rank p's push (PeerComm::halo_flag)
         self.flag_exchange = [None] * world  # model only: which logical exchange raised it
         self.contrib = {}                  # all-reduce number -> set of ranks whose slot has arrived
+        self.reads_done = 0                # exchanges whose halo this rank has finished reading (its SpMV is over)
+        self.reading = False               # between passing a wait and the all-reduce that ends that SpMV
         self.program = []
         exchange = 0
         for iters, converged_at, chunk in solves:
@@ -76,6 +80,9 @@ def run(world, solves, push_after_convergence, rng):
         progressed = False
         if step[0] == "push":
             for p in neighbours(r.rank, world):
+                if step[1] is not None and ranks[p].reads_done < step[1]:
+                    # the new entries would land in a halo region the receiver has not finished reading
+                    violations.append((r.rank, p, "overwrite", step[1], ranks[p].reads_done))
                 ranks[p].flag[r.rank] = r.seq + 1          # st.release flag = seq + 1   (halo_push_kernel)
                 ranks[p].flag_exchange[r.rank] = step[1]
             r.pc += 1
@@ -86,11 +93,15 @@ def run(world, solves, push_after_convergence, rng):
                 for p in neighbours(r.rank, world):
                     if r.flag_exchange[p] != step[1]:
                         violations.append((r.rank, p, step[1], r.flag_exchange[p]))
+                r.reading = True
                 r.pc += 1
                 progressed = True
         else:                                               # peer_allreduce number seq + 1
             s = r.seq + 1
             if r.rank not in ranks[0].contrib.setdefault(s, set()):
+                if r.reading:                               # the all-reduce sits at the END of the SpMV: its reads are over
+                    r.reading = False
+                    r.reads_done += 1
                 for q in ranks:                             # store the slot into every peer (and itself)
                     q.contrib.setdefault(s, set()).add(r.rank)
                 progressed = True
@@ -123,6 +134,6 @@ def test_the_model_reproduces_the_stale_push_of_the_old_rule(world):
     bad = []
     for _ in range(60):
         bad += run(world, SOLVES_TOL, push_after_convergence=True, rng=rng)
-    assert bad and all(seen is None for (_, _, _, seen) in bad)
+    assert bad and all(len(v) == 4 and v[3] is None for v in bad)
     for _ in range(20):
         assert run(world, SOLVES_FIXED, push_after_convergence=True, rng=rng) == []
