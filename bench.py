@@ -417,6 +417,15 @@ def run_row_block(args, wl, dtype, rank, local_rank, world):
         kms = M.time_kernel(name, reps=reps)
         kernels[name] = {"ms": kms, "algorithmic_bytes": nbytes, "gbs": nbytes / kms / 1e6, "frac": nbytes / kms / 1e6 / peak}
     sinfo = M.info()
+    try:
+        npat = M.get_option("patterns")
+        if npat > 0:       # see the single-GPU line: CSR bytes stay the yardstick, the format moves fewer
+            moved = ln * (2 + 2 * v_bytes)
+            kernels["spmv_dot"].update(format=f"row-pattern dictionary, {npat} distinct rows (DESIGN.md 4.3)",
+                                       moved_bytes=moved, moved_gbs=moved / kernels["spmv_dot"]["ms"] / 1e6,
+                                       moved_frac=moved / kernels["spmv_dot"]["ms"] / 1e6 / peak)
+    except Exception:
+        pass
     M.close()
     if rank == 0:
         it_ms = info["timing_ms"]["iterations"] / ITERS_PER_STEP

@@ -256,6 +256,13 @@ class ShardedMatrix:
     def set_option(self, key, value):
         _lib.check(_lib.lib().cgb200_shard_set_option(self._h, key.encode(), int(value)))
 
+    def get_option(self, key):
+        """An option / read-only fact of the local row block's handle (e.g. "patterns")."""
+        v = ctypes.c_longlong()
+        h = ctypes.c_void_p(_lib.lib().cgb200_shard_local(self._h))
+        _lib.check(_lib.lib().cgb200_get_option(h, key.encode(), ctypes.byref(v)))
+        return v.value
+
     def info(self):
         out = (ctypes.c_longlong * 8)()
         _lib.check(_lib.lib().cgb200_shard_info(self._h, out))
