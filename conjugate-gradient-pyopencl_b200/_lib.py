@@ -15,6 +15,7 @@ except ImportError:  # imported as a top-level module (package dir on sys.path, 
 F32, F64, C64, C128 = 0, 1, 2, 3
 LAYOUT_CLCG, LAYOUT_ROWMAJOR = 0, 1
 FLAG_MAXIT, FLAG_BREAKDOWN = 1, 2
+P2P_BLOB_BYTES = 256       # CGB200_P2P_BLOB_BYTES
 DTYPE_CODE = {np.dtype(np.float32): F32, np.dtype(np.float64): F64,
               np.dtype(np.complex64): C64, np.dtype(np.complex128): C128}
 CODE_DTYPE = {v: k for k, v in DTYPE_CODE.items()}

@@ -42,21 +42,45 @@ def _stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def _replace_copy(src, dst):
+    """Copy through a temporary name + os.replace: a reader never sees a half-written file."""
+    os.makedirs(os.path.dirname(dst), exist_ok=True)
+    tmp = f"{dst}.tmp.{os.getpid()}"
+    shutil.copy2(src, tmp)
+    os.replace(tmp, dst)
+
+
 def build(force=False, verbose=False):
-    """Compile (if stale) and place the copies the reference drivers expect.  Returns the path."""
-    if force or _stale():
-        cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-              ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
-        # the image exports CC/CXX pointing at a wrapper without OpenMP specs; nvcc wants plain g++
-        env = dict(os.environ)
-        env.pop("CC", None)
-        env.pop("CXX", None)
-        subprocess.check_call(cmd, cwd=CSRC, env=env)
-    for dst in (os.path.join(ROOT, "build", "liboclcg.so"), os.path.join(ROOT, "liboclcg.so")):
-        os.makedirs(os.path.dirname(dst), exist_ok=True)
-        if not os.path.exists(dst) or os.path.getmtime(dst) < os.path.getmtime(LIB):
-            shutil.copy2(LIB, dst)
-    build_example()
+    """Compile (if stale) and place the copies the reference drivers expect.  Returns the path.
+
+    Safe under torchrun: the ranks of one box serialise on a file lock, the first one in builds into a
+    temporary file and renames it into place, the others find a fresh library."""
+    import fcntl
+    import hashlib
+    os.makedirs(os.path.join(ROOT, "build"), exist_ok=True)
+    with open(os.path.join(ROOT, "build", ".lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if force or _stale():
+                tmp = f"{LIB}.tmp.{os.getpid()}"
+                cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+                      ["-o", tmp] + [os.path.join(CSRC, s) for s in SOURCES]
+                # the image exports CC/CXX pointing at a wrapper without OpenMP specs; nvcc wants plain g++
+                env = dict(os.environ)
+                env.pop("CC", None)
+                env.pop("CXX", None)
+                subprocess.check_call(cmd, cwd=CSRC, env=env)
+                os.replace(tmp, LIB)
+                # so that a build log proves which binary a run used
+                with open(LIB, "rb") as f:
+                    digest = hashlib.sha256(f.read()).hexdigest()[:16]
+                print("cgb200 build:", " ".join(cmd[:-3] + ["-o", LIB] + cmd[-1:]), f"-> sha256 {digest}", file=sys.stderr)
+            for dst in (os.path.join(ROOT, "build", "liboclcg.so"), os.path.join(ROOT, "liboclcg.so")):
+                if not os.path.exists(dst) or os.path.getmtime(dst) < os.path.getmtime(LIB):
+                    _replace_copy(LIB, dst)
+            build_example()
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB
 
 
@@ -70,8 +94,10 @@ def build_example(force=False):
     if not force and os.path.exists(EXE) and os.path.getmtime(EXE) >= max(os.path.getmtime(src), os.path.getmtime(LIB)):
         return EXE
     gcc = shutil.which("gcc") or "/usr/bin/gcc"
-    subprocess.check_call([gcc, "-O2", "-std=c11", "-Wall", "-o", EXE, src, "-L" + os.path.join(ROOT, "build"),
+    tmp = f"{EXE}.tmp.{os.getpid()}"
+    subprocess.check_call([gcc, "-O2", "-std=c11", "-Wall", "-o", tmp, src, "-L" + os.path.join(ROOT, "build"),
                            "-loclcg", "-lm", "-Wl,-rpath,$ORIGIN"])
+    os.replace(tmp, EXE)
     return EXE
 
 

@@ -26,6 +26,7 @@
 #include "../../include/cgb200.h"
 #include "../../include/clcg.h"
 #include "kernels.cuh"
+#include "cg2.cuh"
 
 using namespace cgb;
 
@@ -79,6 +80,13 @@ struct cgb200_ctx {
     int *d_pat_chunks = nullptr;
     int npat = 0, pat_ok = 0, pattern = 1, pat_chunks = 0, pat_chunks_interior = 0;
     int pattern_regs = 0;        // experiment: the last pattern kept in registers (spmv_pattern_regs_kernel), unmeasured
+    // two-kernel iteration (cg2.cuh): window plan of the pattern dictionary's column offsets
+    PatWindows win;
+    int cg2 = 1;                 // option: use the two-kernel iteration when the matrix allows it (k = 1)
+    int cg2_ok = 0;              // the dictionary's offsets fit the window plan
+    int cg2_blocks = 0;          // option: blocks per SM of dir_spmv (0: what fits)
+    int *d_pspos = nullptr;      // [npat][PAT_MAXLEN] staging position of every pattern entry
+    unsigned *d_pat_mask = nullptr, *d_chunk_mask = nullptr;   // windows used per pattern / per chunk of rows
     int irregular = 0;           // row lengths vary wildly inside a tile (power-law graphs), see upload_matrix
     // CSR-stream schedule (k = 1): tiles of whole rows / chunks of long rows
     void *d_tiles = nullptr, *d_long = nullptr, *d_chunk_sum = nullptr;
@@ -102,16 +110,22 @@ struct cgb200_ctx {
     // workspace (for ws_k right-hand sides)
     int ws_k = 0;
     void *x = nullptr, *r = nullptr, *d = nullptr, *q = nullptr, *stage = nullptr;
+    void *r2 = nullptr, *d2 = nullptr;   // second residual / direction buffer of the two-kernel iteration (k = 1)
+    void *vec_block = nullptr;           // r, r2, d, d2 live in ONE allocation (one CUDA-IPC handle for the peers)
+    size_t vec_off[4] = {0, 0, 0, 0};    // byte offsets of d, d2, r, r2 in vec_block (PeerComm::vec order)
     void *scal_mem = nullptr;   // device block the CgScalars arrays are carved from
     void *partial = nullptr;
     int grid_cap = 0;
     double *d_hist = nullptr;
     size_t hist_doubles = 0;
     int *h_flag = nullptr;      // pinned
+    int *d_flag = nullptr;      // device word for upload-time checks
+    int matrix_ok = 0;          // 0: the last upload was rejected half-way (bad column index): solves refuse
     // graphs: (k, chunk) -> exec ; dropped whenever buffers or options change
     cudaGraphExec_t graph = nullptr;
     int graph_k = 0, graph_chunk_built = 0;
     int graph_hist_cap = -1;
+    int graph_cg2 = -1;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     double last_ms[4] = {0, 0, 0, 0};
     long long launches = 0, graph_launches = 0, graph_nodes = 0;
@@ -137,11 +151,12 @@ static void drop_graph(cgb200_ctx *c) {
 
 static void free_workspace(cgb200_ctx *c) {
     drop_graph(c);
-    void **bufs[] = {&c->x, &c->r, &c->d, &c->q, &c->stage, &c->scal_mem, &c->partial};
+    void **bufs[] = {&c->x, &c->vec_block, &c->q, &c->stage, &c->scal_mem, &c->partial};
     for (void **b : bufs) {
         if (*b) cudaFree(*b);
         *b = nullptr;
     }
+    c->r = c->r2 = c->d = c->d2 = nullptr;
     c->ws_k = 0;
 }
 
@@ -238,6 +253,9 @@ template <typename T> struct Engine {
         s.it = (int *)take(sizeof(int));
         s.ticket = (unsigned *)take(4 * sizeof(unsigned));
         s.rr = (T *)take(kk * sizeof(T));
+        s.alpha = (T *)take(kk * sizeof(T));
+        s.beta = (T *)take(kk * sizeof(T));
+        s.cg2 = 0;
         s.tol = (const double *)take(sizeof(double));
         s.defer = 0;
         s.peer = nullptr;
@@ -254,7 +272,7 @@ template <typename T> struct Engine {
         return s;
     }
     static size_t scalars_bytes(int k) {
-        return (size_t)k * (3 * sizeof(T) + sizeof(double) + 2 * sizeof(int)) + (size_t)k * sizeof(T) + 16 * 14 + 64;
+        return (size_t)k * (3 * sizeof(T) + sizeof(double) + 2 * sizeof(int)) + (size_t)k * 3 * sizeof(T) + 16 * 16 + 64;
     }
 
     static int ensure_workspace(cgb200_ctx *c, int k) {
@@ -262,8 +280,21 @@ template <typename T> struct Engine {
         free_workspace(c);
         const size_t bytes = (size_t)c->n * k * sizeof(T) + 64;
         CU(cudaMalloc(&c->x, bytes));
-        CU(cudaMalloc(&c->r, bytes));
-        CU(cudaMalloc(&c->d, bytes + (size_t)c->extra_cols * k * sizeof(T)));
+        {   // d, d2, r, r2 ([owned | halo] each; the second buffers only for k = 1) in one block
+            const size_t each = (((size_t)(c->n + c->extra_cols) * k * sizeof(T) + 256) + 255) & ~(size_t)255;
+            const int nvec = k == 1 ? 4 : 2;
+            CU(cudaMalloc(&c->vec_block, each * nvec));
+            CU(cudaMemset(c->vec_block, 0, each * nvec));
+            char *base = (char *)c->vec_block;
+            for (int i = 0; i < 4; i++) c->vec_off[i] = 0;
+            if (k == 1) {
+                c->d = base; c->d2 = base + each; c->r = base + 2 * each; c->r2 = base + 3 * each;
+                for (int i = 0; i < 4; i++) c->vec_off[i] = each * i;
+            } else {
+                c->d = base; c->r = base + each;
+                c->vec_off[2] = each;
+            }
+        }
         CU(cudaMalloc(&c->q, bytes));
         if (k > 1) CU(cudaMalloc(&c->stage, bytes));
         CU(cudaMalloc(&c->scal_mem, scalars_bytes(k)));
@@ -357,7 +388,151 @@ template <typename T> struct Engine {
             CU(cudaMalloc(&c->d_pat_chunks, inner.size() * sizeof(int)));
             CU(cudaMemcpy(c->d_pat_chunks, inner.data(), inner.size() * sizeof(int), cudaMemcpyHostToDevice));
         }
+        TRY(build_windows(c));
         return 0;
+    }
+    // Window plan of the two-kernel iteration (cg2.cuh): the distinct column offsets of the dictionary, merged
+    // into windows when they are closer than a chunk of rows, and for every pattern entry its position in
+    // the staged array.  Fails softly (cg2_ok = 0: the three-kernel iteration stays in use).
+    static size_t cg2_smem_bytes(const cgb200_ctx *c, int stride) {
+        return (size_t)(PAT_THREADS + c->npat * stride + c->win.total) * sizeof(T) + (size_t)c->npat * stride * sizeof(int) +
+               (size_t)c->npat * sizeof(int) + 16;
+    }
+    static int pat_stride(const cgb200_ctx *c) { return c->max_row <= 8 ? 8 : (c->max_row <= 16 ? 16 : 32); }
+    static int build_windows(cgb200_ctx *c) {
+        c->cg2_ok = 0;
+        const int npat = c->npat;
+        std::vector<int> len(npat), off((size_t)npat * PAT_MAXLEN);
+        CU(cudaMemcpy(len.data(), c->d_plen, (size_t)npat * sizeof(int), cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(off.data(), c->d_poff, off.size() * sizeof(int), cudaMemcpyDeviceToHost));
+        std::set<int> offs;
+        offs.insert(0);
+        for (int p = 0; p < npat; p++)
+            for (int j = 0; j < len[p]; j++) offs.insert(off[(size_t)p * PAT_MAXLEN + j]);
+        auto floor_to = [](long long v, int m) { return (int)(v >= 0 ? v - v % m : v - ((v % m) + m) % m); };
+        PatWindows w;
+        memset(&w, 0, sizeof(w));
+        int cur_lo = 0, cur_hi = 0;
+        bool open = false;
+        std::vector<std::pair<int, int>> groups;
+        for (int o : offs) {
+            if (open && (long long)o - cur_hi < PAT_CHUNK) {
+                cur_hi = o;
+            } else {
+                if (open) groups.push_back({cur_lo, cur_hi});
+                cur_lo = cur_hi = o;
+                open = true;
+            }
+        }
+        if (open) groups.push_back({cur_lo, cur_hi});
+        if ((int)groups.size() > WIN_MAX) return 0;
+        long long total = 0;
+        for (size_t g = 0; g < groups.size(); g++) {
+            const int lo = floor_to(groups[g].first, VW);
+            const long long size = (((long long)groups[g].second - lo + PAT_CHUNK) + VW - 1) / VW * VW;
+            w.lo[g] = lo;
+            w.size[g] = (int)size;
+            w.base[g] = (int)total;
+            total += size;
+            if (total > (1 << 20)) return 0;
+        }
+        w.nwin = (int)groups.size();
+        w.total = (int)total;
+        auto spos_of = [&](int o) {
+            for (int g = 0; g < w.nwin; g++)
+                if (o >= w.lo[g] && o < w.lo[g] + w.size[g] - PAT_CHUNK + 1 && o >= groups[g].first && o <= groups[g].second)
+                    return std::make_pair(g, w.base[g] + (o - w.lo[g]));
+            return std::make_pair(-1, -1);
+        };
+        w.diag = spos_of(0).second;
+        c->win = w;
+        // the staged array, the table and the reduction scratch must leave room for >= 2 blocks per SM
+        if (cg2_smem_bytes(c, pat_stride(c)) > 100 * 1024) return 0;
+        std::vector<int> spos((size_t)npat * PAT_MAXLEN);
+        std::vector<unsigned> pmask(npat);
+        for (int p = 0; p < npat; p++) {
+            unsigned m = 1u << spos_of(0).first;
+            for (int j = 0; j < PAT_MAXLEN; j++) {
+                if (j < len[p]) {
+                    const auto gp = spos_of(off[(size_t)p * PAT_MAXLEN + j]);
+                    if (gp.first < 0) return 0;
+                    spos[(size_t)p * PAT_MAXLEN + j] = gp.second;
+                    m |= 1u << gp.first;
+                } else {
+                    spos[(size_t)p * PAT_MAXLEN + j] = w.diag;      // padding: the row's own entry, coefficient 0
+                }
+            }
+            pmask[p] = m;
+        }
+        if (!c->d_pspos) {
+            CU(cudaMalloc(&c->d_pspos, (size_t)PAT_MAXCOUNT * PAT_MAXLEN * sizeof(int)));
+            CU(cudaMalloc(&c->d_pat_mask, (size_t)PAT_MAXCOUNT * sizeof(unsigned)));
+            CU(cudaMalloc(&c->d_chunk_mask, (size_t)((c->n + PAT_CHUNK - 1) / PAT_CHUNK) * sizeof(unsigned)));
+        }
+        CU(cudaMemcpy(c->d_pspos, spos.data(), spos.size() * sizeof(int), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(c->d_pat_mask, pmask.data(), pmask.size() * sizeof(unsigned), cudaMemcpyHostToDevice));
+        chunk_window_mask_kernel<<<std::min(c->pat_chunks, c->sm_count * 8), 256, 0, c->stream>>>(
+            c->n, c->pat_chunks, (const unsigned short *)c->d_pat, c->d_pat_mask, c->d_chunk_mask);
+        CU(cudaStreamSynchronize(c->stream));
+        c->launches++;
+        c->cg2_ok = 1;
+        return 0;
+    }
+    // ---- the two-kernel iteration ------------------------------------------------
+    static bool use_cg2(const cgb200_ctx *c, int k) {
+        return k == 1 && c->cg2 && c->cg2_ok && c->pat_ok && c->pattern && c->d_tiles && c->spmv_variant == 0;
+    }
+    template <bool PEER>
+    static int launch_dir_spmv(cgb200_ctx *c, const CgScalars<T> &sc) {
+        const int stride = pat_stride(c);
+        const size_t smem = cg2_smem_bytes(c, stride);
+        auto launch = [&](auto kern) -> int {
+            const void *key = (const void *)kern;
+            if (c->occ.find(key) == c->occ.end())
+                CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(100 * 1024 + 1024)));
+            const int bps = c->blocks_per_sm;
+            if (c->cg2_blocks > 0) c->blocks_per_sm = c->cg2_blocks;
+            int grid = persistent_grid(c, kern, PAT_THREADS, smem, c->pat_chunks);
+            c->blocks_per_sm = bps;
+            const int per = (c->pat_chunks + grid - 1) / grid;
+            grid = (c->pat_chunks + per - 1) / per;
+            c->spmv_grid_last = grid;
+            CU(launch_kernel(kern, dim3(grid), dim3(PAT_THREADS), smem, c->stream, (c->pdl & 1) != 0, c->n, c->n + c->extra_cols,
+                             c->pat_chunks, c->npat, c->win, (const unsigned short *)c->d_pat, (const unsigned *)c->d_chunk_mask,
+                             (const int *)c->d_plen, (const int *)c->d_pspos, (const T *)c->d_pval, (T *)c->x, (T *)c->q,
+                             (T *)c->r, (T *)c->r2, (T *)c->d, (T *)c->d2, sc));
+            c->launches++;
+            return 0;
+        };
+        if (stride == 8) return launch(cg2_dir_spmv_kernel<T, 8, PEER>);
+        if (stride == 16) return launch(cg2_dir_spmv_kernel<T, 16, PEER>);
+        return launch(cg2_dir_spmv_kernel<T, 32, PEER>);
+    }
+    template <bool PEER>
+    static int launch_update_r(cgb200_ctx *c, const CgScalars<T> &sc) {
+        auto kern = cg2_update_r_kernel<T, VW, PEER>;
+        const int block = 256;
+        const size_t smem = (size_t)block * sizeof(T);
+        const size_t nelem = (size_t)c->n, npacks = nelem / VW;
+        const int grid = persistent_grid(c, kern, block, smem, (long long)((npacks + block - 1) / block));
+        CU(launch_kernel(kern, dim3(grid), dim3(block), smem, c->stream, (c->pdl & 2) != 0, npacks, nelem, (const T *)c->q,
+                         (T *)c->r, (T *)c->r2, sc));
+        c->launches++;
+        return 0;
+    }
+    static int launch_finish_x(cgb200_ctx *c, const CgScalars<T> &sc) {
+        const int grid = (int)std::min<long long>((long long)c->sm_count * 8, ((long long)c->n + 255) / 256);
+        cg2_finish_x_kernel<T><<<grid, 256, 0, c->stream>>>((size_t)c->n, (T *)c->x, (const T *)c->d, (const T *)c->d2, sc);
+        c->launches++;
+        return 0;
+    }
+    static int cg2_iteration(cgb200_ctx *c, const CgScalars<T> &sc) {
+        if (sc.peer) {
+            TRY(launch_dir_spmv<true>(c, sc));
+            return launch_update_r<true>(c, sc);
+        }
+        TRY(launch_dir_spmv<false>(c, sc));
+        return launch_update_r<false>(c, sc);
     }
     template <bool DOT>
     static int spmv_pattern(cgb200_ctx *c, const T *x, T *y, const CgScalars<T> &sc) {
@@ -748,6 +923,12 @@ template <typename T> struct Engine {
                 }
             }
             CU(cudaGetLastError());
+            // the header promises asynchrony for DEVICE pointers only: with (pinned) host memory the copies above
+            // are truly asynchronous and y would not be filled on return
+            cudaPointerAttributes ax, ay;
+            CU(cudaPointerGetAttributes(&ax, x));
+            CU(cudaPointerGetAttributes(&ay, y));
+            if (ax.type != cudaMemoryTypeDevice || ay.type != cudaMemoryTypeDevice) CU(cudaStreamSynchronize(c->stream));
             return 0;
         }
         // k == 1, or row-major: device pointers are used in place, host pointers are staged
@@ -793,14 +974,18 @@ template <typename T> struct Engine {
             }
             CU(cudaMemsetAsync(c->d_hist, 0, need * sizeof(double), c->stream));
         }
-        const CgScalars<T> sc = scalars(c, k, tol, hist_cap);
+        CgScalars<T> sc = scalars(c, k, tol, hist_cap);
         const VecGeom g = geom(c, k);
+        const bool fused = fused_eligible(c, k);
+        const bool cg2 = !fused && use_cg2(c, k);
+        sc.cg2 = cg2 ? 1 : 0;
         CU(cudaMemcpyAsync((void *)sc.tol, &tol, sizeof(double), cudaMemcpyHostToDevice, c->stream));
 
         CU(cudaEventRecord(c->ev[0], c->stream));
-        // inputs: b -> d (temporarily), x0 -> x
+        // inputs: b -> d (temporarily; the two-kernel iteration parks it in the spare residual buffer), x0 -> x
+        void *b_dev = cg2 ? c->r2 : c->d;
         if (k == 1 || layout == CGB200_LAYOUT_ROWMAJOR) {
-            CU(cudaMemcpyAsync(c->d, b, bytes, cudaMemcpyDefault, c->stream));
+            CU(cudaMemcpyAsync(b_dev, b, bytes, cudaMemcpyDefault, c->stream));
             CU(cudaMemcpyAsync(c->x, x, bytes, cudaMemcpyDefault, c->stream));
         } else {
             CU(cudaMemcpyAsync(c->stage, b, bytes, cudaMemcpyDefault, c->stream));
@@ -810,7 +995,7 @@ template <typename T> struct Engine {
         }
         CU(cudaEventRecord(c->ev[1], c->stream));
 
-        if (fused_eligible(c, k)) {
+        if (fused) {
             // initialisation and every iteration in one cooperative launch; converged columns freeze and
             // the kernel returns by itself once none is active, so there is nothing to poll
             CU(cudaEventRecord(c->ev[2], c->stream));
@@ -818,21 +1003,23 @@ template <typename T> struct Engine {
         } else {
             // q = A x0 ; r = b - q ; d = r ; delta = r.r          clcg.c:253-292
             TRY(spmv<false>(c, k, (const T *)c->x, (T *)c->q, sc));
-            if (g.V == 1) TRY(launch_init<1>(c, k, g, (const T *)c->d, (const T *)c->q, (T *)c->r, (T *)c->d, sc));
-            else TRY(launch_init<VW>(c, k, g, (const T *)c->d, (const T *)c->q, (T *)c->r, (T *)c->d, sc));
+            if (g.V == 1) TRY(launch_init<1>(c, k, g, (const T *)b_dev, (const T *)c->q, (T *)c->r, (T *)c->d, sc));
+            else TRY(launch_init<VW>(c, k, g, (const T *)b_dev, (const T *)c->q, (T *)c->r, (T *)c->d, sc));
             CU(cudaEventRecord(c->ev[2], c->stream));
 
             // the loop, clcg.c:296-419
+            auto iterate = [&]() -> int { return cg2 ? cg2_iteration(c, sc) : iteration(c, k, g, sc); };
             int done = 0;
             const int chunk = std::max(1, c->graph_chunk);
             if (c->use_graph && maxit >= chunk) {
-                if (!c->graph || c->graph_k != k || c->graph_chunk_built != chunk || c->graph_hist_cap != hist_cap) {
+                if (!c->graph || c->graph_k != k || c->graph_chunk_built != chunk || c->graph_hist_cap != hist_cap ||
+                    c->graph_cg2 != (int)cg2) {
                     drop_graph(c);
                     cudaGraph_t gr = nullptr;
                     const long long before = c->launches;
                     CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
                     int rc = 0;
-                    for (int i = 0; i < chunk && rc == 0; i++) rc = iteration(c, k, g, sc);
+                    for (int i = 0; i < chunk && rc == 0; i++) rc = iterate();
                     cudaError_t ce = cudaStreamEndCapture(c->stream, &gr);
                     c->graph_nodes = c->launches - before;
                     c->launches = before;
@@ -841,6 +1028,7 @@ template <typename T> struct Engine {
                     ce = cudaGraphInstantiate(&c->graph, gr, 0);
                     cudaGraphDestroy(gr);
                     if (ce != cudaSuccess) return fail(CGB200_ERR_CUDA, "graph instantiate: %s", cudaGetErrorString(ce));
+                    c->graph_cg2 = (int)cg2;
                     c->graph_k = k;
                     c->graph_chunk_built = chunk;
                     c->graph_hist_cap = hist_cap;
@@ -858,13 +1046,14 @@ template <typename T> struct Engine {
                 }
             }
             for (; done < maxit; done++) {
-                TRY(iteration(c, k, g, sc));
+                TRY(iterate());
                 if (tol > 0 && (done % chunk) == chunk - 1) {
                     CU(cudaMemcpyAsync(c->h_flag, sc.n_active, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
                     CU(cudaStreamSynchronize(c->stream));
                     if (*c->h_flag == 0) break;
                 }
             }
+            if (cg2) TRY(launch_finish_x(c, sc));      // x lags one update behind in the two-kernel iteration
         }
         CU(cudaEventRecord(c->ev[3], c->stream));
 
@@ -934,14 +1123,20 @@ template <typename T> struct Engine {
         int one = k;
         CU(cudaMemcpyAsync(sc.n_active, &one, sizeof(int), cudaMemcpyHostToDevice, c->stream));
         CU(cudaStreamSynchronize(c->stream));
-        if (which == 1) CU(cudaMemsetAsync(sc.dq, 0, k * sizeof(T), c->stream));
+        if (which == 1 || which == 5) CU(cudaMemsetAsync(sc.dq, 0, k * sizeof(T), c->stream));
         if (which == 2) CU(cudaMemsetAsync(sc.delta_new, 0, k * sizeof(T), c->stream));
+        if (which >= 4) {      // alpha = beta = 0: x and the direction stay what they are
+            CU(cudaMemsetAsync(sc.alpha, 0, k * sizeof(T), c->stream));
+            CU(cudaMemsetAsync(sc.beta, 0, k * sizeof(T), c->stream));
+        }
         auto launch = [&]() -> int {
             switch (which) {
             case 0: return spmv<true>(c, k, (const T *)c->d, (T *)c->q, sc);
             case 1: return g.V == 1 ? launch_update_xr<1>(c, k, g, sc) : launch_update_xr<VW>(c, k, g, sc);
             case 2: return g.V == 1 ? launch_update_d<1>(c, k, g, sc) : launch_update_d<VW>(c, k, g, sc);
             case 3: return spmv<false>(c, k, (const T *)c->d, (T *)c->q, sc);
+            case 4: return use_cg2(c, k) ? launch_dir_spmv<false>(c, sc) : fail(CGB200_ERR_UNSUPPORTED, "no two-kernel iteration for this matrix / k");
+            case 5: return use_cg2(c, k) ? launch_update_r<false>(c, sc) : fail(CGB200_ERR_UNSUPPORTED, "no two-kernel iteration for this matrix / k");
             }
             return fail(CGB200_ERR_ARG, "time_kernel: which=%d", which);
         };
@@ -990,9 +1185,18 @@ template <typename T> struct Engine {
         return fail(CGB200_ERR_ARG, "bad dtype %d", (c)->dtype);             \
     }()
 
-static uint64_t hash_span(const unsigned char *p, size_t bytes, uint64_t seed) {
+// Content identity of a host array: two independent 64-bit lanes (a 128-bit identity), one pass over the bytes.
+struct Hash128 {
+    uint64_t a = 0, b = 0;
+    bool operator==(const Hash128 &o) const { return a == o.a && b == o.b; }
+    bool operator!=(const Hash128 &o) const { return !(*this == o); }
+};
+
+static Hash128 hash_span(const unsigned char *p, size_t bytes, uint64_t seed) {
     uint64_t h[4] = {seed ^ 0x9E3779B97F4A7C15ull, seed ^ 0xC2B2AE3D27D4EB4Full, seed ^ 0x165667B19E3779F9ull,
                      seed ^ 0x27D4EB2F165667C5ull};
+    uint64_t g[4] = {~seed ^ 0xA0761D6478BD642Full, seed + 0xE7037ED1A0B428DBull, seed ^ 0x8EBC6AF09C88C6E3ull,
+                     seed + 0x589965CC75374CC3ull};
     size_t i = 0;
     for (; i + 32 <= bytes; i += 32) {
         uint64_t w[4];
@@ -1000,31 +1204,55 @@ static uint64_t hash_span(const unsigned char *p, size_t bytes, uint64_t seed) {
         for (int l = 0; l < 4; l++) {
             h[l] = (h[l] ^ w[l]) * 0x100000001B3ull;
             h[l] = (h[l] << 27) | (h[l] >> 37);
+            g[l] = (g[l] + w[l]) * 0xFF51AFD7ED558CCDull;     // a second, unrelated mixing of the same words
+            g[l] ^= g[l] >> 29;
         }
     }
     uint64_t tail = 0;
     for (; i < bytes; i++) tail = tail * 131 + p[i];
-    uint64_t r = h[0];
-    for (int l = 1; l < 4; l++) r = (r ^ h[l]) * 0x9E3779B97F4A7C15ull + (r >> 29);
-    return (r ^ tail) * 0xD6E8FEB86659FD93ull;
+    Hash128 r;
+    r.a = h[0];
+    r.b = g[0];
+    for (int l = 1; l < 4; l++) {
+        r.a = (r.a ^ h[l]) * 0x9E3779B97F4A7C15ull + (r.a >> 29);
+        r.b = (r.b + g[l]) * 0xC4CEB9FE1A85EC53ull ^ (r.b >> 31);
+    }
+    r.a = (r.a ^ tail) * 0xD6E8FEB86659FD93ull;
+    r.b = (r.b + tail + bytes) * 0x94D049BB133111EBull;
+    return r;
 }
 
-static uint64_t hash_bytes(const void *ptr, size_t bytes, uint64_t seed) {
+static Hash128 hash_bytes128(const void *ptr, size_t bytes, Hash128 seed) {
     const unsigned char *p = (const unsigned char *)ptr;
     const size_t min_chunk = 4u << 20;
-    int nt = (int)std::min<size_t>(8, bytes / min_chunk);
-    if (nt <= 1) return hash_span(p, bytes, seed);
-    std::vector<uint64_t> parts(nt);
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    int nt = (int)std::min<size_t>(std::min(32u, hw), bytes / min_chunk);
+    if (nt <= 1) {
+        Hash128 r = hash_span(p, bytes, seed.a);
+        r.b ^= seed.b * 0x9E3779B97F4A7C15ull;
+        return r;
+    }
+    std::vector<Hash128> parts(nt);
     std::vector<std::thread> th;
     const size_t chunk = ((bytes / nt) + 31) & ~(size_t)31;
     for (int i = 0; i < nt; i++) {
         const size_t lo = std::min(bytes, (size_t)i * chunk), hi = (i == nt - 1) ? bytes : std::min(bytes, lo + chunk);
-        th.emplace_back([&, i, lo, hi] { parts[i] = hash_span(p + lo, hi - lo, seed + i); });
+        th.emplace_back([&, i, lo, hi] { parts[i] = hash_span(p + lo, hi - lo, seed.a + i); });
     }
     for (auto &t : th) t.join();
-    uint64_t r = seed;
-    for (int i = 0; i < nt; i++) r = (r ^ parts[i]) * 0x9E3779B97F4A7C15ull + (r >> 31);
+    Hash128 r = seed;
+    for (int i = 0; i < nt; i++) {
+        r.a = (r.a ^ parts[i].a) * 0x9E3779B97F4A7C15ull + (r.a >> 31);
+        r.b = (r.b + parts[i].b) * 0xD6E8FEB86659FD93ull ^ (r.b >> 27);
+    }
     return r;
+}
+
+static uint64_t hash_bytes(const void *ptr, size_t bytes, uint64_t seed) {
+    Hash128 s;
+    s.a = seed;
+    s.b = ~seed;
+    return hash_bytes128(ptr, bytes, s).a;
 }
 
 
@@ -1064,24 +1292,33 @@ static void detect_grid(cgb200_ctx *c, const std::vector<int> &rp) {
     }
 }
 
+// 1 in *bad when some column index lies outside [0, ncols).  One pass over the index array at upload (C4: 0.75 GB,
+// ~0.15 ms): a bad index then is CGB200_ERR_ARG instead of a sticky device fault for the whole process.
+__global__ void __launch_bounds__(256) check_cols_kernel(long long nnz, const int *__restrict__ cols, int ncols, int *bad) {
+    bool out = false;
+    for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < nnz; j += (long long)gridDim.x * blockDim.x) {
+        const int cidx = cols[j];
+        out |= (cidx < 0) | (cidx >= ncols);
+    }
+    if (__syncthreads_or(out) && threadIdx.x == 0) *bad = 1;
+}
+
 // Copies the CSR arrays (host or device pointers) into the handle's buffers and (re)builds the
 // SpMV schedule when the sparsity pattern's row offsets changed.
+//
+// Order matters (a rejected cgb200_update() must not leave a half-replaced matrix behind a live handle):
+// the row offsets are read to the host and validated BEFORE anything resident is overwritten; the column
+// indices can only be range-checked once they are on the device, so a handle whose new indices are bad
+// is marked unusable (`matrix_ok`) until an update succeeds.  Every captured graph has the SpMV kernel
+// choice, the pattern count and the dictionary pointers baked in, so it is dropped first.
 static int upload_matrix(cgb200_ctx *c, const void *aValues, const int *aPointers, const int *aCols) {
     const int n = c->n;
     const long long nnz = c->nnz;
     const size_t vs = c->vsize;
-    CU(cudaMemcpyAsync(c->d_vals, aValues, (size_t)nnz * vs, cudaMemcpyDefault, c->stream));
-    CU(cudaMemcpyAsync(c->d_cols, aCols, (size_t)nnz * sizeof(int), cudaMemcpyDefault, c->stream));
-    CU(cudaMemcpyAsync(c->d_rowptr, aPointers, ((size_t)n + 1) * sizeof(int), cudaMemcpyDefault, c->stream));
-    // row-length statistics choose the SpMV schedule
+    drop_graph(c);
     std::vector<int> rp((size_t)n + 1);
-    CU(cudaMemcpyAsync(rp.data(), c->d_rowptr, ((size_t)n + 1) * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(rp.data(), aPointers, ((size_t)n + 1) * sizeof(int), cudaMemcpyDefault, c->stream));
     CU(cudaStreamSynchronize(c->stream));
-    const uint64_t rh = hash_bytes(rp.data(), rp.size() * sizeof(int), 7);
-    if (c->d_tiles && rh == c->rowptr_hash) {               // same row offsets: the tiles stand,
-        TRY(DISPATCH(c, E::build_patterns(c)));             // the row patterns (values!) may not
-        return 0;
-    }
     if (rp[0] != 0 || rp[n] != (int)nnz)
         return fail(CGB200_ERR_ARG, "aPointers[0]=%d aPointers[n]=%d but nnz=%lld", rp[0], rp[n], nnz);
     int mx = 0;
@@ -1092,12 +1329,34 @@ static int upload_matrix(cgb200_ctx *c, const void *aValues, const int *aPointer
         mx = std::max(mx, len);
         if (len > 32) in_long_rows += len;
     }
+    c->matrix_ok = 0;
+    CU(cudaMemcpyAsync(c->d_vals, aValues, (size_t)nnz * vs, cudaMemcpyDefault, c->stream));
+    CU(cudaMemcpyAsync(c->d_cols, aCols, (size_t)nnz * sizeof(int), cudaMemcpyDefault, c->stream));
+    CU(cudaMemcpyAsync(c->d_rowptr, rp.data(), ((size_t)n + 1) * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    if (nnz > 0) {
+        int *d_bad = c->d_flag;
+        CU(cudaMemsetAsync(d_bad, 0, sizeof(int), c->stream));
+        const int grid = (int)std::min<long long>((long long)c->sm_count * 8, (nnz + 255) / 256);
+        check_cols_kernel<<<grid, 256, 0, c->stream>>>(nnz, c->d_cols, c->n + c->extra_cols, d_bad);
+        int bad = 0;
+        CU(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        c->launches++;
+        if (bad) return fail(CGB200_ERR_ARG, "aCols holds an index outside [0, %d)", c->n + c->extra_cols);
+    } else {
+        CU(cudaStreamSynchronize(c->stream));
+    }
+    const uint64_t rh = hash_bytes(rp.data(), rp.size() * sizeof(int), 7);
+    if (c->d_tiles && rh == c->rowptr_hash) {               // same row offsets: the tiles stand,
+        TRY(DISPATCH(c, E::build_patterns(c)));             // the row patterns (values!) may not
+        c->matrix_ok = 1;
+        return 0;
+    }
     c->max_row = mx;
     c->mean_row = (double)nnz / n;
     // the share of the non-zeros that sits in rows of more than 32 entries, next to a short mean row: the rows of
     // a tile then differ wildly in length and the per-non-zero balanced kernel is the faster schedule
     c->irregular = (nnz > 0 && c->mean_row < 32.0 && (double)in_long_rows > 0.05 * (double)nnz) ? 1 : 0;
-    drop_graph(c);
     void **old[] = {&c->d_tiles, &c->d_long, &c->d_chunk_sum};
     for (void **b : old) {
         if (*b) cudaFree(*b);
@@ -1107,6 +1366,7 @@ static int upload_matrix(cgb200_ctx *c, const void *aValues, const int *aPointer
     c->rowptr_hash = rh;
     detect_grid(c, rp);
     TRY(DISPATCH(c, E::build_patterns(c)));
+    c->matrix_ok = 1;
     return 0;
 }
 
@@ -1138,8 +1398,12 @@ int cgb200_device_count(void) {
     return n;
 }
 
-int cgb200_create(cgb200_handle *out, int n, long long nnz, const void *aValues, const int *aPointers,
-                  const int *aCols, int dtype, int device) {
+}  // extern "C"
+
+// extra_cols / row_boundary: the row block of a shard has n_halo more columns than rows, and its halo-touching
+// rows are scheduled last (shard.cuh); a plain handle passes 0 / NULL.
+static int create_ctx(cgb200_handle *out, int n, long long nnz, const void *aValues, const int *aPointers,
+                      const int *aCols, int dtype, int device, int extra_cols, const unsigned char *row_boundary) {
     if (!out) return fail(CGB200_ERR_ARG, "out is NULL");
     *out = nullptr;
     if (n <= 0 || nnz < 0 || !aPointers || (nnz > 0 && (!aValues || !aCols)))
@@ -1158,6 +1422,8 @@ int cgb200_create(cgb200_handle *out, int n, long long nnz, const void *aValues,
     c->n = n;
     c->nnz = nnz;
     c->vsize = vs;
+    c->extra_cols = extra_cols;
+    if (row_boundary) c->row_boundary.assign(row_boundary, row_boundary + n);
     auto bail = [&](int rc) {
         cgb200_destroy(c);
         return rc;
@@ -1178,6 +1444,7 @@ int cgb200_create(cgb200_handle *out, int n, long long nnz, const void *aValues,
     c->own_stream = true;
     for (auto &e : c->ev) CUB(cudaEventCreate(&e));
     CUB(cudaMallocHost(&c->h_flag, sizeof(int)));
+    CUB(cudaMalloc(&c->d_flag, 64));
     // padded by 16 entries so 128-bit stream loads may run past the end
     CUB(cudaMalloc(&c->d_vals, ((size_t)nnz + 16) * vs));
     CUB(cudaMalloc(&c->d_cols, ((size_t)nnz + 16) * sizeof(int)));
@@ -1202,6 +1469,13 @@ int cgb200_create(cgb200_handle *out, int n, long long nnz, const void *aValues,
     return CGB200_OK;
 }
 
+extern "C" int cgb200_create(cgb200_handle *out, int n, long long nnz, const void *aValues, const int *aPointers,
+                             const int *aCols, int dtype, int device) {
+    return create_ctx(out, n, nnz, aValues, aPointers, aCols, dtype, device, 0, nullptr);
+}
+
+extern "C" {
+
 int cgb200_update(cgb200_handle c, const void *aValues, const int *aPointers, const int *aCols) {
     if (!c || !aValues || !aPointers || !aCols) return fail(CGB200_ERR_ARG, "NULL argument");
     DeviceGuard guard(c->device);
@@ -1216,7 +1490,8 @@ int cgb200_destroy(cgb200_handle c) {
     if (c->d_hist) cudaFree(c->d_hist);
     if (c->d_trace) cudaFree(c->d_trace);
     if (c->d_runs) cudaFree(c->d_runs);
-    for (void *b : {c->d_pat, c->d_pat_table, c->d_pat_build, c->d_plen, c->d_poff, c->d_pval, (void *)c->d_pat_chunks})
+    for (void *b : {c->d_pat, c->d_pat_table, c->d_pat_build, c->d_plen, c->d_poff, c->d_pval, (void *)c->d_pat_chunks,
+                    (void *)c->d_pspos, (void *)c->d_pat_mask, (void *)c->d_chunk_mask})
         if (b) cudaFree(b);
     if (c->d_tiles) cudaFree(c->d_tiles);
     if (c->d_long) cudaFree(c->d_long);
@@ -1225,6 +1500,7 @@ int cgb200_destroy(cgb200_handle c) {
     if (c->d_cols) cudaFree(c->d_cols);
     if (c->d_rowptr) cudaFree(c->d_rowptr);
     if (c->h_flag) cudaFreeHost(c->h_flag);
+    if (c->d_flag) cudaFree(c->d_flag);
     for (auto &e : c->ev)
         if (e) cudaEventDestroy(e);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
@@ -1261,6 +1537,9 @@ static int *option_slot(cgb200_handle c, const char *key) {
     if (!strcmp(key, "l2_keep")) return &c->l2_keep;
     if (!strcmp(key, "pattern")) return &c->pattern;
     if (!strcmp(key, "pattern_regs")) return &c->pattern_regs;
+    if (!strcmp(key, "cg2")) return &c->cg2;
+    if (!strcmp(key, "cg2_blocks")) return &c->cg2_blocks;
+    if (!strcmp(key, "cg2_ok")) return &c->cg2_ok;          // read-only: the dictionary's offsets fit the window plan
     if (!strcmp(key, "patterns")) return &c->npat;        // read-only: distinct row patterns found (0: CSR kernels in use)
     if (!strcmp(key, "spmm_schedule")) return &c->spmm_schedule;
     if (!strcmp(key, "pdl_early")) return &c->pdl_early;
@@ -1277,7 +1556,7 @@ int cgb200_set_option(cgb200_handle c, const char *key, long long value) {
         value != 16 && value != 32)
         return fail(CGB200_ERR_ARG, "lanes_per_row must be 0 or a power of two <= 32");
     if (!strcmp(key, "graph_chunk") && value < 1) return fail(CGB200_ERR_ARG, "graph_chunk must be >= 1");
-    if (!strcmp(key, "patterns")) return fail(CGB200_ERR_ARG, "'patterns' is read-only");
+    if (!strcmp(key, "patterns") || !strcmp(key, "cg2_ok")) return fail(CGB200_ERR_ARG, "'%s' is read-only", key);
     if (!strcmp(key, "trace")) {
         if (value < 0 || value > (1 << 20)) return fail(CGB200_ERR_ARG, "trace: 0 .. 2^20 iterations");
         DeviceGuard guard(c->device);
@@ -1325,6 +1604,7 @@ int cgb200_read_trace(cgb200_handle c, unsigned long long *out, int iterations) 
 int cgb200_spmv(cgb200_handle c, const void *x, void *y, int k, int layout) {
     if (!c || !x || !y || k < 1) return fail(CGB200_ERR_ARG, "bad spmv arguments");
     if (layout != CGB200_LAYOUT_CLCG && layout != CGB200_LAYOUT_ROWMAJOR) return fail(CGB200_ERR_ARG, "bad layout");
+    if (!c->matrix_ok) return fail(CGB200_ERR_ARG, "the handle holds no valid matrix (the last upload was rejected)");
     DeviceGuard guard(c->device);
     return DISPATCH(c, E::spmv_api(c, x, y, k, layout));
 }
@@ -1334,6 +1614,7 @@ int cgb200_solve(cgb200_handle c, const void *b, void *x, int k, int max_iterati
     if (!c || !b || !x || k < 1 || max_iterations < 0 || !(tol >= 0))
         return fail(CGB200_ERR_ARG, "bad solve arguments");
     if (layout != CGB200_LAYOUT_CLCG && layout != CGB200_LAYOUT_ROWMAJOR) return fail(CGB200_ERR_ARG, "bad layout");
+    if (!c->matrix_ok) return fail(CGB200_ERR_ARG, "the handle holds no valid matrix (the last upload was rejected)");
     DeviceGuard guard(c->device);
     return DISPATCH(c, E::solve_api(c, b, x, k, max_iterations, tol, iterations, relres, delta_hist, layout));
 }
@@ -1379,7 +1660,8 @@ int cgb200_info(cgb200_handle c, long long out[10]) {
 struct CacheSlot {
     std::mutex mu;
     cgb200_handle h = nullptr;
-    uint64_t hash = 0;
+    Hash128 hash;               // 128-bit content identity of (values, cols, row offsets) + sizes + dtype
+    bool hash_valid = false;
     int n = 0, dtype = -1;
     long long nnz = 0;
 };
@@ -1416,11 +1698,28 @@ static int legacy_cg(int dev, int dtype, int size, int nonZeros, const void *aVa
     CacheSlot &s = g_cache[dev];
     std::lock_guard<std::mutex> lock(s.mu);
     const size_t vs = dtype_size(dtype);
-    uint64_t hsh = 0;
-    if (mode == 1) {
-        hsh = hash_bytes(aValues, (size_t)nonZeros * vs, 1);
-        hsh = hash_bytes(aCols, (size_t)nonZeros * sizeof(int), hsh);
-        hsh = hash_bytes(aPointers, ((size_t)size + 1) * sizeof(int), hsh);
+    // The content identity is computed by the HOST: only for host-readable arrays.  A caller whose CSR arrays
+    // already live in device memory gets mode 2 (buffers kept, content copied device-to-device on every call).
+    int cache_mode = mode;
+    if (cache_mode == 1) {
+        DeviceGuard guard(dev);
+        for (const void *p : {aValues, (const void *)aCols, (const void *)aPointers}) {
+            cudaPointerAttributes at;
+            if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+                cudaGetLastError();
+                continue;                      // not known to CUDA: plain host memory
+            }
+            if (at.type == cudaMemoryTypeDevice) cache_mode = 2;
+        }
+    }
+    Hash128 hsh;
+    if (cache_mode == 1) {
+        Hash128 seed;
+        seed.a = (uint64_t)size * 0x9E3779B97F4A7C15ull + (uint64_t)nonZeros;
+        seed.b = (uint64_t)dtype + 0x632BE59BD9B4E019ull;
+        hsh = hash_bytes128(aValues, (size_t)nonZeros * vs, seed);
+        hsh = hash_bytes128(aCols, (size_t)nonZeros * sizeof(int), hsh);
+        hsh = hash_bytes128(aPointers, ((size_t)size + 1) * sizeof(int), hsh);
     }
     const bool same_shape = s.h && s.n == size && s.nnz == nonZeros && s.dtype == dtype;
     if (!same_shape) {
@@ -1430,7 +1729,7 @@ static int legacy_cg(int dev, int dtype, int size, int nonZeros, const void *aVa
         s.n = size;
         s.nnz = nonZeros;
         s.dtype = dtype;
-    } else if (mode != 1 || s.hash != hsh) {
+    } else if (cache_mode != 1 || !s.hash_valid || s.hash != hsh) {
         // same sizes, new content: refill the resident buffers, no allocation
         const int rc = cgb200_update(s.h, aValues, aPointers, aCols);
         if (rc < 0) {
@@ -1440,6 +1739,7 @@ static int legacy_cg(int dev, int dtype, int size, int nonZeros, const void *aVa
         }
     }
     s.hash = hsh;
+    s.hash_valid = cache_mode == 1;
     return cgb200_solve(s.h, b, x, nRHS, nIterations, 0.0, nullptr, nullptr, nullptr, CGB200_LAYOUT_CLCG);
 }
 

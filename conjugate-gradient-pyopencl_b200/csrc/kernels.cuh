@@ -61,6 +61,10 @@ struct PeerComm {
     int send_off[PEER_MAX + 1];                 // this rank's send list is segmented by destination rank
     int recv_from[PEER_MAX];                    // 1 if rank p sends halo entries to this rank
     unsigned int push_ticket[PEER_MAX];
+    // two-kernel iteration (cg2.cuh): rank p's direction buffers d0, d1 and residual buffers r0, r1, each
+    // [owned | halo]; the producing kernels store the entries rank p references straight into its halos
+    void *vec[4][PEER_MAX];
+    const int *send_idx;                        // this rank's owned rows to send, segmented by destination (send_off)
 };
 
 __device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long *p) {
@@ -96,6 +100,9 @@ template <typename T> __device__ __forceinline__ T peer_allreduce(PeerComm *pc, 
     const unsigned long long tag = (seq & 0xffffffffull) << 32;
     const int parity = (int)(seq & 1);
     if (t < pc->world) {
+        // release: whatever this GPU's blocks stored into peers' memory before they arrived at the kernel's ticket
+        // (halo entries, cg2.cuh) is ordered before the words below at system scope
+        __threadfence_system();
         double v[2] = {0.0, 0.0};
         Sc<T>::to_double2(local, v);
         PeerSlot *dst = pc->slots[t] + (size_t)parity * pc->world + pc->rank;
@@ -117,6 +124,7 @@ template <typename T> __device__ __forceinline__ T peer_allreduce(PeerComm *pc, 
             if (ok) break;
             if (++spins > (1ull << 31)) __trap();
         }
+        __threadfence_system();     // acquire: the peers' earlier stores into this GPU's halos are visible to what follows
         s_val[0][t] = __longlong_as_double((long long)(((w[1] & 0xffffffffull) << 32) | (w[0] & 0xffffffffull)));
         s_val[1][t] = NW == 4 ? __longlong_as_double((long long)(((w[3] & 0xffffffffull) << 32) | (w[2] & 0xffffffffull))) : 0.0;
     }
@@ -147,6 +155,23 @@ __device__ __forceinline__ void peer_wait_halo(const PeerComm *pc) {
         while (ld_acquire_sys_u64(pc->halo_flag[pc->rank] + p) < want)
             if (++spins > (1ull << 31)) __trap();
     }
+}
+
+// Stores value_of_row(i) for every owned row i that a peer references into that peer's halo of vector
+// `which` (PeerComm::vec).  Grid-strided over the send list, run by every block ahead of its own work so
+// that the NVLink transfer overlaps the rest of the kernel.
+template <typename T, typename F>
+__device__ __forceinline__ void peer_push_rows(const PeerComm *pc, int which, F value_of_row) {
+    const int total = pc->send_off[pc->world];
+    bool stored = false;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+        int p = 0;
+        while (e >= pc->send_off[p + 1]) p++;
+        T *dst = reinterpret_cast<T *>(pc->vec[which][p]) + pc->remote_off[p] + (e - pc->send_off[p]);
+        *dst = value_of_row(pc->send_idx[e]);
+        stored = true;
+    }
+    if (stored) __threadfence_system();     // ordered before this block's arrival at the kernel's ticket
 }
 
 // Programmatic dependent launch: the three kernels of an iteration are launched with the
@@ -191,6 +216,9 @@ template <typename T> struct CgScalars {
     int defer;          // row-block sharded solve: the dot products are only partial sums here; the
                         // bookkeeping runs in init_bookkeep_kernel / update_bookkeep_kernel after the
                         // all-reduce over the devices (dq is all-reduced in place)
+    T *alpha;           // [k] two-kernel iteration (cg2.cuh): the step of the latest update (x lags by it)
+    T *beta;            // [k] ... and the weight of the old direction in the next one
+    int cg2;            // 1: the solve runs the two-kernel iteration
 };
 
 template <typename T> __device__ __forceinline__ void trace_mark(const CgScalars<T> &sc, int it, int ev) {
@@ -207,6 +235,8 @@ template <typename T> __device__ __forceinline__ void init_bookkeep(const CgScal
     const bool live = (a0 > 0.0) && Sc<T>::finite(dl);
     sc.state[c] = live ? ST_ACTIVE : (a0 == 0.0 ? ST_CONVERGED : ST_BREAKDOWN);
     sc.iters[c] = 0;
+    sc.alpha[c] = Sc<T>::zero();
+    sc.beta[c] = Sc<T>::zero();
     if (sc.hist && sc.hist_cap > 0) Sc<T>::to_double2(dl, sc.hist + (size_t)c * (Sc<T>::cplx ? 2 : 1));
 }
 
@@ -1659,6 +1689,10 @@ init_kernel(size_t npacks, size_t nelem, int k, int kv, const T *b /* may alias 
     T acc[V];
 #pragma unroll
     for (int v = 0; v < V; v++) acc[v] = Sc<T>::zero();
+    // two-kernel iteration on a row-block shard (k = 1; b is then NOT aliased with d): the boundary entries of
+    // r0 go straight into the peers' halos of residual buffer 0, which the first dir_spmv reads
+    if (sc.cg2 && sc.peer && sc.peer->world > 1)
+        peer_push_rows<T>(sc.peer, 2, [&](int row) { return Sc<T>::sub(b[row], q[row]); });
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t p = (size_t)blockIdx.x * blockDim.x + t; p < npacks; p += stride) {
         const P bv = reinterpret_cast<const P *>(b)[p];

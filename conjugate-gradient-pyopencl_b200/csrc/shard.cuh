@@ -165,6 +165,9 @@ template <typename T> struct ShardEngine {
 
     static int iteration(cgb200_shard_ctx *sh, const typename E::VecGeom &g, const CgScalars<T> &sc) {
         cgb200_ctx *c = sh->m;
+        // two kernels, no exchange step: the producing kernels store the boundary entries of d and r straight
+        // into the peers' halos and the all-reduces at their tails order everything (cg2.cuh)
+        if (sc.cg2) return E::cg2_iteration(c, sc);
         TRY(exchange(sh, (T *)c->d, sh->p2p ? sc.n_active : nullptr));
         TRY(E::template spmv<true>(c, 1, (const T *)c->d, (T *)c->q, sc));          // q = A d, local d.q -> sc.dq
         TRY(allreduce(sh, sc.dq, 1));
@@ -188,6 +191,9 @@ template <typename T> struct ShardEngine {
         CgScalars<T> sc = E::scalars(c, 1, tol, 0);
         sc.defer = sh->p2p ? 0 : 1;                    // p2p: reduced and book-kept inside the kernels
         sc.peer = sh->p2p ? sh->d_peer : nullptr;
+        if (sh->world == 1) sc.defer = 0;
+        const bool cg2 = E::use_cg2(c, 1) && (sh->world == 1 || sh->p2p);
+        sc.cg2 = cg2 ? 1 : 0;
         if (sh->p2p && c->spmv_variant != 0 && c->spmv_variant != 6)
             return fail(CGB200_ERR_UNSUPPORTED, "peer-memory collectives need the default SpMV schedule (spmv_variant 0)");
         const typename E::VecGeom g = E::geom(c, 1);
@@ -202,9 +208,10 @@ template <typename T> struct ShardEngine {
         TRY(exchange(sh, (T *)c->d));
         TRY(E::template spmv<false>(c, 1, (const T *)c->d, (T *)c->q, sc));
         TRY(join_push(sh));
-        CU(cudaMemcpyAsync(c->d, b, bytes, cudaMemcpyDefault, c->stream));
-        if (g.V == 1) TRY(E::template launch_init<1>(c, 1, g, (const T *)c->d, (const T *)c->q, (T *)c->r, (T *)c->d, sc));
-        else TRY(E::template launch_init<E::VW>(c, 1, g, (const T *)c->d, (const T *)c->q, (T *)c->r, (T *)c->d, sc));
+        void *b_dev = cg2 ? c->r2 : c->d;             // (the two-kernel iteration's init must not alias b with d)
+        CU(cudaMemcpyAsync(b_dev, b, bytes, cudaMemcpyDefault, c->stream));
+        if (g.V == 1) TRY(E::template launch_init<1>(c, 1, g, (const T *)b_dev, (const T *)c->q, (T *)c->r, (T *)c->d, sc));
+        else TRY(E::template launch_init<E::VW>(c, 1, g, (const T *)b_dev, (const T *)c->q, (T *)c->r, (T *)c->d, sc));
         if (sc.defer) {
             TRY(allreduce(sh, sc.rr, 1));
             init_bookkeep_kernel<T><<<1, 32, 0, c->stream>>>(1, sc);
@@ -219,7 +226,7 @@ template <typename T> struct ShardEngine {
             // captured once per shard (the tolerance lives in device memory); re-captured only when the
             // chunk length or the stream changed
             const int gkey = sh->p2p ? -2 : -1;
-            if (!c->graph || c->graph_k != gkey || c->graph_chunk_built != chunk) {
+            if (!c->graph || c->graph_k != gkey || c->graph_chunk_built != chunk || c->graph_cg2 != (int)cg2) {
                 drop_graph(c);
                 cudaGraph_t gr = nullptr;
                 const long long before = c->launches;
@@ -235,6 +242,7 @@ template <typename T> struct ShardEngine {
                 ce = cudaGraphInstantiate(&c->graph, gr, 0);
                 cudaGraphDestroy(gr);
                 if (ce != cudaSuccess) return fail(CGB200_ERR_CUDA, "graph instantiate: %s", cudaGetErrorString(ce));
+                c->graph_cg2 = (int)cg2;
                 c->graph_k = gkey;             // marks a shard graph (never matches a plain solve's k)
                 c->graph_chunk_built = chunk;
                 DBG("rank %d: graph ready (%lld nodes)", sh->rank, c->graph_nodes);
@@ -260,6 +268,7 @@ template <typename T> struct ShardEngine {
                 if (*c->h_flag == 0) break;
             }
         }
+        if (cg2) TRY(E::launch_finish_x(c, sc));
         CU(cudaEventRecord(c->ev[3], c->stream));
         CU(cudaMemcpyAsync(x, c->x, bytes, cudaMemcpyDefault, c->stream));
         CU(cudaEventRecord(c->ev[4], c->stream));
@@ -322,22 +331,11 @@ int cgb200_shard_create(cgb200_shard *out, int rank, int world, const void *nccl
         cgb200_shard_destroy(sh);
         return rc;
     };
-    int rc = cgb200_create(&sh->m, n_owned, nnz, aValues, aPointers, aColsLocal, dtype, device);
+    // (the halo-touching rows, when given, are scheduled last: the exchange hides behind the interior rows)
+    int rc = create_ctx(&sh->m, n_owned, nnz, aValues, aPointers, aColsLocal, dtype, device, n_halo,
+                        world > 1 ? row_boundary : nullptr);
     if (rc < 0) return bail(rc);
-    sh->m->extra_cols = n_halo;
-    // Programmatic dependent launch stays off in the sharded iteration: with it the graph-launched tolerance solve
-    // stopped one iteration later than the plain-launched one (measured on 2 and 4 GPUs), i.e. some kernel of the
-    // halo / all-reduce chain saw a value one step early.  The single-GPU gain (<= 4 % on small systems) is not
-    // worth an ordering that is not understood.
-    if (world > 1 && !getenv("CGB200_PDL")) sh->m->pdl = 0;
-    if (row_boundary && world > 1) {
-        // rebuild the SpMV schedule with the halo-touching tiles last
-        sh->m->row_boundary.assign(row_boundary, row_boundary + n_owned);
-        sh->m->rowptr_hash = 0;
-        DeviceGuard g0(device);
-        rc = upload_matrix(sh->m, aValues, aPointers, aColsLocal);
-        if (rc < 0) return bail(rc);
-    }
+    if (world > 1 && !getenv("CGB200_PDL")) sh->m->pdl = 0;   // see DESIGN.md 6: no measured gain in shards
     DeviceGuard guard(device);
     sh->send_counts.assign(world, 0);
     sh->recv_counts.assign(world, 0);
@@ -402,8 +400,18 @@ int cgb200_shard_destroy(cgb200_shard sh) {
 
 cgb200_handle cgb200_shard_local(cgb200_shard sh) { return sh ? sh->m : nullptr; }
 
-int cgb200_shard_p2p_export(cgb200_shard sh, void *out128) {
-    if (!sh || !out128) return fail(CGB200_ERR_ARG, "NULL argument");
+// The blob a rank publishes: CUDA-IPC handle of its slot/flag buffer, CUDA-IPC handle of the ONE allocation that
+// holds its d, d2, r, r2 vectors ([owned | halo] each), and their byte offsets inside it.
+struct P2pBlob {
+    cudaIpcMemHandle_t buf, vecs;
+    long long off[4];
+    char pad[CGB200_P2P_BLOB_BYTES - 2 * 64 - 4 * 8];
+};
+static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+static_assert(sizeof(P2pBlob) == CGB200_P2P_BLOB_BYTES, "blob layout");
+
+int cgb200_shard_p2p_export(cgb200_shard sh, void *out_blob) {
+    if (!sh || !out_blob) return fail(CGB200_ERR_ARG, "NULL argument");
     if (sh->world > PEER_MAX) return fail(CGB200_ERR_UNSUPPORTED, "peer-memory collectives support up to %d ranks", PEER_MAX);
     cgb200_ctx *c = sh->m;
     DeviceGuard guard(c->device);
@@ -412,16 +420,17 @@ int cgb200_shard_p2p_export(cgb200_shard sh, void *out128) {
         CU(cudaMalloc(&sh->p2p_buf, P2P_BUF_BYTES));
         CU(cudaMemset(sh->p2p_buf, 0, P2P_BUF_BYTES));
     }
-    cudaIpcMemHandle_t h[2];
-    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
-    CU(cudaIpcGetMemHandle(&h[0], sh->p2p_buf));
-    CU(cudaIpcGetMemHandle(&h[1], c->d));
-    memcpy(out128, h, sizeof(h));
+    P2pBlob blob;
+    memset(&blob, 0, sizeof(blob));
+    CU(cudaIpcGetMemHandle(&blob.buf, sh->p2p_buf));
+    CU(cudaIpcGetMemHandle(&blob.vecs, c->vec_block));
+    for (int i = 0; i < 4; i++) blob.off[i] = (long long)c->vec_off[i];
+    memcpy(out_blob, &blob, sizeof(blob));
     return CGB200_OK;
 }
 
-int cgb200_shard_p2p_import(cgb200_shard sh, const void *all_handles, const long long *remote_off) {
-    if (!sh || !all_handles || !remote_off) return fail(CGB200_ERR_ARG, "NULL argument");
+int cgb200_shard_p2p_import(cgb200_shard sh, const void *all_blobs, const long long *remote_off) {
+    if (!sh || !all_blobs || !remote_off) return fail(CGB200_ERR_ARG, "NULL argument");
     if (!sh->p2p_buf) return fail(CGB200_ERR_ARG, "call cgb200_shard_p2p_export first");
     cgb200_ctx *c = sh->m;
     DeviceGuard guard(c->device);
@@ -429,19 +438,20 @@ int cgb200_shard_p2p_import(cgb200_shard sh, const void *all_handles, const long
     memset(&pc, 0, sizeof(pc));
     pc.rank = sh->rank;
     pc.world = sh->world;
-    const cudaIpcMemHandle_t *h = (const cudaIpcMemHandle_t *)all_handles;
+    const P2pBlob *blobs = (const P2pBlob *)all_blobs;
     sh->max_send = 0;
     for (int p = 0; p < sh->world; p++) {
-        void *buf = sh->p2p_buf, *dvec = c->d;
+        void *buf = sh->p2p_buf, *vecs = c->vec_block;
         if (p != sh->rank) {
-            CU(cudaIpcOpenMemHandle(&buf, h[2 * p], cudaIpcMemLazyEnablePeerAccess));
+            CU(cudaIpcOpenMemHandle(&buf, blobs[p].buf, cudaIpcMemLazyEnablePeerAccess));
             sh->opened.push_back(buf);
-            CU(cudaIpcOpenMemHandle(&dvec, h[2 * p + 1], cudaIpcMemLazyEnablePeerAccess));
-            sh->opened.push_back(dvec);
+            CU(cudaIpcOpenMemHandle(&vecs, blobs[p].vecs, cudaIpcMemLazyEnablePeerAccess));
+            sh->opened.push_back(vecs);
         }
         pc.slots[p] = (PeerSlot *)buf;
         pc.halo_flag[p] = (unsigned long long *)((char *)buf + P2P_SLOTS_BYTES);
-        pc.d_peer[p] = dvec;
+        for (int i = 0; i < 4; i++) pc.vec[i][p] = (char *)vecs + blobs[p].off[i];
+        pc.d_peer[p] = pc.vec[0][p];
         pc.remote_off[p] = remote_off[p];
         pc.send_off[p] = sh->send_off[p];
         pc.recv_from[p] = sh->recv_counts[p] > 0;
@@ -449,6 +459,7 @@ int cgb200_shard_p2p_import(cgb200_shard sh, const void *all_handles, const long
     }
     pc.send_off[sh->world] = sh->send_total;
     for (int p = sh->world; p < PEER_MAX; p++) pc.send_off[p + 1] = sh->send_total;
+    pc.send_idx = sh->d_send_idx;
     if (!sh->d_peer) CU(cudaMalloc((void **)&sh->d_peer, sizeof(PeerComm)));
     if (!sh->side) {
         CU(cudaStreamCreateWithFlags(&sh->side, cudaStreamNonBlocking));

@@ -134,7 +134,7 @@ class Matrix:
         columns TRACE_EVENTS, 0 = not recorded."""
         return read_trace(self._h, iterations)
 
-    KERNELS = {"spmv_dot": 0, "update_xr": 1, "update_d": 2, "spmv": 3}
+    KERNELS = {"spmv_dot": 0, "update_xr": 1, "update_d": 2, "spmv": 3, "dir_spmv": 4, "update_r": 5}
 
     def time_kernel(self, which, k=1, reps=50):
         """Mean milliseconds of one kernel of the CG loop over `reps` back-to-back launches (CUDA events)."""

@@ -13,8 +13,8 @@ Two ways the path shards:
               and all-reduces the two dot scalars.
 
 The planning is plain numpy + torch.distributed object collectives, so it runs (and is
-tested) on CPU with the gloo backend; `reference_sharded_cg` is the same algorithm in numpy
-over any backend, used by the tests as the oracle of the communication pattern.
+tested) on CPU with the gloo backend; tests/sharded_numpy.py runs the same communication
+pattern in numpy over any backend as the oracle of the plan (test code, not product).
 """
 import ctypes
 
@@ -216,7 +216,7 @@ class ShardedMatrix:
         """CUDA-IPC handles of every rank's exchange buffer and direction vector, all-gathered; afterwards the
         halo and the dot-product all-reduces go through NVLink-mapped pointers inside the kernels."""
         plan, L = self.plan, _lib.lib()
-        mine = np.zeros(128, dtype=np.uint8)
+        mine = np.zeros(_lib.P2P_BLOB_BYTES, dtype=np.uint8)
         _lib.check(L.cgb200_shard_p2p_export(self._h, _lib.ptr(mine)))
         recv_off = np.concatenate([[0], np.cumsum(plan.recv_counts)[:-1]]).astype(np.int64)
         box = [None] * plan.world
@@ -239,7 +239,7 @@ class ShardedMatrix:
 
     def time_kernel(self, which, reps=50):
         """Mean ms of one kernel of the loop on the local row block (see cgb200_time_kernel)."""
-        kinds = {"spmv_dot": 0, "update_xr": 1, "update_d": 2, "spmv": 3}
+        kinds = {"spmv_dot": 0, "update_xr": 1, "update_d": 2, "spmv": 3, "dir_spmv": 4, "update_r": 5}
         ms = ctypes.c_double()
         h = ctypes.c_void_p(_lib.lib().cgb200_shard_local(self._h))
         _lib.check(_lib.lib().cgb200_time_kernel(h, kinds[which], 1, int(reps), ctypes.byref(ms)))
@@ -285,59 +285,3 @@ class ShardedMatrix:
         _lib.check(_lib.lib().cgb200_shard_last_timing(self._h, ms))
         return x_owned, {"flags": rc, "iterations": its.value, "relres": rel.value,
                          "timing_ms": dict(zip(("h2d", "init", "iterations", "d2h"), list(ms)))}
-
-
-# ----------------------------------------------------------------------------------------
-# the same algorithm in numpy over torch.distributed (any backend): oracle of the plan
-# ----------------------------------------------------------------------------------------
-def halo_exchange_numpy(plan, v_owned, dist):
-    """[v_owned | halo] for this rank: the communication pattern of ShardEngine::exchange."""
-    import torch
-    out = np.empty(plan.n_owned + plan.n_halo, dtype=v_owned.dtype)
-    out[:plan.n_owned] = v_owned
-    sendbuf = v_owned[plan.send_idx]
-    reqs, recv_t, so, ro = [], [], 0, plan.n_owned
-    # bytes are bytes: ship every dtype as float32 / float64 words
-    view = (lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.float64 if a.dtype.itemsize % 8 == 0 else np.float32)))
-    for p in range(plan.world):
-        if plan.send_counts[p]:
-            reqs.append(dist.isend(view(sendbuf[so:so + plan.send_counts[p]]), dst=p))
-            so += plan.send_counts[p]
-        if plan.recv_counts[p]:
-            buf = np.empty(plan.recv_counts[p], dtype=v_owned.dtype)
-            t = view(buf)
-            recv_t.append((ro, buf, t))
-            reqs.append(dist.irecv(t, src=p))
-            ro += plan.recv_counts[p]
-    for r in reqs:
-        r.wait()
-    for ro, buf, t in recv_t:
-        out[ro:ro + buf.size] = t.numpy().view(v_owned.dtype)
-    return out
-
-
-def reference_sharded_cg(plan, b_owned, x_owned, iters, dist):
-    """Row-block CG in numpy with the plan's halo exchange and two all-reduces per iteration:
-    the recurrence of clcg.c:253-419 / helmFE_var.py:507-544 distributed by rows."""
-    import scipy.sparse as sp
-    import torch
-    A = sp.csr_matrix((plan.data, plan.cols_local, plan.indptr), shape=(plan.n_owned, plan.n_owned + plan.n_halo))
-
-    def allsum(z):
-        z = np.asarray([z], dtype=np.complex128 if np.iscomplexobj(z) else np.float64)
-        t = torch.from_numpy(z.view(np.float64))
-        dist.all_reduce(t)
-        return z[0]
-
-    x = x_owned.copy()
-    r = b_owned - A @ halo_exchange_numpy(plan, x, dist)
-    d = r.copy()
-    delta_new = allsum(np.dot(r, r))
-    for _ in range(iters):
-        q = A @ halo_exchange_numpy(plan, d, dist)
-        alpha = delta_new / allsum(np.dot(d, q))
-        x = x + alpha * d
-        r = r - alpha * q
-        delta_old, delta_new = delta_new, allsum(np.dot(r, r))
-        d = r + (delta_new / delta_old) * d
-    return x

@@ -101,6 +101,10 @@ CGB200_API int cgb200_set_stream(cgb200_handle h, void *cuda_stream);
  *   "pattern"        1 (default): k = 1 runs from the row-pattern dictionary when the matrix has <= 4096 distinct rows
  *                    ("patterns", read-only, tells how many were found; 0 = CSR kernels in use)
  *   "pattern_regs"   0 (default) | 1: EXPERIMENT, not yet run on hardware -- the last pattern kept in registers
+ *   "cg2"            1 (default): k = 1 on a matrix with a row-pattern dictionary whose column offsets fit a window
+ *                    plan runs the TWO-kernel iteration (csrc/cg2.cuh: direction update folded into the SpMV's
+ *                    gather, x lagging one update, 9 vector passes instead of 11); "cg2_ok" (read-only) tells
+ *                    whether the matrix qualifies; "cg2_blocks" caps the blocks per SM of its first kernel
  *   "spmm_schedule"  0 (default) | 1: k > 1 on a matrix with grid structure (few fixed column offsets) visits rows
  *                    patch by patch for L1 reuse of the gathered rows (spmm_sched_kernel)
  *   "trace"          n > 0: the loop kernels stamp %globaltimer into an 8-slot record per iteration for the
@@ -135,7 +139,8 @@ CGB200_API int cgb200_last_timing(cgb200_handle h, double ms[4]);
 /* Measurement hook: launches ONE kernel of the CG loop `reps` times back to back on the
  * handle's stream (after 3 warm-up launches) between two CUDA events and returns the mean
  * duration.  which: 0 spmv fused with d.q (spmv.cl + vdot.cl), 1 x/r update fused with r.r
- * (axpy.cl x2 + vdot.cl), 2 direction update (aypx.cl), 3 plain spmv.  Call it after a
+ * (axpy.cl x2 + vdot.cl), 2 direction update (aypx.cl), 3 plain spmv, 4 / 5 the two kernels of the
+ * two-kernel iteration (direction + spmv + x update + d.q; residual update + r.r).  Call it after a
  * cgb200_solve() with the same k; the next solve re-initialises the state it disturbs. */
 CGB200_API int cgb200_time_kernel(cgb200_handle h, int which, int k, int reps, double *ms_avg);
 
@@ -202,12 +207,14 @@ CGB200_API int cgb200_shard_set_option(cgb200_shard sh, const char *key, long lo
 /* Peer-memory collectives (optional, <= 8 ranks of one NVLink domain).  With them the halo entries are
  * written straight into the peers' vectors and the two dot products are all-reduced by the compute kernels
  * themselves through CUDA-IPC mapped pointers: no NCCL launch inside the iteration.
- *   export: this rank's two 64-byte IPC handles (exchange buffer, direction vector) -> out128
- *   import: all ranks' handles (world x 128 bytes, rank order) and, per peer p, the element offset in
- *           p's direction vector where this rank's entries land (n_owned_p + p's receive offset for us)
+ *   export: this rank's blob of CGB200_P2P_BLOB_BYTES bytes: two 64-byte CUDA-IPC handles (exchange buffer;
+ *           the allocation holding the direction and residual buffers) and the vectors' byte offsets in it
+ *   import: all ranks' blobs (world x CGB200_P2P_BLOB_BYTES bytes, rank order) and, per peer p, the element
+ *           offset in p's vectors where this rank's entries land (n_owned_p + p's receive offset for us)
  *   enable: switch between peer memory (1) and NCCL (0) afterwards */
-CGB200_API int cgb200_shard_p2p_export(cgb200_shard sh, void *out128);
-CGB200_API int cgb200_shard_p2p_import(cgb200_shard sh, const void *all_handles, const long long *remote_off);
+#define CGB200_P2P_BLOB_BYTES 256
+CGB200_API int cgb200_shard_p2p_export(cgb200_shard sh, void *out_blob);
+CGB200_API int cgb200_shard_p2p_import(cgb200_shard sh, const void *all_blobs, const long long *remote_off);
 CGB200_API int cgb200_shard_p2p_enable(cgb200_shard sh, int on);
 
 /* Collective: every rank calls it with its slice of b and x (host or device pointers).

@@ -15,6 +15,7 @@ REFERENCE = "/root/reference"
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
     config.addinivalue_line("markers", "reference: needs /root/reference (build container only)")
+    config.addinivalue_line("markers", "fullsize: a BASELINE config at its full size (tens of seconds of host-side set-up each)")
 
 
 def _has_gpu():

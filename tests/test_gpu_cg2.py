@@ -1,0 +1,373 @@
+"""Round-2 GPU tests: the two-kernel iteration (csrc/cg2.cuh), the upload-time checks, the row-block
+sharded path through `cgb200_shard_*` (one process per GPU under torchrun when the box has several),
+and one parity test per BASELINE config AT SIZE (marked `fullsize`: they generate 27 M-row systems).
+
+Everything calls through the C ABI (ctypes) and compares with the CPU oracle (oracle/cpu_ref.c).
+"""
+import ctypes
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from test_gpu_parity import DT, ROOT, check_parity, oracle_pair, rand, rel, system
+
+pytestmark = pytest.mark.gpu
+
+
+def _grid_system(kind, dt):
+    import cg_b200.problems as P
+    if kind == "lap3d":
+        A = P.laplace3d(23).astype(dt)                 # 12167 rows: 11 full chunks of 1024 + a ragged one
+        return A, np.ones(A.shape[0], dtype=dt)
+    if kind == "lap3d_slab":
+        A = P.laplace3d(40, nz=5).astype(dt)           # plane offset (1600) larger than a chunk: three windows
+        return A, np.ones(A.shape[0], dtype=dt)
+    return system(kind, 70, dt)
+
+
+# ---------------------------------------------------------------------------------------
+# two-kernel iteration
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dname", ["f32", "f64", "c64", "c128"])
+@pytest.mark.parametrize("kind", ["poisson", "helm", "lap3d", "lap3d_slab"])
+def test_two_kernel_iteration_matches_three_kernel_path_and_oracle(gpu, cpu_ref, dname, kind):
+    """dir_spmv + update_r (direction folded into the gather, x lagging one update) computes what
+    spmv_dot + update_xr + update_d computes: the same FMAs, only the dot-product association differs."""
+    dt = DT[dname]
+    if kind == "helm" and dname in ("f32", "f64"):
+        pytest.skip("the real twin of the Helmholtz system has no repeated rows: no pattern dictionary")
+    A, b = _grid_system(kind, dt)
+    n = A.shape[0]
+    rng = np.random.default_rng(11)
+    x0 = (0.1 * rand(rng, n, dt)).astype(dt)
+    its = 48
+    with gpu.Matrix.from_scipy(A) as M:
+        M.set_option("solver", 1)                      # not the single cooperative launch
+        assert M.get_option("cg2_ok") == 1
+        x2, i2 = M.solve(b, x=x0.copy(), max_iterations=its, history=True)
+        l2 = M.info()["launches"]
+        M.set_option("use_graph", 0)
+        x2p, i2p = M.solve(b, x=x0.copy(), max_iterations=its, history=True)
+        M.set_option("use_graph", 1)
+        M.set_option("cg2", 0)
+        x3, i3 = M.solve(b, x=x0.copy(), max_iterations=its, history=True)
+        # tolerance mode: same stopping iteration, and the lagging x update is applied on exit
+        M.set_option("cg2", 1)
+        tol = 1e-4 if dname in ("f32", "c64") else 1e-9
+        xt2, it2 = M.solve(b, max_iterations=2000, tol=tol)
+        M.set_option("cg2", 0)
+        xt3, it3 = M.solve(b, max_iterations=2000, tol=tol)
+    assert l2 > 0
+    assert np.array_equal(x2, x2p) and np.array_equal(i2.delta_hist, i2p.delta_hist)     # graphs change nothing
+    single = dname in ("f32", "c64")
+    # identical arithmetic up to the association of two sums per iteration
+    assert rel(i2.delta_hist[:20], i3.delta_hist[:20]) < (1e-4 if single else 1e-12)
+    ref, w = oracle_pair(cpu_ref, dname, A.data, A.indptr, A.indices, b, x0=x0, iters=its)
+    check_parity(x2, ref, w, dname)
+    check_parity(x3, ref, w, dname)
+    if not single:
+        assert rel(x2, x3) < 1e-11
+        assert abs(int(it2.iterations[0]) - int(it3.iterations[0])) <= 1
+        assert rel(xt2, xt3) < 1e-8
+    else:
+        assert abs(int(it2.iterations[0]) - int(it3.iterations[0])) <= max(2, int(0.02 * it3.iterations[0]))
+
+
+@pytest.mark.parametrize("n", [37, 255, 1023, 1024, 1025, 2049])
+def test_two_kernel_iteration_small_and_ragged_sizes(gpu, cpu_ref, n):
+    # 1-D Laplacian + shift: 3 patterns, sizes around the chunk length
+    A = sp.diags([-1.0, 2.5, -1.0], [-1, 0, 1], shape=(n, n), format="csr")
+    b = np.linspace(1.0, 2.0, n)
+    with gpu.Matrix.from_scipy(A) as M:
+        M.set_option("solver", 1)
+        assert M.get_option("cg2_ok") == 1
+        x, info = M.solve(b, max_iterations=30)
+    ref, _, _ = cpu_ref.cg(A.data, A.indptr, A.indices, b, iters=30)
+    assert rel(x, ref) < 1e-10
+
+
+def test_two_kernel_iteration_zero_iterations_and_breakdown(gpu):
+    import cg_b200.problems as P
+    A = P.poisson2d(40)
+    n = A.shape[0]
+    x0 = np.arange(n, dtype=np.float64)
+    with gpu.Matrix.from_scipy(A) as M:
+        M.set_option("solver", 1)
+        x, _ = M.solve(np.ones(n), x=x0.copy(), max_iterations=0)
+        assert np.array_equal(x, x0)
+        # b = 0, x0 = 0: delta_0 = 0 -> converged at once, x stays 0 (no NaN from 0/0)
+        x, info = M.solve(np.zeros(n), max_iterations=20)
+        assert np.all(x == 0) and info.iterations[0] == 0
+
+
+def test_graph_is_dropped_when_an_update_changes_the_pattern_dictionary(gpu, cpu_ref):
+    """a captured graph has the SpMV kernel choice, the pattern count and the dictionary pointers
+    baked in; cgb200_update with the same row offsets rebuilt the dictionary without dropping the graph."""
+    import cg_b200.problems as P
+    A = P.poisson2d(72).astype(np.float64)
+    n = A.shape[0]
+    rng = np.random.default_rng(3)
+    b = rng.standard_normal(n)
+    # same sparsity, (1) 9 patterns, (2) every row different -> no dictionary, (3) 18 patterns (two value sets)
+    R = A.copy()
+    R.data = R.data * (1.0 + 0.05 * rng.random(R.nnz))
+    R = ((R + R.T) * 0.5).tocsr()
+    R.sort_indices()
+    assert np.array_equal(R.indptr, A.indptr) and np.array_equal(R.indices, A.indices)
+    H = A.copy()
+    half = H.indptr[n // 2]
+    H.data[half:] *= 2.0
+    H = ((H + H.T) * 0.5).tocsr()
+    H.sort_indices()
+    for cg2 in (1, 0):
+        with gpu.Matrix.from_scipy(A) as M:
+            M.set_option("solver", 1)
+            M.set_option("cg2", cg2)
+            for mat in (A, R, A, H, A):
+                M.update(mat.data, mat.indptr, mat.indices)
+                x, _ = M.solve(b, max_iterations=32)           # >= graph_chunk: replays a graph if one is cached
+                ref, _, _ = cpu_ref.cg(mat.data, mat.indptr, mat.indices, b, iters=32)
+                assert rel(x, ref) < 1e-10, (cg2, M.get_option("patterns"))
+
+
+def test_bad_column_index_is_an_argument_error_not_a_device_fault(gpu, cpu_ref):
+    import cg_b200.problems as P
+    A = P.poisson2d(32).astype(np.float64)
+    n = A.shape[0]
+    bad = A.indices.copy()
+    bad[17] = n + 5
+    L = gpu._lib.lib()
+    h = ctypes.c_void_p()
+    rc = L.cgb200_create(ctypes.byref(h), n, A.nnz, gpu._lib.ptr(A.data), gpu._lib.ptr(A.indptr), gpu._lib.ptr(bad), 1, 0)
+    assert rc == -1 and b"aCols" in L.cgb200_last_error()
+    neg = A.indices.copy()
+    neg[3] = -1
+    with gpu.Matrix.from_scipy(A) as M:
+        b = np.ones(n)
+        x_ok, _ = M.solve(b, max_iterations=20)
+        with pytest.raises(gpu._lib.CgError):
+            M.update(A.data, A.indptr, neg)
+        with pytest.raises(gpu._lib.CgError):                 # the handle refuses to work with the rejected matrix
+            M.solve(b, max_iterations=20)
+        badptr = A.indptr.copy()
+        badptr[5], badptr[6] = badptr[6], badptr[5]
+        with pytest.raises(gpu._lib.CgError):
+            M.update(A.data, badptr, A.indices)
+        M.update(A.data, A.indptr, A.indices)                 # a good upload heals it
+        x, _ = M.solve(b, max_iterations=20)
+        assert np.array_equal(x, x_ok)
+    # and the device is still alive
+    with gpu.Matrix.from_scipy(A) as M:
+        assert rel(M.spmv(np.ones(n)), A @ np.ones(n)) < 1e-14
+
+
+def test_cgb200_cg_with_device_resident_csr(gpu, cpu_ref):
+    """include/cgb200.h: every pointer may be a host or a device pointer -- also for the cached cg() path
+    (the content hash read device pointers on the host)."""
+    import torch
+    import cg_b200.problems as P
+    A = P.poisson2d(48).astype(np.float64)
+    n = A.shape[0]
+    b = np.ones(n)
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    vals, ptr, cols, bd, xd = dev(A.data), dev(A.indptr), dev(A.indices), dev(b), dev(np.zeros(n))
+    L = gpu._lib.lib()
+    for _ in range(2):
+        xd.zero_()
+        rc = L.cgb200_cg(0, 1, n, A.nnz, gpu._lib.ptr(vals), gpu._lib.ptr(bd), gpu._lib.ptr(ptr), gpu._lib.ptr(cols),
+                         gpu._lib.ptr(xd), 1, 25)
+        assert rc >= 0, L.cgb200_last_error()
+        torch.cuda.synchronize()
+        ref, _, _ = cpu_ref.cg(A.data, A.indptr, A.indices, b, iters=25)
+        assert rel(xd.cpu().numpy(), ref) < 1e-10
+    L.cgb200_clear_cache()
+
+
+def test_clcg_layout_spmv_with_pinned_host_buffers_is_complete_on_return(gpu):
+    import torch
+    import cg_b200.problems as P
+    A = P.laplace3d(30).astype(np.float64)
+    n, k = A.shape[0], 4
+    X = torch.from_numpy(np.random.default_rng(0).standard_normal(n * k)).pin_memory()
+    Y = torch.zeros(n * k, dtype=torch.float64).pin_memory()
+    with gpu.Matrix.from_scipy(A) as M:
+        L = gpu._lib.lib()
+        for _ in range(3):
+            Y.zero_()
+            gpu._lib.check(L.cgb200_spmv(M._h, gpu._lib.ptr(X), gpu._lib.ptr(Y), k, 0))
+            y = Y.numpy().copy()                                # no synchronisation by the caller
+            ref = np.concatenate([A @ X.numpy()[r * n:(r + 1) * n] for r in range(k)])
+            assert rel(y, ref) < 1e-14
+
+
+# ---------------------------------------------------------------------------------------
+# row-block shards
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", ["lap3d", "helm", "powerlaw"])
+def test_shard_entry_points_with_one_rank(gpu, cpu_ref, kind):
+    """cgb200_shard_* with world = 1 (no peer, no NCCL): the code path every rank of a sharded run takes for
+    its local rows, so that a one-GPU box covers it."""
+    import cg_b200.problems as P
+    from cg_b200 import sharded
+    if kind == "lap3d":
+        A, b = P.laplace3d(22), np.ones(22 ** 3)
+    elif kind == "helm":
+        A, b = P.helmholtz_fe(48), P.rhs_a(48, 12.0)
+    else:
+        A = P.powerlaw_spd(n=9000, nnz_target=120000, max_row=2500)
+        b = A @ np.linspace(-1, 1, A.shape[0])
+    bounds = np.array([0, A.shape[0]], dtype=np.int64)
+    plan = sharded.plan_row_block(A.indptr, A.indices, A.data, bounds, 0, exchange=lambda o: [o])
+    assert plan.n_halo == 0
+    M = sharded.ShardedMatrix(plan, device=0)
+    try:
+        x, info = M.solve(b.astype(A.dtype), max_iterations=40)
+        ref, _, _ = cpu_ref.cg(A.data, A.indptr, A.indices, b.astype(A.dtype), iters=40)
+        assert rel(x, ref) < 1e-10
+        xt, it = M.solve(b.astype(A.dtype), max_iterations=3000, tol=1e-9)
+        _, its_ref, _ = cpu_ref.cg(A.data, A.indptr, A.indices, b.astype(A.dtype), iters=3000, tol=1e-9)
+        assert abs(it["iterations"] - int(its_ref[0])) <= 1
+    finally:
+        M.close()
+
+
+def _torchrun(nproc, script, *args, timeout=600):
+    import socket
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
+           "--master-addr", "127.0.0.1", "--master-port", str(port), script, *map(str, args)]
+    return subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=timeout)
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_row_block_sharded_cg_parity_over_nvlink(gpu, world):
+    """One process per GPU (torchrun): halo entries stored into the peers' vectors by the producing kernels, both dot
+    products all-reduced inside the kernels.  tools/shard_check.py asserts, on every rank: two-kernel vs three-kernel
+    iteration, peer memory vs NCCL, graphs vs plain launches, 60 iterations vs the CPU oracle (1e-10) and the
+    iteration count to 1e-9 (+-1) on a Laplacian, a complex Helmholtz and a power-law system."""
+    if gpu.device_count() < world:
+        pytest.skip(f"{world} GPUs needed, {gpu.device_count()} visible")
+    r = _torchrun(world, os.path.join("tools", "shard_check.py"), "--parity-only")
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-6000:]
+    out = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    assert out["world"] == world
+    for name in ("lap3d24", "helm64_c128", "powerlaw"):
+        assert out[name]["err60"] < 1e-10 and abs(out[name]["iters"] - out[name]["iters_oracle"]) <= 1, out[name]
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_rhs_split_over_several_gpus(gpu, cpu_ref, world):
+    """The reference's own multi-GPU mode (p_h-PY_C-CL-multi-GPU.py:2123-2181): right-hand sides split over the
+    devices, one host thread per device, matrix replicated, no communication."""
+    if gpu.device_count() < world:
+        pytest.skip(f"{world} GPUs needed, {gpu.device_count()} visible")
+    import cg_b200.problems as P
+    from cg_b200 import sharded
+    A = P.helmholtz_fe(40).astype(np.complex64)
+    n, k, its = A.shape[0], 7, 50
+    b = P.rhs_a(40, 12.0)
+    B = np.concatenate([b * (r + 1) for r in range(k)]).astype(np.complex64)
+    x = np.zeros(n * k, np.complex64)
+    sharded.cg_rhs_split(n, A.nnz, A.data, B, A.indptr, A.indices, x, k, its, devices=list(range(world)))
+    ref, w = oracle_pair(cpu_ref, "c64", A.data, A.indptr, A.indices, B, k=k, iters=its)
+    check_parity(x, ref, w, "c64")
+    gpu._lib.lib().cgb200_clear_cache()
+
+
+# ---------------------------------------------------------------------------------------
+# the BASELINE configs AT SIZE: a prefix of the iteration against the oracle, then size-independent properties
+# ---------------------------------------------------------------------------------------
+fullsize = pytest.mark.fullsize
+
+
+def _true_relres(A, x, b):
+    return float(np.linalg.norm(b - A @ x) / np.linalg.norm(b))
+
+
+@fullsize
+def test_config2_helmholtz_1024_at_size(gpu, cpu_ref):
+    import cg_b200.problems as P
+    A = P.helmholtz_fe(1024)
+    b = P.rhs_a(1024, 12.0)
+    its = 20
+    ref, _, _ = cpu_ref.cg(A.data, A.indptr, A.indices, b, iters=its)
+    ref32, w32 = oracle_pair(cpu_ref, "c64", A.data.astype(np.complex64), A.indptr, A.indices, b.astype(np.complex64), iters=its)
+    with gpu.Matrix.from_scipy(A) as M:
+        for cg2 in (1, 0):
+            M.set_option("cg2", cg2)
+            x, info = M.solve(b, max_iterations=its, history=True)
+            assert rel(x, ref) < 1e-10
+        x600, i600 = M.solve(b, max_iterations=600)
+    # size-independent property: the recursive residual the engine reports is the true one
+    assert abs(_true_relres(A, x600, b) - i600.relres[0]) < 1e-8 * max(1.0, i600.relres[0])
+    with gpu.Matrix.from_scipy(A.astype(np.complex64)) as M:
+        x, _ = M.solve(b.astype(np.complex64), max_iterations=its)
+    check_parity(x, ref32, w32, "c64")
+
+
+@fullsize
+def test_config3_laplace_128_cubed_32_rhs_at_size(gpu, cpu_ref):
+    import cg_b200.problems as P
+    A = P.laplace3d(128)
+    n, k, its = A.shape[0], 32, 10
+    B = np.concatenate([np.random.default_rng(1000 + r).uniform(-1.0, 1.0, n) for r in range(k)])
+    ref, _, _ = cpu_ref.cg(A.data, A.indptr, A.indices, B, k=k, iters=its)
+    with gpu.Matrix.from_scipy(A) as M:
+        X, info = M.solve(B, k=k, max_iterations=its)
+        assert rel(X, ref) < 1e-10
+        # linearity of the SpMM in the right-hand sides: A (X1 + 2 X2) = A X1 + 2 A X2, column by column
+        Y = M.spmv(B, k=k)
+        Y2 = M.spmv(B[:n] + 2.0 * B[n:2 * n])
+    assert rel(Y2, Y[:n] + 2.0 * Y[n:2 * n]) < 1e-13
+
+
+@fullsize
+def test_config4_laplace_300_cubed_at_size(gpu, cpu_ref):
+    import cg_b200.problems as P
+    A = P.laplace3d(300)
+    n, its = A.shape[0], 12
+    b = np.ones(n)
+    ref, _, _ = cpu_ref.cg(A.data, A.indptr, A.indices, b, iters=its)
+    with gpu.Matrix.from_scipy(A) as M:
+        assert M.get_option("patterns") == 27
+        hist = {}
+        for name, opts in (("two-kernel", {"cg2": 1}), ("three-kernel", {"cg2": 0}), ("csr", {"cg2": 0, "pattern": 0})):
+            for key, v in opts.items():
+                M.set_option(key, v)
+            x, info = M.solve(b, max_iterations=its, history=True)
+            assert rel(x, ref) < 1e-10, name
+            hist[name] = info.delta_hist[:, 0]
+        assert rel(hist["two-kernel"], hist["three-kernel"]) < 1e-12
+        assert rel(hist["csr"], hist["three-kernel"]) < 1e-12
+        M.set_option("cg2", 1)
+        M.set_option("pattern", 1)
+        x, info = M.solve(b, max_iterations=256)
+        # symmetry of the problem (b = ones on a cube): the solution is invariant under reversing the numbering
+        assert rel(x[::-1], x) < 1e-9
+        assert abs(_true_relres(A, x, b) - info.relres[0]) < 1e-9
+
+
+@fullsize
+def test_config5_power_law_5m_rows_at_size(gpu, cpu_ref):
+    import cg_b200.problems as P
+    A = P.powerlaw_spd()
+    n, its = A.shape[0], 12
+    assert A.nnz > 45_000_000
+    xs = np.random.default_rng(7).uniform(-1.0, 1.0, n)
+    b = A @ xs
+    ref, _, _ = cpu_ref.cg(A.data, A.indptr, A.indices, b, iters=its)
+    with gpu.Matrix.from_scipy(A) as M:
+        x, info = M.solve(b, max_iterations=its)
+        assert rel(x, ref) < 1e-10
+        y = M.spmv(xs)
+        assert rel(y, b) < 1e-13                                # includes the chunked long rows (max row ~ 2e5 entries)
+        x, info = M.solve(b, max_iterations=200, tol=1e-12)
+    assert rel(x, xs) < 1e-9                                    # known solution

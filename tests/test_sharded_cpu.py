@@ -40,10 +40,12 @@ def _worker(rank, world, port, kind, by, out_dir):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
     import torch.distributed as dist
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         from cg_b200 import sharded
+        import sharded_numpy
         import np_cg
         A, b = _matrix(kind)
         n = A.shape[0]
@@ -62,7 +64,7 @@ def _worker(rank, world, port, kind, by, out_dir):
         assert plan.recv_counts.sum() == plan.n_halo and plan.send_counts.sum() == plan.send_idx.size
         # halo exchange delivers exactly the referenced remote entries
         v = (np.arange(n) * 1.5 + 0.25).astype(A.dtype)
-        loc = sharded.halo_exchange_numpy(plan, v[rb:re], dist)
+        loc = sharded_numpy.halo_exchange_numpy(plan, v[rb:re], dist)
         assert np.array_equal(loc[:plan.n_owned], v[rb:re])
         assert np.array_equal(loc[plan.n_owned:], v[plan.halo_globals])
         # local SpMV == rows of the global one
@@ -70,7 +72,7 @@ def _worker(rank, world, port, kind, by, out_dir):
         assert np.allclose(Al @ loc, (A @ v)[rb:re], rtol=1e-13, atol=1e-13)
         # sharded CG == the global oracle
         its = 25
-        x = sharded.reference_sharded_cg(plan, b[rb:re].astype(A.dtype), np.zeros(re - rb, A.dtype), its, dist)
+        x = sharded_numpy.reference_sharded_cg(plan, b[rb:re].astype(A.dtype), np.zeros(re - rb, A.dtype), its, dist)
         ref = np_cg.cg(A, b.astype(A.dtype), x=np.zeros(n, A.dtype), maxit=its)
         err = np.linalg.norm(x - ref[rb:re]) / np.linalg.norm(ref[rb:re])
         assert err < 1e-11, err

@@ -1,5 +1,7 @@
 """Row-block sharded CG on N GPUs (torchrun): parity with the single-GPU engine and the oracle,
-then timing.  python -m torch.distributed.run --nproc-per-node N tools/shard_check.py [N3d] [iters]"""
+then timing.  python -m torch.distributed.run --nproc-per-node N tools/shard_check.py [--parity-only] [N3d] [iters]
+
+The parity half is what tests/test_gpu_cg2.py::test_row_block_sharded_cg_parity_over_nvlink runs on 2/4/8 GPUs."""
 import json, os, sys, time
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -11,6 +13,8 @@ import cg_b200.problems as P
 
 import faulthandler
 faulthandler.dump_traceback_later(150, exit=True)
+PARITY_ONLY = "--parity-only" in sys.argv
+ARGS = [a for a in sys.argv[1:] if not a.startswith("--")]
 
 
 def log(*a):
@@ -40,6 +44,16 @@ for name, A, b, tolv in (("lap3d24", P.laplace3d(24), np.ones(24 ** 3), 1e-10),
     log(name, "shard created; plain-launch solve", "p2p" if M.p2p else "nccl")
     M.set_option("use_graph", 0)
     x, info = M.solve(b[rb:re].astype(A.dtype), max_iterations=60)
+    cg2 = M.get_option("cg2_ok")
+    if cg2:
+        # the two-kernel iteration (halo stores from inside the producing kernels) vs the three-kernel one
+        # (halo_push_kernel on a side stream + arrival flags): same FMAs, other association of the dot sums
+        M.set_option("cg2", 0)
+        x3, _ = M.solve(b[rb:re].astype(A.dtype), max_iterations=60)
+        M.set_option("cg2", 1)
+        e3 = float(np.linalg.norm(x - x3) / np.linalg.norm(x3))
+        log(name, "two-kernel vs three-kernel iteration:", e3)
+        assert e3 < 1e-10, e3
     if world > 1:
         M.enable_peer_memory(False)
         xn, _ = M.solve(b[rb:re].astype(A.dtype), max_iterations=60)
@@ -72,13 +86,21 @@ for name, A, b, tolv in (("lap3d24", P.laplace3d(24), np.ones(24 ** 3), 1e-10),
         "x difference", float(np.linalg.norm(x2 - x2p) / np.linalg.norm(x2p)))
     assert np.array_equal(x2, x2p) and info2["iterations"] == info2p["iterations"]
     _, its_ref, _ = cpu_ref.cg(A.data, A.indptr, A.indices, b.astype(A.dtype), iters=5000, tol=1e-9)
-    out[name] = dict(err60=err, iters=info2["iterations"], iters_oracle=int(its_ref[0]), n_halo=plan.n_halo, info=M.info())
+    out[name] = dict(err60=err, iters=info2["iterations"], iters_oracle=int(its_ref[0]), n_halo=plan.n_halo, info=M.info(),
+                     two_kernel=int(cg2))
     assert err < tolv, (name, err)
     assert abs(info2["iterations"] - int(its_ref[0])) <= 1, (name, info2, its_ref)
     M.close()
+if PARITY_ONLY:
+    if rank == 0:
+        print(json.dumps({"world": world, **out}))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    sys.exit(0)
 # ---- timing: 3-D Laplacian N^3, each rank builds only its slab
-N3 = int(sys.argv[1]) if len(sys.argv) > 1 else 300
-iters = int(sys.argv[2]) if len(sys.argv) > 2 else 256
+N3 = int(ARGS[0]) if len(ARGS) > 0 else 300
+iters = int(ARGS[1]) if len(ARGS) > 1 else 256
 n = N3 ** 3
 planes = [(N3 * p) // world for p in range(world + 1)]
 bounds = np.array([pl * N3 * N3 for pl in planes], dtype=np.int64)
@@ -110,7 +132,8 @@ for use_graph, p2p in ((1, 1), (1, 0), (0, 1)):
     if world > 1: dist.all_reduce(t, op=dist.ReduceOp.MAX)
     out[f"lap{N3}_graph{use_graph}_p2p{p2p}"] = dict(ms_per_iter=float(t.item()) / iters, its_per_s=iters / float(t.item()) * 1e3,
                                             n_owned=plan.n_owned, n_halo=plan.n_halo, gen_s=tgen)
-out["local_kernels_us"] = {nm: round(1e3 * M.time_kernel(nm, reps=100), 2) for nm in ("spmv_dot", "update_xr", "update_d")}
+out["local_kernels_us"] = {nm: round(1e3 * M.time_kernel(nm, reps=100), 2)
+                           for nm in ("spmv_dot", "update_xr", "update_d") + (("dir_spmv", "update_r") if M.get_option("cg2_ok") else ())}
 M.close()
 if rank == 0:
     print(json.dumps({"world": world, **out}))
