@@ -10,10 +10,12 @@ driver default, p_h-PY_C-CL.py:3553), i.e. 256 CG iterations on one batch of k r
 
   value   iterations/s with the matrix, b and x already resident in HBM (device pointers through
           cgb200_solve), CUDA events on the launching stream, max over ranks.
-  e2e     the same metric through the exported `cg`/`cgd` symbol with pinned HOST buffers:
-          every step uploads the CSR matrix, b and x0 and reads x back (resident-matrix cache off).
-  roofline  the dominant kernel (SpMV fused with d.q) timed alone with CUDA events, algorithmic
-          bytes B_spmv = nnz(v+4) + 4(n+1) + 2knv against MEASURED_PEAKS.json.
+  e2e     the same metric through the exported `cg`/`cgd` symbol with pinned HOST buffers: every step uploads b and
+          x0 and reads x back; the matrix of the previous call stays resident (content-hashed every call) -- the same
+          kind of number as the sharded e2e at N > 1; `e2e.matrix_uploaded` has the matrix uploaded inside every call.
+  roofline  the kernel that takes the most time, timed alone with CUDA events on the engine's stream; algorithmic
+          bytes per SURVEY.md 8(d) (B_spmv = nnz(v+4) + 4(n+1) + 2knv, + 9knv for the vector passes) against
+          MEASURED_PEAKS.json, and the bytes the kernel really moves (moved_*) where a format compresses them.
   cpu_baseline  the oracle port (oracle/cpu_ref.c, OpenMP, all host cores) on a bounded sample.
 
 Default workload: C4, the 3-D 7-point Laplacian 300^3 (27 M unknowns, f64) -- the configuration
@@ -260,17 +262,24 @@ def run_reference(args, wl, dtype, k, rank, world):
 
 
 def config_of(args, wl, A, k, dtype, world, n=None, nnz=None):
+    v = A.dtype.itemsize
+    per_gpu_rows = A.shape[0] // world if (world > 1 and args.mode == "row-block") else A.shape[0]
+    matrix_bytes = A.nnz * (v + 4) // (world if args.mode == "row-block" else 1)
+    vec_bytes = 6 * per_gpu_rows * k * v          # x, q and the two buffers each of r and d (k = 1), per GPU
     return {"workload": f"{wl['desc']}; n={A.shape[0]}, nnz={A.nnz}, k={k} per GPU, dtype {dtype}; "
                         f"step = one cg() call of {ITERS_PER_STEP} iterations from x0=0",
             "name": args.workload, "n": int(A.shape[0]), "nnz": int(A.nnz), "k": int(k),
             "iters_per_step": ITERS_PER_STEP,
             "parallelism": "single GPU" if world == 1 else
                            (f"rhs-split x{world} (matrix replicated, one RHS per GPU, no collective)" if args.mode == "rhs-split"
-                            else f"row-block x{world}: halo of d pushed peer to peer over NVLink, the 2 dot products per "
-                                 f"iteration all-reduced inside the kernels through peer memory"),
-            "l2": "no L2 flush: matrix + vectors per iteration exceed the 126 MB L2"
-                  if A.nnz * (A.dtype.itemsize + 4) > 126e6 else
-                  "working set fits the 126 MB L2 (latency-bound config); no flush between iterations"}
+                            else f"row-block x{world}: the boundary entries of d and r are stored into the peers' halos over "
+                                 f"NVLink by the kernels that produce them, the 2 dot products per iteration are all-reduced "
+                                 f"inside the kernels through peer memory"),
+            "l2": (f"no L2 flush: the vectors an iteration touches ({vec_bytes / 1e6:.0f} MB per GPU, + {matrix_bytes / 1e6:.0f} MB of "
+                   f"CSR arrays when the row-pattern dictionary is off) exceed the 126 MB L2"
+                   if vec_bytes > 126e6 or matrix_bytes > 126e6 else
+                   f"working set per GPU ({vec_bytes / 1e6:.0f} MB of vectors) fits the 126 MB L2 (latency-bound config); "
+                   f"no flush between iterations")}
 
 
 def save_trace(args, M, world, rank):
@@ -282,40 +291,128 @@ def save_trace(args, M, world, rank):
                 M.read_trace(min(n[0], ITERS_PER_STEP)))
 
 
-def also_single_gpu(name, dtype, peak, tdt_of, stream):
+def kernel_specs(M, n, nnz, k, dtype):
+    """[(kernel name, algorithmic bytes, bytes really moved)] of the iteration the handle runs for k right-hand sides."""
+    import cg_b200.problems as P
+    v = P.DTYPES[dtype][2]
+    b_spmv, _ = P.algorithmic_bytes(n, nnz, k, dtype)
+    npat = M.get_option("patterns") if (k == 1 and M.get_option("pattern")) else 0
+    if k == 1 and npat > 0 and M.get_option("cg2_ok") and M.get_option("cg2") and M.get_option("solver") != 2:
+        # two kernels per iteration (csrc/cg2.cuh): algorithmic = the SURVEY 8(d) bytes of the operations each one
+        # replaces (spmv + aypx + the x-axpy | the r-axpy + vdot); moved = what the format really has to move
+        return [("dir_spmv", b_spmv + 6 * n * v, n * (2 + 6 * v)), ("update_r", 3 * n * v, 3 * n * v)], npat
+    moved_spmv = n * (2 + 2 * v) if npat > 0 else b_spmv
+    return [("spmv_dot", b_spmv, moved_spmv), ("update_xr", 6 * k * n * v, 6 * k * n * v),
+            ("update_d", 3 * k * n * v, 3 * k * n * v)], npat
+
+
+def time_kernels(M, specs, k, peak, reps):
+    out = {}
+    for name, nbytes, moved in specs:
+        kms = M.time_kernel(name, k=k, reps=reps)
+        out[name] = {"ms": kms, "algorithmic_bytes": nbytes, "gbs": nbytes / kms / 1e6, "frac": nbytes / kms / 1e6 / peak,
+                     "moved_bytes": moved, "moved_gbs": moved / kms / 1e6, "moved_frac": moved / kms / 1e6 / peak}
+    return out
+
+
+def also_single_gpu(name, dtype, peak, tdt_of, stream, k=1, opts=None, steps=5):
     """Short resident-data measurement of another BASELINE config on this GPU (value + kernel rooflines)."""
     import torch
     import cg_b200
     import cg_b200.problems as P
-    A, B = make_problem(name, dtype, 1)
+    A, B = make_problem(name, dtype, k)
     n, nnz = A.shape[0], A.nnz
-    v = P.DTYPES[dtype][2]
-    b_spmv, b_iter = P.algorithmic_bytes(n, nnz, 1, dtype)
+    _, b_iter = P.algorithmic_bytes(n, nnz, k, dtype)
     M = cg_b200.Matrix.from_scipy(A)
     M.set_stream(stream.cuda_stream)
+    for key, val in (opts or {}).items():
+        M.set_option(key, val)
     with torch.cuda.stream(stream):
         b_dev = torch.from_numpy(B).to("cuda")
-        x_dev = torch.zeros(n, dtype=tdt_of[dtype], device="cuda")
+        x_dev = torch.zeros(n * k, dtype=tdt_of[dtype], device="cuda")
         for _ in range(3):
             x_dev.zero_()
-            M.solve(b_dev, x=x_dev, max_iterations=ITERS_PER_STEP)
+            M.solve(b_dev, x=x_dev, k=k, max_iterations=ITERS_PER_STEP)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        for _ in range(10):
+        for _ in range(steps):
             x_dev.zero_()
-            info = M.solve(b_dev, x=x_dev, max_iterations=ITERS_PER_STEP)[1]
+            info = M.solve(b_dev, x=x_dev, k=k, max_iterations=ITERS_PER_STEP)[1]
         e1.record(stream)
         torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / 10
-        out = {"workload": WORKLOADS[name]["desc"], "n": int(n), "nnz": int(nnz), "dtype": dtype,
-               "value": ITERS_PER_STEP / (ms / 1e3), "unit": "iterations/s", "ms_per_step": ms, "kernels": {}}
-        for kn, nb in (("spmv_dot", b_spmv), ("update_xr", 6 * n * v), ("update_d", 3 * n * v)):
-            kms = M.time_kernel(kn, reps=100)
-            out["kernels"][kn] = {"ms": kms, "gbs": nb / kms / 1e6, "frac": nb / kms / 1e6 / peak}
+        ms = e0.elapsed_time(e1) / steps
+        out = {"workload": WORKLOADS[name]["desc"], "n": int(n), "nnz": int(nnz), "k": int(k), "dtype": dtype,
+               "options": opts or {}, "value": k * ITERS_PER_STEP / (ms / 1e3), "unit": "iterations/s", "ms_per_step": ms}
         it_ms = info.timing_ms["iterations"] / ITERS_PER_STEP
         out["iteration"] = {"ms": it_ms, "gbs": b_iter / it_ms / 1e6, "frac": b_iter / it_ms / 1e6 / peak}
+        if M.get_option("solver") != 2 and (b_iter > 40e6 or M.get_option("solver") == 1):
+            specs, npat = kernel_specs(M, n, nnz, k, dtype)
+            out["kernels"] = time_kernels(M, specs, k, peak, 100 if b_iter < 500e6 else 30)
+            if npat:
+                out["format"] = f"row-pattern dictionary, {npat} distinct rows"
+        else:
+            out["kernels"] = "single cooperative launch for the whole solve (working set fits the L2): no per-kernel timing"
     M.close()
     return out
+
+
+# relative recursive residual sqrt(|delta_256| / |delta_0|) of a full step (256 iterations from x0 = 0), as the
+# single-GPU engine and the CPU oracle compute it (tests/test_gpu_cg2.py::test_config4_*): what every sharded run must reproduce
+EXPECTED_RELRES_256 = {("c4", "f64"): 0.16825512278}
+
+
+def roofline_of(kernels, peak, peak_src, traffic, traffic_src, where=""):
+    """The `roofline` object for the kernel that takes the most time.  `achieved` / `frac` are on ALGORITHMIC bytes
+    (SURVEY.md 8(d)); a kernel that runs from the row-pattern dictionary moves fewer bytes than that, so its fraction
+    on the bytes it really moves is given too (moved_*)."""
+    dom = max(kernels, key=lambda nm: kernels[nm]["ms"])
+    kd = kernels[dom]
+    out = {"bound": "hbm", "kernel": dom + where, "achieved": kd["gbs"], "peak": peak, "unit": "GB/s", "frac": kd["frac"],
+           "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+           "algorithmic_bytes_per_launch": kd["algorithmic_bytes"], "ms_per_launch": kd["ms"]}
+    if kd.get("moved_bytes", kd["algorithmic_bytes"]) != kd["algorithmic_bytes"]:
+        out.update(moved_bytes_per_launch=kd["moved_bytes"], moved_achieved=kd["moved_gbs"], moved_frac=kd["moved_frac"],
+                   note="this kernel runs from the row-pattern dictionary (2 bytes per row instead of the CSR arrays): "
+                        "`frac` on the CSR-based algorithmic bytes can exceed 1 -- that is format compression; "
+                        "`moved_frac` is the fraction of the HBM roofline on the bytes it really moves")
+    return out
+
+
+def sharded_parity(args, M, plan, b_owned, rb, re, dtype, rank, world, dist, torch, prefix_iters=8):
+    """Collective.  (1) `prefix_iters` iterations of the sharded solve, x gathered on rank 0 and compared with
+    oracle/cpu_ref.c run on the WHOLE system there; (2) the recursive residual after a full 256-iteration step
+    against the single-GPU value.  Returns the `parity` object of the JSON line (rank 0; a dict with ok on all)."""
+    import cg_b200.problems as P
+    np_t = P.DTYPES[dtype][0]
+    x, info = M.solve(b_owned, np.zeros(re - rb, dtype=np_t), max_iterations=prefix_iters)
+    sizes = [int(plan.bounds[p + 1] - plan.bounds[p]) for p in range(world)]
+    xt = torch.from_numpy(np.ascontiguousarray(x)).cuda()
+    outs = [xt if p == rank else torch.zeros(sizes[p], dtype=xt.dtype, device="cuda") for p in range(world)]
+    for p in range(world):                      # (slices differ in length: one broadcast per owner)
+        dist.broadcast(outs[p], src=p)
+    _, full = M.solve(b_owned, np.zeros(re - rb, dtype=np_t), max_iterations=ITERS_PER_STEP)
+    res = {"ok": True}
+    if rank == 0:
+        xg = torch.cat(outs).cpu().numpy()
+        A, B = make_problem(args.workload, dtype, 1)
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import cpu_ref
+        cpu_ref.build()
+        cpu_ref.lib().cpu_ref_set_threads(os.cpu_count() or 1)
+        ref, _, _ = cpu_ref.cg(A.data, A.indptr, A.indices, B, k=1, iters=prefix_iters)
+        err = float(np.linalg.norm(xg - ref) / np.linalg.norm(ref))
+        bar = 1e-10 if dtype in ("f64", "c128") else 1e-5
+        res = {"max_rel": err, "bar": bar, "iters": prefix_iters, "against": "oracle/cpu_ref.c on the whole system (rank 0 host)",
+               "relres_256": full["relres"], "ok": bool(err < bar)}
+        exp = EXPECTED_RELRES_256.get((args.workload, dtype))
+        if exp is not None:
+            res["relres_256_single_gpu"] = exp
+            res["ok"] = bool(res["ok"] and abs(full["relres"] - exp) < 1e-8 * exp)
+    flag = torch.tensor([1 if res["ok"] else 0], device="cuda")
+    dist.broadcast(flag, src=0)
+    if rank != 0:
+        res = {"ok": bool(flag.item())}
+    return res
 
 
 def run_row_block(args, wl, dtype, rank, local_rank, world):
@@ -413,20 +510,33 @@ def run_row_block(args, wl, dtype, rank, local_rank, world):
     b_spmv = lnnz * (v_bytes + 4) + 4 * (ln + 1) + 2 * ln * v_bytes
     kernels = {}
     reps = 50 if b_spmv > 50e6 else 400
-    for name, nbytes in (("spmv_dot", b_spmv), ("update_xr", 6 * ln * v_bytes), ("update_d", 3 * ln * v_bytes)):
+    npat = M.get_option("patterns")
+    two_kernel = bool(M.get_option("cg2_ok") and M.get_option("cg2") and npat > 0)
+    if two_kernel:
+        # two kernels per iteration (csrc/cg2.cuh).  algorithmic = the SURVEY 8(d) bytes of the operations each one
+        # replaces (spmv + aypx + the x-axpy | the r-axpy + vdot); moved = what the format really has to move
+        specs = (("dir_spmv", b_spmv + 6 * ln * v_bytes, ln * (2 + 6 * v_bytes)), ("update_r", 3 * ln * v_bytes, 3 * ln * v_bytes))
+    else:
+        moved_spmv = ln * (2 + 2 * v_bytes) if npat > 0 else b_spmv
+        specs = (("spmv_dot", b_spmv, moved_spmv), ("update_xr", 6 * ln * v_bytes, 6 * ln * v_bytes),
+                 ("update_d", 3 * ln * v_bytes, 3 * ln * v_bytes))
+    for name, nbytes, moved in specs:
         kms = M.time_kernel(name, reps=reps)
-        kernels[name] = {"ms": kms, "algorithmic_bytes": nbytes, "gbs": nbytes / kms / 1e6, "frac": nbytes / kms / 1e6 / peak}
+        kernels[name] = {"ms": kms, "algorithmic_bytes": nbytes, "gbs": nbytes / kms / 1e6, "frac": nbytes / kms / 1e6 / peak,
+                         "moved_bytes": moved, "moved_gbs": moved / kms / 1e6, "moved_frac": moved / kms / 1e6 / peak}
+    if npat > 0:
+        kernels[specs[0][0]]["format"] = f"row-pattern dictionary, {npat} distinct rows (DESIGN.md 4.3)"
     sinfo = M.info()
-    try:
-        npat = M.get_option("patterns")
-        if npat > 0:       # see the single-GPU line: CSR bytes stay the yardstick, the format moves fewer
-            moved = ln * (2 + 2 * v_bytes)
-            kernels["spmv_dot"].update(format=f"row-pattern dictionary, {npat} distinct rows (DESIGN.md 4.3)",
-                                       moved_bytes=moved, moved_gbs=moved / kernels["spmv_dot"]["ms"] / 1e6,
-                                       moved_frac=moved / kernels["spmv_dot"]["ms"] / 1e6 / peak)
-    except Exception:
-        pass
+
+    # ---- parity, outside the timed region: a prefix of the iteration against the CPU oracle on the WHOLE system
+    # (rank 0 builds it), and the recursive residual after a full step against the single-GPU engine's value
+    parity = sharded_parity(args, M, plan, b_owned, rb, re, dtype, rank, world, dist, torch)
     M.close()
+    if parity is not None and not parity["ok"]:
+        if rank == 0:
+            print("bench.py: PARITY FAILURE of the sharded solve: " + json.dumps(parity), file=sys.stderr, flush=True)
+        dist.destroy_process_group()
+        raise SystemExit(3)
     if rank == 0:
         it_ms = info["timing_ms"]["iterations"] / ITERS_PER_STEP
 
@@ -439,11 +549,8 @@ def run_row_block(args, wl, dtype, rank, local_rank, world):
             "metric": "CG iters/sec", "value": value, "unit": "iterations/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": dtype, "data": "synthetic", "config": config_of(args, wl, a, 1, dtype, world),
-            "roofline": {"bound": "hbm", "kernel": "spmv_dot (rank 0 row block)", "achieved": kernels["spmv_dot"]["gbs"],
-                         "peak": peak, "unit": "GB/s", "frac": kernels["spmv_dot"]["frac"], "traffic": None,
-                         "peak_source": peak_src, "algorithmic_bytes_per_launch": b_spmv,
-                         "ms_per_launch": kernels["spmv_dot"]["ms"]},
-            "kernels": kernels,
+            "roofline": roofline_of(kernels, peak, peak_src, None, None, where=" (rank 0 row block)"),
+            "kernels": kernels, "parity": parity,
             "iteration": {"ms": it_ms, "local_algorithmic_bytes": b_iter_local, "gbs_per_gpu": b_iter_local / it_ms / 1e6,
                           "frac": b_iter_local / it_ms / 1e6 / peak},
             "shard": sinfo, "options": args.opt, "cpu_baseline": None, "e2e": e2e, "gpu_launches": int(launches),
@@ -554,25 +661,19 @@ def main():
     # ---- per-kernel rooflines (rank 0), CUDA events around back-to-back launches of one kernel
     peak, peak_src = measured_peak()
     kernels = {}
+    npat = 0
     if rank == 0:
-        reps = 50 if b_iter > 50e6 else 400
-        bytes_of = {"spmv_dot": b_spmv, "update_xr": 6 * k * n * v_bytes, "update_d": 3 * k * n * v_bytes}
-        for name, nbytes in bytes_of.items():
-            kms = M.time_kernel(name, k=k, reps=reps)
-            kernels[name] = {"ms": kms, "algorithmic_bytes": nbytes, "gbs": nbytes / kms / 1e6,
-                             "frac": nbytes / kms / 1e6 / peak}
+        specs, npat = kernel_specs(M, n, nnz, k, dtype)
+        kernels = time_kernels(M, specs, k, peak, 50 if b_iter > 50e6 else 400)
         M.solve(b_dev, x=x_dev, k=k, max_iterations=2)          # restore a sane state
-        npat = M.get_option("patterns") if k == 1 else 0
         if npat > 0:
-            # the SpMV ran from the row-pattern dictionary: "algorithmic_bytes" stays the CSR figure of SURVEY.md 8(d)
-            # (so frac can exceed 1); what the kernel really has to move is 2 bytes per row + x + y
-            moved = n * (2 + 2 * v_bytes)
-            kernels["spmv_dot"].update(format=f"row-pattern dictionary, {npat} distinct rows (DESIGN.md 4.3)",
-                                       moved_bytes=moved, moved_gbs=moved / kernels["spmv_dot"]["ms"] / 1e6,
-                                       moved_frac=moved / kernels["spmv_dot"]["ms"] / 1e6 / peak)
+            kernels[specs[0][0]]["format"] = f"row-pattern dictionary, {npat} distinct rows (DESIGN.md 4.3)"
     it_ms = timing["iterations"] / ITERS_PER_STEP
 
-    # ---- e2e through the exported cg / cgd symbol, pinned host buffers, matrix re-uploaded each step
+    # ---- e2e through the exported cg / cgd symbol with pinned HOST buffers.  Top level: the matrix stays resident between
+    # calls (the as_prec pattern the symbol exists for, and the same kind of number as the sharded line's e2e at
+    # N > 1): every timed call hashes the CSR arrays it is handed (content identity), uploads b and x0 and reads x
+    # back.  Beside it: the matrix uploaded inside every call too, and the reference's allocate-everything life cycle.
     e2e = None
     if not args.no_e2e:
         os.environ["CGB200_DEVICE"] = str(local_rank)
@@ -597,21 +698,22 @@ def main():
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
             return float(t.item())
 
-        h2d = nnz * (v_bytes + 4) + 4 * (n + 1) + 2 * k * n * v_bytes
-        tt = e2e_run("2")
-        e2e = {"value": world * k * ITERS_PER_STEP * args.steps / tt, "unit": "iterations/s",
-               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(k * n * v_bytes),
-               "ms_per_step": 1e3 * tt / args.steps,
-               "how": "cg()/cgd() C symbol on pinned host numpy arrays; the CSR matrix, b and x0 are uploaded and x is "
-                      "read back inside every timed call (CGB200_CACHE=2: device buffers are reused, content is "
-                      "not); wall clock around the blocking call"}
+        its_total = world * k * ITERS_PER_STEP * args.steps
+        h2d_matrix = nnz * (v_bytes + 4) + 4 * (n + 1)
+        tt1 = e2e_run("1")
+        e2e = {"value": its_total / tt1, "unit": "iterations/s",
+               "h2d_bytes_per_step": int(2 * k * n * v_bytes), "d2h_bytes_per_step": int(k * n * v_bytes),
+               "ms_per_step": 1e3 * tt1 / args.steps, "kind": "matrix resident",
+               "how": "cg()/cgd() C symbol on pinned host numpy arrays, wall clock around the blocking call; the matrix "
+                      "of the previous call is still resident (default CGB200_CACHE=1: the call hashes the CSR arrays "
+                      "it is handed -- 128-bit content identity -- and re-uploads only on a change); b and x0 are "
+                      "uploaded and x is read back inside every timed call"}
+        tt2 = e2e_run("2")          # device buffers reused, content uploaded on every call
+        e2e["matrix_uploaded"] = {"value": its_total / tt2, "ms_per_step": 1e3 * tt2 / args.steps,
+                                  "h2d_bytes_per_step": int(h2d_matrix + 2 * k * n * v_bytes)}
         # the reference's own life cycle: allocate, upload, solve, free on every call (clcg.c:142-214, :432-459)
         tt0 = e2e_run("0")
-        e2e["alloc_every_call_value"] = world * k * ITERS_PER_STEP * args.steps / tt0
-        # the as_prec pattern: same matrix on every call -> resident copy reused (content hash), only b/x move
-        tt1 = e2e_run("1")
-        e2e["resident_matrix_value"] = world * k * ITERS_PER_STEP * args.steps / tt1
-        e2e["resident_matrix_h2d_bytes_per_step"] = int(2 * k * n * v_bytes)
+        e2e["alloc_every_call"] = {"value": its_total / tt0, "ms_per_step": 1e3 * tt0 / args.steps}
         cg_b200._lib.lib().cgb200_clear_cache()
 
     if rank == 0:
@@ -630,29 +732,35 @@ def main():
         line = {
             "metric": "CG iters/sec", "value": value, "unit": "iterations/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": dtype, "data": "synthetic",
+            "scaling": "strong", "vs_baseline": None, "dtype": dtype, "data": "synthetic",
             "config": config_of(args, wl, A, k, dtype, world),
-            "roofline": {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["gbs"], "peak": peak, "unit": "GB/s",
-                         "frac": kernels[dom]["frac"], "traffic": traffic, "traffic_source": traffic_src,
-                         "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": kernels[dom]["algorithmic_bytes"],
-                         "ms_per_launch": kernels[dom]["ms"]},
+            "roofline": roofline_of(kernels, peak, peak_src, traffic, traffic_src),
             "kernels": kernels,
             "iteration": {"ms": it_ms, "algorithmic_bytes": b_iter, "gbs": b_iter / it_ms / 1e6,
-                          "frac": b_iter / it_ms / 1e6 / peak, "spmv_pct_of_nominal_8TBs": None},
+                          "frac": b_iter / it_ms / 1e6 / peak,
+                          "kernels_per_iteration": len(kernels)},
             "options": args.opt, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "solve_phases_ms": timing,
         }
-        line["iteration"]["spmv_pct_of_nominal_8TBs"] = 100.0 * kernels["spmv_dot"]["gbs"] / 8000.0
-        if "format" in kernels["spmv_dot"]:
-            note = ("the SpMV runs from the row-pattern dictionary and moves fewer bytes than the CSR figure its "
-                    "'algorithmic_bytes' is (kernels.spmv_dot.moved_*): fractions above 1 are format compression, "
-                    "not bandwidth")
-            line["iteration"]["note"] = note
-            if dom == "spmv_dot":
-                line["roofline"]["note"] = note
-        if world == 1 and not args.no_also and args.workload != "c2":
-            line["also"] = {"c2_c128": also_single_gpu("c2", "c128", peak, tdt_of, stream)}
+        if npat > 0:
+            line["iteration"]["note"] = ("the SpMV runs from the row-pattern dictionary and moves fewer bytes than the CSR "
+                                         "figure the algorithmic bytes are (kernels.*.moved_*): fractions above 1 are format "
+                                         "compression, not bandwidth")
+        if world == 1 and not args.no_also:
+            # the other BASELINE configs on this GPU, resident data, short; c4_csr = the CSR kernels (the north star's
+            # SpMV: nnz(v+4) bytes streamed by TMA) on the headline system, with the row-pattern dictionary switched off
+            also = {}
+            legs = [("c4_csr", "c4", "f64", 1, {"pattern": 0}, 3), ("c2_c128", "c2", "c128", 1, None, 5),
+                    ("c1_f64", "c1", "f64", 1, None, 5), ("c3_f64_k32", "c3", "f64", 32, None, 3),
+                    ("c5_f64", "c5", "f64", 1, None, 3)]
+            for key, name, dt_, k_, opts, steps_ in legs:
+                if name == args.workload and not opts:
+                    continue
+                try:
+                    also[key] = also_single_gpu(name, dt_, peak, tdt_of, stream, k=k_, opts=opts, steps=steps_)
+                except Exception as e:          # a reporting extra must never break the line
+                    also[key] = {"error": str(e)[:200]}
+            line["also"] = also
         print(json.dumps(line), flush=True)
     M.close()
     if world > 1:

@@ -13,6 +13,6 @@ Import as `cg_b200` (see /cg_b200.py at the repo root; the directory name has a 
 """
 from . import _lib, problems            # noqa: F401
 from ._lib import CgError, F32, F64, C64, C128, LAYOUT_CLCG, LAYOUT_ROWMAJOR  # noqa: F401
-from .engine import Matrix, cg, device_count  # noqa: F401
+from .engine import Matrix, PCG, cg, device_count  # noqa: F401
 
-__all__ = ["Matrix", "cg", "device_count", "problems", "CgError"]
+__all__ = ["Matrix", "PCG", "cg", "device_count", "problems", "CgError"]

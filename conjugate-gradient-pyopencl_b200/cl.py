@@ -163,3 +163,20 @@ def conjugate_gradient_multi_gpu(ctx, queue, kernels, size, non_zeros, a_values,
     releases the GIL and each device has its own resident matrix and stream."""
     return _solve(_ordinal(ctx, device), size, non_zeros, a_values, b_values, a_pointers, a_cols, x,
                   n_rhs, n_iterations)
+
+
+def PCG(ctx, queue, kernels, size, non_zeros, a_values, b_values, a_pointers, a_cols, x, n_rhs, n_iterations,
+        m_inv_diag=None, tol=0.0, device=None):
+    """NOT in the reference's cl.py: the device twin of its numpy PCG (helmFE_var.py:546-586) in the calling
+    convention of `CG` above, for the drivers that want a preconditioned subdomain solve (the report's own
+    future work).  m_inv_diag: `size` values of M = inverse diagonal (None: 1 / diag(A), Jacobi);
+    tol: absolute, on sqrt|r.r| as the reference stops (0: exactly n_iterations).  x is filled in place and returned."""
+    try:
+        from . import engine
+    except ImportError:
+        import engine
+    a_values = np.ascontiguousarray(a_values)
+    with engine.Matrix(a_values[:int(non_zeros)], np.asarray(a_pointers)[:int(size) + 1], np.asarray(a_cols)[:int(non_zeros)],
+                       n=int(size), device=_ordinal(ctx, device)) as M:
+        M.solve_pcg(b_values, x=x, k=int(n_rhs), M_inv_diag=m_inv_diag, max_iterations=int(n_iterations), tol=float(tol))
+    return x

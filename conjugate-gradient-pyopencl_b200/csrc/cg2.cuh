@@ -19,14 +19,18 @@
 // three-kernel path (the row sums follow CSR order, dn = fma(beta, d, r), x = fma(alpha, d, x),
 // r = fma(-alpha, q, r)); only the association of the two dot-product reductions differs.
 //
-// The gather.  A block works on chunks of PAT_CHUNK consecutive rows.  The pattern dictionary knows every
-// column offset (col - row) the matrix uses -- 7 for the 3-D Laplacian --; offsets that are closer than a
-// chunk are merged into a WINDOW, and for a chunk starting at row c0 the window [lo, hi] needs exactly the
-// vector entries [c0 + lo, c0 + hi + PAT_CHUNK).  Those are read with coalesced 128-bit loads from both r and
-// d, combined (r + beta d) and left in shared memory once; the rows then read their neighbours from shared
-// memory at consecutive addresses (conflict-free).  Compared with 7 scattered 8-byte gathers per row and
-// vector this is 3.6 contiguous elements per row and vector for the 300^3 Laplacian, and the L1 pipe sees
-// 128-bit requests instead of 64-bit ones.
+// The gather.  A block (one per SM, one row per thread) works on chunks of PAT_CHUNK consecutive rows.  The
+// pattern dictionary knows every column offset (col - row) the matrix uses -- 7 for the 3-D Laplacian --;
+// offsets that are closer than a chunk are merged into a WINDOW, and for a chunk starting at row c0 the
+// window [lo, hi] needs exactly the vector entries [c0 + lo, c0 + hi + PAT_CHUNK).  Those pieces of r and of
+// d arrive in shared memory by TMA bulk copies (cp.async.bulk + mbarrier, one elected thread issues them,
+// nstage - 1 chunks ahead of the one being consumed), and the rows read their neighbours from shared memory
+// at consecutive addresses (conflict-free).  Compared with 7 scattered 8-byte gathers per row and vector
+// this is 3.6 contiguous elements per row and vector for the 300^3 Laplacian, none of them through
+// registers or the L1 request path; what the threads still load themselves -- the 16-bit pattern number
+// and x -- is requested one chunk ahead.  (First version, kept in git: windows staged THROUGH registers as
+// r + beta d by 256-thread blocks, 3 per SM -- 885 us on C4, bound by ~7 dependent memory round trips per
+// chunk with only 3 blocks to overlap them.)
 //
 // Row-block shards.  Ping-pong buffers for d (the SpMV reads the old one everywhere while owners write the
 // new one) and for r make every kernel read-only on its inputs, so the entries a peer needs can be
@@ -81,29 +85,56 @@ __device__ __forceinline__ T cg2_grid_total(const CgScalars<T> &sc, T *red) {
     return total;
 }
 
+// dir_spmv is warp-specialised: DIR_CONSUMERS threads own the rows of a chunk (PAT_CHUNK / DIR_CONSUMERS rows
+// each, independent accumulation chains), one more warp does nothing but feed the ring of stages with TMA.
+constexpr int DIR_CONSUMERS = 512;
+constexpr int DIR_THREADS = DIR_CONSUMERS + 32;
+constexpr int DIR_MAX_STAGES = 4;
+
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Shared-memory layout of dir_spmv (the host computes the same sizes, Engine::cg2_smem_bytes):
+//   [0, 128)   mbarriers: full[stage] (the stage's copies have landed), empty[stage] (every consumer warp is done with it)
+//   red        [32]                 block reduction scratch (one slot per warp)
+//   s_val      [npat][STRIDE]       pattern coefficients
+//   stages     nstage x { r window(s) [total], d window(s) [total] }   raw pieces of the two vectors, by TMA
+//   s_pos      [npat][STRIDE] int   staging position of every pattern entry
+//   s_len      [npat] int
 template <typename T, int STRIDE, bool PEER>
-__global__ void __launch_bounds__(PAT_THREADS, sizeof(T) == 16 ? 2 : 3)
-cg2_dir_spmv_kernel(int n, int ncols, int nchunks, int npat, PatWindows win, const unsigned short *__restrict__ pat,
+__global__ void __launch_bounds__(DIR_THREADS, 1)
+cg2_dir_spmv_kernel(int n, int ncols, int nchunks, int npat, int nstage, PatWindows win, const unsigned short *__restrict__ pat,
                     const unsigned *__restrict__ chunk_mask, const int *__restrict__ p_len, const int *__restrict__ p_spos,
                     const T *__restrict__ p_val, T *__restrict__ x, T *__restrict__ q, T *r0, T *r1, T *d0, T *d1,
                     CgScalars<T> sc) {
-    constexpr int NT = PAT_THREADS;
+    constexpr int NT = DIR_CONSUMERS;
+    constexpr int RPT = PAT_CHUNK / NT;                                        // rows per consumer thread and chunk
     constexpr int VPT = VecW<T>::value;
-    using P = Pack<T, VPT>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    T *red = reinterpret_cast<T *>(smem_raw);                                  // [NT]
-    T *s_val = red + NT;                                                       // [npat][STRIDE]
-    T *S = s_val + npat * STRIDE;                                              // [win.total]   r + beta d around the chunk
-    int *s_pos = reinterpret_cast<int *>(S + win.total);                       // [npat][STRIDE] staging position of every entry
-    int *s_len = s_pos + npat * STRIDE;                                        // [npat]
+    unsigned long long *full = reinterpret_cast<unsigned long long *>(smem_raw);
+    unsigned long long *empty = full + DIR_MAX_STAGES;
+    T *red = reinterpret_cast<T *>(smem_raw + 128);                            // [32]
+    T *s_val = red + 32;                                                       // [npat][STRIDE]
+    T *stage0 = s_val + npat * STRIDE;                                         // [nstage][2][win.total]
+    int *s_pos = reinterpret_cast<int *>(stage0 + (size_t)nstage * 2 * win.total);
+    int *s_len = s_pos + npat * STRIDE;
     const int t = threadIdx.x;
+    const bool producer = t >= NT;
     // the table is part of the matrix, not the previous kernel's output: staged before the grid dependency wait
-    for (int i = t; i < npat * STRIDE; i += NT) {
+    for (int i = t; i < npat * STRIDE; i += DIR_THREADS) {
         const int id = i / STRIDE, j = i % STRIDE;
         s_val[i] = p_val[id * PAT_MAXLEN + j];
         s_pos[i] = p_spos[id * PAT_MAXLEN + j];
     }
-    for (int i = t; i < npat; i += NT) s_len[i] = p_len[i];
+    for (int i = t; i < npat; i += DIR_THREADS) s_len[i] = p_len[i];
+    if (t == 0) {
+        for (int s = 0; s < nstage; s++) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], NT / 32);
+        }
+        mbar_fence_init();
+    }
     __syncthreads();
     pdl_wait();
     if (sc.pdl_early) pdl_trigger();
@@ -115,99 +146,210 @@ cg2_dir_spmv_kernel(int n, int ncols, int nchunks, int npat, PatWindows win, con
     const T *__restrict__ dold = odd ? d1 : d0;
     T *__restrict__ dnew = odd ? d0 : d1;
     const T beta = sc.beta[0], alpha_prev = sc.alpha[0];
+    const int count = ((int)blockIdx.x < nchunks) ? (nchunks - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    T dot = Sc<T>::zero();
 
-    if constexpr (PEER) {
-        if (sc.peer && sc.peer->world > 1)
-            peer_push_rows<T>(sc.peer, odd ? 0 : 1, [&](int row) { return Sc<T>::fma(beta, dold[row], r[row]); });
-    }
-
-    T dot[1] = {Sc<T>::zero()};
-    const int npk = win.total / VPT;
-    constexpr int ROWS_PT = PAT_CHUNK / NT;
-
-    for (int ch = (int)blockIdx.x; ch < nchunks; ch += (int)gridDim.x) {
-        const int c0 = ch * PAT_CHUNK;
-        const unsigned wmask = chunk_mask[ch];
-        int ids[ROWS_PT];
-#pragma unroll
-        for (int s = 0; s < ROWS_PT; s++) {
-            const int row = c0 + t + s * NT;
-            ids[s] = row < n ? (int)pat[row] : -1;
-        }
-        // ---- stage r + beta d of every window: packs t, t + NT, ..., four loads of each vector in flight per thread
-        for (int e0 = t; e0 < npk; e0 += 4 * NT) {
-            P rv[4], dv[4];
-            int spos[4];
-            bool ld[4];
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const int e = e0 + u * NT;
-                const int pos = e * VPT;
-                int w = 0;
-#pragma unroll
-                for (int i = 1; i < WIN_MAX; i++) w += (i < win.nwin && pos >= win.base[i]) ? 1 : 0;
-                const long long g = (long long)c0 + win.lo[w] + (pos - win.base[w]);
-                spos[u] = e < npk ? pos : -1;
-                ld[u] = e < npk && ((wmask >> w) & 1u) && g >= 0 && g < ncols;
-                if (ld[u]) {
-                    rv[u] = *reinterpret_cast<const P *>(r + g);
-                    dv[u] = *reinterpret_cast<const P *>(dold + g);
+    if (producer) {
+        // ---- one elected thread: the windows of this block's i-th chunk, both vectors, into stage i % nstage,
+        // as soon as the consumers have released the stage.  Parts of a window outside the vector are not
+        // copied: no row of the chunk reads them.
+        {
+            const bool elected = t == NT;      // (the other lanes walk the loop with it and meet it at __syncwarp)
+            const long long ncols_pad = ((long long)ncols + VPT - 1) / VPT * VPT;      // (every vector has >= 256 bytes of slack)
+            unsigned wmask = (elected && count > 0) ? chunk_mask[blockIdx.x] : 0u;
+            int s = 0;                          // stage i % nstage and the parity of its use, tracked without divisions
+            unsigned use_parity = 1;            // ((i / nstage) - 1) & 1
+            for (int i = 0; i < count; i++, s++) {
+                __syncwarp();
+                if (s == nstage) {
+                    s = 0;
+                    use_parity ^= 1u;
                 }
-            }
+                if (!elected) continue;
+                const int ch = (int)blockIdx.x + i * (int)gridDim.x;
+                const long long c0 = (long long)ch * PAT_CHUNK;
+                const unsigned wm = wmask;
+                if (i + 1 < count) wmask = chunk_mask[ch + (int)gridDim.x];             // requested one chunk ahead
+                if (i >= nstage) mbar_wait(&empty[s], use_parity);
+                T *Sr = stage0 + (size_t)s * 2 * win.total, *Sd = Sr + win.total;
+                unsigned bytes = 0;
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
-                if (spos[u] >= 0) {
-                    P wv;
+                for (int w = 0; w < WIN_MAX; w++) {          // (fully unrolled: `win` stays in the constant bank)
+                    if (w >= win.nwin || !((wm >> w) & 1u)) continue;
+                    const long long g0 = c0 + win.lo[w];
+                    const long long a = g0 > 0 ? g0 : 0, b = min(g0 + win.size[w], ncols_pad);
+                    if (b > a) bytes += (unsigned)((b - a) * sizeof(T));
+                }
+                mbar_arrive_expect_tx(&full[s], 2 * bytes);
 #pragma unroll
-                    for (int v = 0; v < VPT; v++) wv.v[v] = ld[u] ? Sc<T>::fma(beta, dv[u].v[v], rv[u].v[v]) : Sc<T>::zero();
-                    *reinterpret_cast<P *>(S + spos[u]) = wv;
+                for (int w = 0; w < WIN_MAX; w++) {
+                    if (w >= win.nwin || !((wm >> w) & 1u)) continue;
+                    const long long g0 = c0 + win.lo[w];
+                    const long long a = g0 > 0 ? g0 : 0, b = min(g0 + win.size[w], ncols_pad);
+                    if (b <= a) continue;
+                    const unsigned nb = (unsigned)((b - a) * sizeof(T));
+                    bulk_g2s(Sr + win.base[w] + (a - g0), r + a, nb, &full[s]);
+                    bulk_g2s(Sd + win.base[w] + (a - g0), dold + a, nb, &full[s]);
                 }
             }
         }
-        __syncthreads();
-        // ---- rows: neighbours out of shared memory at consecutive addresses.
-        // STRIDE 8: the pattern of a thread's previous row of the chunk stays in registers (on a grid nearly
-        // every row has the same one); longer rows read the table out of shared memory entry by entry
+    } else {
+        if constexpr (PEER) {
+            if (sc.peer && sc.peer->world > 1) {
+                // (grid-strided over the send list by the consumer threads of all blocks)
+                const PeerComm *pc = sc.peer;
+                const int total = pc->send_off[pc->world];
+                bool stored = false;
+                for (int e = blockIdx.x * NT + t; e < total; e += gridDim.x * NT) {
+                    int p = 0;
+                    while (e >= pc->send_off[p + 1]) p++;
+                    const int row = pc->send_idx[e];
+                    T *dst = reinterpret_cast<T *>(pc->vec[odd ? 0 : 1][p]) + pc->remote_off[p] + (e - pc->send_off[p]);
+                    *dst = Sc<T>::fma(beta, dold[row], r[row]);
+                    stored = true;
+                }
+                if (stored) __threadfence_system();
+            }
+        }
+        // The pattern number and x of a thread's rows are requested one chunk ahead.  The loads are unconditional
+        // (clamped row) and nothing touches their result before the next chunk, so that the wait for a stage
+        // below never waits for THEM (a select on the loaded value right after the load did exactly that: 37 % of
+        // the stall samples of the first version, profiles/r02_ncu_dir_spmv_c4_v3.txt).
+        unsigned short id_cur[RPT];
+        T x_cur[RPT];
+        const long long last_row = (long long)n - 1;
+#pragma unroll
+        for (int s = 0; s < RPT; s++) {
+            const long long row = min((long long)blockIdx.x * PAT_CHUNK + t + s * NT, last_row);
+            id_cur[s] = pat[row];
+            x_cur[s] = ld_stream_bytes(x + row);
+        }
+        // STRIDE 8: the pattern a thread used last stays in registers (on a grid nearly every row of a thread has
+        // the same one); longer rows read the table out of shared memory entry by entry.  Positions are kept as
+        // byte offsets: one add per shared-memory access.
         int cid = -1;
-        int cpos[STRIDE <= 8 ? STRIDE : 1];
+        int cposb[STRIDE <= 8 ? STRIDE : 1];
         T cval[STRIDE <= 8 ? STRIDE : 1];
+        const unsigned d_off = (unsigned)win.total * (unsigned)sizeof(T);          // the d pieces follow the r pieces
+        const unsigned diag_b = (unsigned)win.diag * (unsigned)sizeof(T);
+        const unsigned stage_bytes = 2u * d_off;
+        const unsigned char *stage_base = reinterpret_cast<const unsigned char *>(stage0);
+        int st = 0;
+        unsigned parity = 0;
+
+        for (int i = 0; i < count; i++) {
+            const int ch = (int)blockIdx.x + i * (int)gridDim.x;
+            const int c0 = ch * PAT_CHUNK;
+            unsigned short id_nxt[RPT];
+            T x_nxt[RPT];
 #pragma unroll
-        for (int s = 0; s < ROWS_PT; s++) {
-            const int tl = t + s * NT, row = c0 + tl;
-            const int id = ids[s];
-            if (id < 0) break;
-            const T xo = ld_stream_bytes(x + row);
-            const T dd = dold[row];
-            T sum = Sc<T>::zero();
-            if constexpr (STRIDE <= 8) {
-                if (id != cid) {
-                    cid = id;
-#pragma unroll
-                    for (int j = 0; j < STRIDE; j++) {
-                        cpos[j] = s_pos[id * STRIDE + j];
-                        cval[j] = s_val[id * STRIDE + j];
-                    }
-                }
-                // padded entries point at the row's own position with coefficient 0 (as spmv_pattern_kernel pads)
-#pragma unroll
-                for (int j = 0; j < STRIDE; j++) sum = Sc<T>::fma(cval[j], S[cpos[j] + tl], sum);
-            } else {
-                const int len = s_len[id];
-                for (int j = 0; j < len; j++) sum = Sc<T>::fma(s_val[id * STRIDE + j], S[s_pos[id * STRIDE + j] + tl], sum);
+            for (int s = 0; s < RPT; s++) {
+                const long long row = min((long long)c0 + (long long)gridDim.x * PAT_CHUNK + t + s * NT, last_row);
+                id_nxt[s] = pat[row];
+                x_nxt[s] = ld_stream_bytes(x + row);
             }
-            const T dn = S[win.diag + tl];
-            q[row] = sum;
-            dnew[row] = dn;
-            st_stream_bytes(x + row, Sc<T>::fma(alpha_prev, dd, xo));
-            dot[0] = Sc<T>::fma(dn, sum, dot[0]);
+            const unsigned char *Sb = stage_base + (size_t)st * stage_bytes;
+            mbar_wait(&full[st], parity);
+#pragma unroll
+            for (int s = 0; s < RPT; s++) {
+                const int tl = t + s * NT, row = c0 + tl;
+                if (row < n) {
+                    const int id = id_cur[s];
+                    const unsigned char *Srow = Sb + (size_t)tl * sizeof(T);             // the row's own position in the r pieces
+                    T sum = Sc<T>::zero();
+                    if constexpr (STRIDE <= 8) {
+                        if (id != cid) {
+                            cid = id;
+#pragma unroll
+                            for (int j = 0; j < STRIDE; j++) {
+                                cposb[j] = s_pos[id * STRIDE + j] * (int)sizeof(T);
+                                cval[j] = s_val[id * STRIDE + j];
+                            }
+                        }
+                        // every neighbour loaded before the first FMA; padded entries point at the row's own
+                        // position with coefficient 0 (as spmv_pattern_kernel pads)
+                        T rw[STRIDE], dw[STRIDE];
+#pragma unroll
+                        for (int j = 0; j < STRIDE; j++) {
+                            rw[j] = *reinterpret_cast<const T *>(Srow + cposb[j]);
+                            dw[j] = *reinterpret_cast<const T *>(Srow + cposb[j] + d_off);
+                        }
+#pragma unroll
+                        for (int j = 0; j < STRIDE; j++) sum = Sc<T>::fma(cval[j], Sc<T>::fma(beta, dw[j], rw[j]), sum);
+                    } else {
+                        const int len = s_len[id];
+                        for (int j = 0; j < len; j++) {
+                            const unsigned char *pp = Srow + (size_t)s_pos[id * STRIDE + j] * sizeof(T);
+                            sum = Sc<T>::fma(s_val[id * STRIDE + j],
+                                             Sc<T>::fma(beta, *reinterpret_cast<const T *>(pp + d_off), *reinterpret_cast<const T *>(pp)), sum);
+                        }
+                    }
+                    const T dd = *reinterpret_cast<const T *>(Srow + diag_b + d_off);
+                    const T dn = Sc<T>::fma(beta, dd, *reinterpret_cast<const T *>(Srow + diag_b));
+                    q[row] = sum;
+                    dnew[row] = dn;
+                    st_stream_bytes(x + row, Sc<T>::fma(alpha_prev, dd, x_cur[s]));
+                    dot = Sc<T>::fma(dn, sum, dot);
+                }
+                id_cur[s] = id_nxt[s];
+                x_cur[s] = x_nxt[s];
+            }
+            __syncwarp();
+            if ((t & 31) == 0) mbar_arrive(&empty[st]);          // this warp has read everything it needs from the stage
+            if (++st == nstage) {
+                st = 0;
+                parity ^= 1u;
+            }
         }
-        __syncthreads();        // S is rewritten by the next chunk
     }
 
-    block_col_reduce<T, 1>(dot, 1, red);
+    // block sum in a fixed order: lanes by butterfly, then the warps one after the other
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        if constexpr (Sc<T>::cplx) {
+            dot.x += __shfl_xor_sync(0xffffffffu, dot.x, off);
+            dot.y += __shfl_xor_sync(0xffffffffu, dot.y, off);
+        } else {
+            dot += __shfl_xor_sync(0xffffffffu, dot, off);
+        }
+    }
+    if ((t & 31) == 0) red[t >> 5] = dot;
+    __syncthreads();
+    if (t == 0) {
+        T sum = Sc<T>::zero();
+        for (int w = 0; w < NT / 32; w++) sum = Sc<T>::add(sum, red[w]);
+        red[0] = sum;
+    }
+    __syncthreads();
     if (publish_and_arrive<T, 1>(red, 1, 1, sc.partial, sc.ticket + TK_SPMV)) {
         if (t == 0 && sc.trace) trace_mark<T>(sc, it, TR_SPMV_ALL_DONE);
-        const T total = cg2_grid_total<T, PEER>(sc, red);
+        // sum of the per-block partials in a fixed order (grid_col_reduce wants a power-of-two block): strided
+        // loads issued together, lanes by butterfly, then the warps one after the other
+        __shared__ T s_total;
+        __threadfence();
+        T v = Sc<T>::zero();
+        for (int b = t; b < (int)gridDim.x; b += DIR_THREADS) v = Sc<T>::add(v, ld_cg(sc.partial + b));
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            if constexpr (Sc<T>::cplx) {
+                v.x += __shfl_xor_sync(0xffffffffu, v.x, off);
+                v.y += __shfl_xor_sync(0xffffffffu, v.y, off);
+            } else {
+                v += __shfl_xor_sync(0xffffffffu, v, off);
+            }
+        }
+        if ((t & 31) == 0) red[t >> 5] = v;
+        __syncthreads();
+        if (t == 0) {
+            T sum = Sc<T>::zero();
+            for (int w = 0; w < DIR_THREADS / 32; w++) sum = Sc<T>::add(sum, red[w]);
+            s_total = sum;
+        }
+        __syncthreads();
+        T total = s_total;
+        if constexpr (PEER) {
+            if (sc.peer) total = peer_allreduce<T>(sc.peer, total);
+        }
         if (t == 0) {
             sc.dq[0] = total;
             sc.ticket[TK_SPMV] = 0;

@@ -27,6 +27,7 @@
 #include "../../include/clcg.h"
 #include "kernels.cuh"
 #include "cg2.cuh"
+#include "pcg.cuh"
 
 using namespace cgb;
 
@@ -84,7 +85,9 @@ struct cgb200_ctx {
     PatWindows win;
     int cg2 = 1;                 // option: use the two-kernel iteration when the matrix allows it (k = 1)
     int cg2_ok = 0;              // the dictionary's offsets fit the window plan
-    int cg2_blocks = 0;          // option: blocks per SM of dir_spmv (0: what fits)
+    int cg2_stages = 0;          // option: stages of dir_spmv's TMA ring (0: 3, or what fits)
+    void *d_dinv = nullptr;      // [n] inverse diagonal of the preconditioned solve (caller's, or 1/diag(A))
+    int dinv_is_jacobi = 0;      // d_dinv currently holds 1/diag(A) of the resident matrix
     int *d_pspos = nullptr;      // [npat][PAT_MAXLEN] staging position of every pattern entry
     unsigned *d_pat_mask = nullptr, *d_chunk_mask = nullptr;   // windows used per pattern / per chunk of rows
     int irregular = 0;           // row lengths vary wildly inside a tile (power-law graphs), see upload_matrix
@@ -394,9 +397,15 @@ template <typename T> struct Engine {
     // Window plan of the two-kernel iteration (cg2.cuh): the distinct column offsets of the dictionary, merged
     // into windows when they are closer than a chunk of rows, and for every pattern entry its position in
     // the staged array.  Fails softly (cg2_ok = 0: the three-kernel iteration stays in use).
-    static size_t cg2_smem_bytes(const cgb200_ctx *c, int stride) {
-        return (size_t)(PAT_THREADS + c->npat * stride + c->win.total) * sizeof(T) + (size_t)c->npat * stride * sizeof(int) +
-               (size_t)c->npat * sizeof(int) + 16;
+    static size_t cg2_smem_bytes(const cgb200_ctx *c, int stride, int nstage) {
+        return 128 + (size_t)(32 + c->npat * stride + (size_t)nstage * 2 * c->win.total) * sizeof(T) +
+               (size_t)c->npat * stride * sizeof(int) + (size_t)c->npat * sizeof(int) + 16;
+    }
+    // as many stages as fit 226 KB of shared memory (one block per SM), at most DIR_MAX_STAGES; < 2: no two-kernel path
+    static int cg2_stages(const cgb200_ctx *c, int stride) {
+        int ns = c->cg2_stages > 0 ? std::min(c->cg2_stages, DIR_MAX_STAGES) : 3;
+        while (ns >= 2 && cg2_smem_bytes(c, stride, ns) > 226 * 1024) ns--;
+        return ns;
     }
     static int pat_stride(const cgb200_ctx *c) { return c->max_row <= 8 ? 8 : (c->max_row <= 16 ? 16 : 32); }
     static int build_windows(cgb200_ctx *c) {
@@ -446,8 +455,8 @@ template <typename T> struct Engine {
         };
         w.diag = spos_of(0).second;
         c->win = w;
-        // the staged array, the table and the reduction scratch must leave room for >= 2 blocks per SM
-        if (cg2_smem_bytes(c, pat_stride(c)) > 100 * 1024) return 0;
+        // two stages of both vectors' windows, the table and the reduction scratch must fit one SM
+        if (cg2_stages(c, pat_stride(c)) < 2) return 0;
         std::vector<int> spos((size_t)npat * PAT_MAXLEN);
         std::vector<unsigned> pmask(npat);
         for (int p = 0; p < npat; p++) {
@@ -485,22 +494,22 @@ template <typename T> struct Engine {
     template <bool PEER>
     static int launch_dir_spmv(cgb200_ctx *c, const CgScalars<T> &sc) {
         const int stride = pat_stride(c);
-        const size_t smem = cg2_smem_bytes(c, stride);
+        const int nstage = cg2_stages(c, stride);
+        const size_t smem = cg2_smem_bytes(c, stride, nstage);
         auto launch = [&](auto kern) -> int {
             const void *key = (const void *)kern;
-            if (c->occ.find(key) == c->occ.end())
-                CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(100 * 1024 + 1024)));
-            const int bps = c->blocks_per_sm;
-            if (c->cg2_blocks > 0) c->blocks_per_sm = c->cg2_blocks;
-            int grid = persistent_grid(c, kern, PAT_THREADS, smem, c->pat_chunks);
-            c->blocks_per_sm = bps;
+            if (c->occ.find(key) == c->occ.end()) {
+                CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+                c->occ[key] = 1;
+            }
+            int grid = std::min(c->sm_count, c->pat_chunks);       // one block per SM, chunks dealt round-robin
             const int per = (c->pat_chunks + grid - 1) / grid;
             grid = (c->pat_chunks + per - 1) / per;
             c->spmv_grid_last = grid;
-            CU(launch_kernel(kern, dim3(grid), dim3(PAT_THREADS), smem, c->stream, (c->pdl & 1) != 0, c->n, c->n + c->extra_cols,
-                             c->pat_chunks, c->npat, c->win, (const unsigned short *)c->d_pat, (const unsigned *)c->d_chunk_mask,
-                             (const int *)c->d_plen, (const int *)c->d_pspos, (const T *)c->d_pval, (T *)c->x, (T *)c->q,
-                             (T *)c->r, (T *)c->r2, (T *)c->d, (T *)c->d2, sc));
+            CU(launch_kernel(kern, dim3(grid), dim3(DIR_THREADS), smem, c->stream, (c->pdl & 1) != 0, c->n, c->n + c->extra_cols,
+                             c->pat_chunks, c->npat, nstage, c->win, (const unsigned short *)c->d_pat,
+                             (const unsigned *)c->d_chunk_mask, (const int *)c->d_plen, (const int *)c->d_pspos,
+                             (const T *)c->d_pval, (T *)c->x, (T *)c->q, (T *)c->r, (T *)c->r2, (T *)c->d, (T *)c->d2, sc));
             c->launches++;
             return 0;
         };
@@ -1108,6 +1117,152 @@ template <typename T> struct Engine {
         return 0;
     }
 
+    // ---- Jacobi-preconditioned CG, one right-hand side (pcg.cuh; helmFE_var.py:546-586) ------------------
+    static int pcg_iteration(cgb200_ctx *c, const CgScalars<T> &sc) {
+        const size_t n = (size_t)c->n;
+        TRY(spmv<true>(c, 1, (const T *)c->d, (T *)c->q, sc));                                   // q = A p, p.q
+        const int grid = (int)std::min<long long>((long long)c->sm_count * 8, ((long long)n + 255) / 256);
+        pcg_update_xr_kernel<T><<<grid, 256, 0, c->stream>>>(n, (const T *)c->d, (const T *)c->q, (const T *)c->d_dinv,
+                                                             (T *)c->x, (T *)c->r, sc);
+        pcg_update_d_kernel<T><<<grid, 256, 0, c->stream>>>(n, (const T *)c->r, (const T *)c->d_dinv, (T *)c->d, sc);
+        c->launches += 2;
+        return 0;
+    }
+    static int solve_pcg_column(cgb200_ctx *c, const T *b, T *x, int maxit, double tol, int *iters, double *resnorm,
+                                double *hist, int hist_stride_k, int hist_col, int *flags, double ms[4]) {
+        TRY(ensure_workspace(c, 1));
+        const size_t n = (size_t)c->n, bytes = n * sizeof(T);
+        const int ncomp = Sc<T>::cplx ? 2 : 1;
+        int hist_cap = 0;
+        if (hist) {
+            hist_cap = maxit + 1;
+            const size_t need = (size_t)hist_cap * ncomp;
+            if (need > c->hist_doubles) {
+                if (c->d_hist) cudaFree(c->d_hist);
+                c->d_hist = nullptr;
+                c->hist_doubles = 0;
+                drop_graph(c);
+                CU(cudaMalloc(&c->d_hist, need * sizeof(double)));
+                c->hist_doubles = need;
+            }
+            CU(cudaMemsetAsync(c->d_hist, 0, need * sizeof(double), c->stream));
+        }
+        CgScalars<T> sc = scalars(c, 1, tol, hist_cap);
+        const int grid = (int)std::min<long long>((long long)c->sm_count * 8, ((long long)n + 255) / 256);
+        if (2 * grid > c->grid_cap) return fail(CGB200_ERR_UNSUPPORTED, "partial-sum scratch too small");
+        CU(cudaMemcpyAsync((void *)sc.tol, &tol, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        CU(cudaEventRecord(c->ev[0], c->stream));
+        CU(cudaMemcpyAsync(c->d, b, bytes, cudaMemcpyDefault, c->stream));
+        CU(cudaMemcpyAsync(c->x, x, bytes, cudaMemcpyDefault, c->stream));
+        CU(cudaEventRecord(c->ev[1], c->stream));
+        TRY(spmv<false>(c, 1, (const T *)c->x, (T *)c->q, sc));
+        pcg_init_kernel<T><<<grid, 256, 0, c->stream>>>(n, (const T *)c->d, (const T *)c->q, (const T *)c->d_dinv, (T *)c->r,
+                                                        (T *)c->d, sc);
+        c->launches++;
+        CU(cudaEventRecord(c->ev[2], c->stream));
+        int done = 0;
+        const int chunk = std::max(1, c->graph_chunk);
+        auto poll = [&]() -> int {
+            CU(cudaMemcpyAsync(c->h_flag, sc.n_active, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+            CU(cudaStreamSynchronize(c->stream));
+            return *c->h_flag;
+        };
+        if (c->use_graph && maxit >= chunk) {
+            if (!c->graph || c->graph_k != 1 || c->graph_chunk_built != chunk || c->graph_hist_cap != hist_cap || c->graph_cg2 != 2) {
+                drop_graph(c);
+                cudaGraph_t gr = nullptr;
+                const long long before = c->launches;
+                CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+                int rc = 0;
+                for (int i = 0; i < chunk && rc == 0; i++) rc = pcg_iteration(c, sc);
+                cudaError_t ce = cudaStreamEndCapture(c->stream, &gr);
+                c->graph_nodes = c->launches - before;
+                c->launches = before;
+                if (rc < 0) return rc;
+                if (ce != cudaSuccess) return fail(CGB200_ERR_CUDA, "graph capture: %s", cudaGetErrorString(ce));
+                ce = cudaGraphInstantiate(&c->graph, gr, 0);
+                cudaGraphDestroy(gr);
+                if (ce != cudaSuccess) return fail(CGB200_ERR_CUDA, "graph instantiate: %s", cudaGetErrorString(ce));
+                c->graph_cg2 = 2;          // a PCG graph
+                c->graph_k = 1;
+                c->graph_chunk_built = chunk;
+                c->graph_hist_cap = hist_cap;
+            }
+            while (done + chunk <= maxit) {
+                CU(cudaGraphLaunch(c->graph, c->stream));
+                c->graph_launches++;
+                c->launches += c->graph_nodes;
+                done += chunk;
+                if (tol > 0) {
+                    int live = 0;
+                    TRY(live = poll());
+                    if (live == 0) { done = maxit; break; }
+                }
+            }
+        }
+        for (; done < maxit; done++) {
+            TRY(pcg_iteration(c, sc));
+            if (tol > 0 && (done % chunk) == chunk - 1) {
+                int live = 0;
+                TRY(live = poll());
+                if (live == 0) break;
+            }
+        }
+        CU(cudaEventRecord(c->ev[3], c->stream));
+        CU(cudaMemcpyAsync(x, c->x, bytes, cudaMemcpyDefault, c->stream));
+        CU(cudaEventRecord(c->ev[4], c->stream));
+        T rr;
+        int st = 0, its = 0;
+        CU(cudaMemcpyAsync(&rr, sc.rr, sizeof(T), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(&st, sc.state, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(&its, sc.iters, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        std::vector<double> hh;
+        if (hist) {
+            hh.resize((size_t)hist_cap * ncomp);
+            CU(cudaMemcpyAsync(hh.data(), c->d_hist, hh.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        }
+        CU(cudaStreamSynchronize(c->stream));
+        CU(cudaGetLastError());
+        for (int i = 0; i < 4; i++) {
+            float f = 0;
+            CU(cudaEventElapsedTime(&f, c->ev[i], c->ev[i + 1]));
+            ms[i] += f;
+        }
+        if (st == ST_ACTIVE) {
+            its = maxit;
+            if (tol > 0) *flags |= CGB200_FLAG_MAXIT;
+        }
+        if (st == ST_BREAKDOWN) *flags |= CGB200_FLAG_BREAKDOWN;
+        if (iters) *iters = its;
+        if (resnorm) *resnorm = sqrt(Sc<T>::abs(rr));
+        if (hist)
+            for (int it = 0; it < hist_cap; it++)
+                for (int m = 0; m < ncomp; m++)
+                    hist[((size_t)it * hist_stride_k + hist_col) * ncomp + m] = hh[(size_t)std::min(it, its) * ncomp + m];
+        return 0;
+    }
+    static int solve_pcg_api(cgb200_ctx *c, const void *dinv, const void *b, void *x, int k, int maxit, double tol, int *iters,
+                             double *resnorm, double *hist) {
+        const size_t n = (size_t)c->n;
+        if (!c->d_dinv) CU(cudaMalloc(&c->d_dinv, n * sizeof(T) + 64));
+        if (dinv) {
+            CU(cudaMemcpyAsync(c->d_dinv, dinv, n * sizeof(T), cudaMemcpyDefault, c->stream));
+            c->dinv_is_jacobi = 0;
+        } else if (!c->dinv_is_jacobi) {
+            jacobi_dinv_kernel<T><<<c->sm_count * 8, 256, 0, c->stream>>>(c->n, (const T *)c->d_vals, c->d_rowptr, c->d_cols,
+                                                                          (T *)c->d_dinv);
+            c->launches++;
+            c->dinv_is_jacobi = 1;
+        }
+        int flags = 0;
+        double ms[4] = {0, 0, 0, 0};
+        for (int col = 0; col < k; col++)
+            TRY(solve_pcg_column(c, (const T *)b + (size_t)col * n, (T *)x + (size_t)col * n, maxit, tol, iters ? iters + col : nullptr,
+                                 resnorm ? resnorm + col : nullptr, hist, k, col, &flags, ms));
+        for (int i = 0; i < 4; i++) c->last_ms[i] = ms[i];
+        return flags;
+    }
+
     // ---- one kernel of the CG loop, launched `reps` times back to back, timed with CUDA
     // events on the handle's stream (for the roofline lines of bench.py).  Must follow a solve
     // with the same k (the work vectors then hold sane values).  Leaves the state unusable
@@ -1316,6 +1471,7 @@ static int upload_matrix(cgb200_ctx *c, const void *aValues, const int *aPointer
     const long long nnz = c->nnz;
     const size_t vs = c->vsize;
     drop_graph(c);
+    c->dinv_is_jacobi = 0;
     std::vector<int> rp((size_t)n + 1);
     CU(cudaMemcpyAsync(rp.data(), aPointers, ((size_t)n + 1) * sizeof(int), cudaMemcpyDefault, c->stream));
     CU(cudaStreamSynchronize(c->stream));
@@ -1491,7 +1647,7 @@ int cgb200_destroy(cgb200_handle c) {
     if (c->d_trace) cudaFree(c->d_trace);
     if (c->d_runs) cudaFree(c->d_runs);
     for (void *b : {c->d_pat, c->d_pat_table, c->d_pat_build, c->d_plen, c->d_poff, c->d_pval, (void *)c->d_pat_chunks,
-                    (void *)c->d_pspos, (void *)c->d_pat_mask, (void *)c->d_chunk_mask})
+                    (void *)c->d_pspos, (void *)c->d_pat_mask, (void *)c->d_chunk_mask, c->d_dinv})
         if (b) cudaFree(b);
     if (c->d_tiles) cudaFree(c->d_tiles);
     if (c->d_long) cudaFree(c->d_long);
@@ -1538,7 +1694,7 @@ static int *option_slot(cgb200_handle c, const char *key) {
     if (!strcmp(key, "pattern")) return &c->pattern;
     if (!strcmp(key, "pattern_regs")) return &c->pattern_regs;
     if (!strcmp(key, "cg2")) return &c->cg2;
-    if (!strcmp(key, "cg2_blocks")) return &c->cg2_blocks;
+    if (!strcmp(key, "cg2_stages")) return &c->cg2_stages;
     if (!strcmp(key, "cg2_ok")) return &c->cg2_ok;          // read-only: the dictionary's offsets fit the window plan
     if (!strcmp(key, "patterns")) return &c->npat;        // read-only: distinct row patterns found (0: CSR kernels in use)
     if (!strcmp(key, "spmm_schedule")) return &c->spmm_schedule;
@@ -1617,6 +1773,15 @@ int cgb200_solve(cgb200_handle c, const void *b, void *x, int k, int max_iterati
     if (!c->matrix_ok) return fail(CGB200_ERR_ARG, "the handle holds no valid matrix (the last upload was rejected)");
     DeviceGuard guard(c->device);
     return DISPATCH(c, E::solve_api(c, b, x, k, max_iterations, tol, iterations, relres, delta_hist, layout));
+}
+
+int cgb200_solve_pcg(cgb200_handle c, const void *dinv, const void *b, void *x, int k, int max_iterations, double tol,
+                     int *iterations, double *resnorm, double *rr_hist) {
+    if (!c || !b || !x || k < 1 || max_iterations < 0 || !(tol >= 0)) return fail(CGB200_ERR_ARG, "bad pcg arguments");
+    if (!c->matrix_ok) return fail(CGB200_ERR_ARG, "the handle holds no valid matrix (the last upload was rejected)");
+    if (c->extra_cols) return fail(CGB200_ERR_UNSUPPORTED, "preconditioned CG is not available on a row-block shard");
+    DeviceGuard guard(c->device);
+    return DISPATCH(c, E::solve_pcg_api(c, dinv, b, x, k, max_iterations, tol, iterations, resnorm, rr_hist));
 }
 
 int cgb200_time_kernel(cgb200_handle c, int which, int k, int reps, double *ms_avg) {

@@ -181,3 +181,61 @@ class Matrix:
         check(lib().cgb200_last_timing(self._h, ms))
         info.timing_ms = dict(zip(("h2d", "init", "iterations", "d2h"), list(ms)))
         return x, info
+
+    def solve_pcg(self, b, x=None, k=1, M_inv_diag=None, max_iterations=1000, tol=0.0, history=False):
+        """Jacobi-preconditioned CG (`cgb200_solve_pcg`; the reference's helmFE_var.PCG with M an inverse diagonal).
+        M_inv_diag: n values, None = 1 / diag(A).  tol is ABSOLUTE on sqrt|r.r|, as the reference stops.
+        Returns (x, SolveInfo) with relres = sqrt|r.r| at exit and delta_hist = the history of r.r."""
+        if isinstance(b, np.ndarray):
+            b = np.ascontiguousarray(b, dtype=self.dtype)
+            if x is None:
+                x = np.zeros(self.n * k, dtype=self.dtype)
+            elif x.dtype != self.dtype or not x.flags["C_CONTIGUOUS"]:
+                raise TypeError("x must be a C-contiguous array of the matrix dtype")
+        elif x is None:
+            raise ValueError("x is required for device pointers")
+        if isinstance(M_inv_diag, np.ndarray):
+            M_inv_diag = np.ascontiguousarray(M_inv_diag, dtype=self.dtype)
+            if M_inv_diag.size != self.n:
+                raise ValueError("M_inv_diag must hold n values")
+        its = np.zeros(k, dtype=np.intc)
+        res = np.zeros(k, dtype=np.float64)
+        ncomp = 2 if np.dtype(self.dtype).kind == "c" else 1
+        hist = np.zeros((max_iterations + 1, k, ncomp)) if history else None
+        rc = check(lib().cgb200_solve_pcg(self._h, ptr(M_inv_diag), ptr(b), ptr(x), int(k), int(max_iterations), float(tol),
+                                          ptr(its), ptr(res), ptr(hist)))
+        info = SolveInfo()
+        info.flags, info.iterations, info.relres = rc, its, res
+        if hist is not None:
+            hist = hist[..., 0] + 1j * hist[..., 1] if ncomp == 2 else hist[..., 0]
+        info.delta_hist = hist
+        ms = (ctypes.c_double * 4)()
+        check(lib().cgb200_last_timing(self._h, ms))
+        info.timing_ms = dict(zip(("h2d", "init", "iterations", "d2h"), list(ms)))
+        return x, info
+
+
+def PCG(A, b, M=None, x=None, tol=1e-6, maxit=1000, verbose=False, device=0):
+    """The calling convention of the reference's `PCG(A, b, M, x, tol, maxit)` (helmFE_var.py:546-586) on the B200:
+    A scipy sparse, M None (plain CG recurrence with the PCG stopping rule), a 1-D array of the inverse diagonal, or a
+    scipy sparse matrix with one entry per row (what the reference multiplies with, :559-563).  Returns (x, i) with i
+    the index of the last iteration performed, like the reference."""
+    import scipy.sparse as sp
+    A = sp.csr_matrix(A)
+    A.sort_indices()
+    dt = np.result_type(A.dtype, np.asarray(b).dtype, np.complex128 if x is None else np.asarray(x).dtype)   # x defaults to complex zeros (:553)
+    dt = np.dtype(dt)
+    if M is None:
+        dinv = np.ones(A.shape[0], dtype=dt)
+    elif sp.issparse(M):
+        if M.nnz > M.shape[0]:
+            raise NotImplementedError("only an inverse-diagonal M runs on the device (helmFE_var.py:560-561 would call spsolve)")
+        dinv = np.asarray(sp.csr_matrix(M).diagonal(), dtype=dt)
+    elif callable(M) or isinstance(M, float):
+        raise NotImplementedError("callable / inner-CG preconditioners (helmFE_var.py:564-567) are host-side constructs")
+    else:
+        dinv = np.asarray(M, dtype=dt)
+    x0 = np.zeros(A.shape[0], dtype=dt) if x is None else np.ascontiguousarray(x, dtype=dt).copy()
+    with Matrix(A.data.astype(dt), A.indptr, A.indices, n=A.shape[0], device=device) as Mx:
+        xs, info = Mx.solve_pcg(np.asarray(b, dtype=dt), x=x0, M_inv_diag=dinv, max_iterations=int(maxit), tol=float(tol))
+    return xs, max(int(info.iterations[0]) - 1, 0)

@@ -104,7 +104,7 @@ CGB200_API int cgb200_set_stream(cgb200_handle h, void *cuda_stream);
  *   "cg2"            1 (default): k = 1 on a matrix with a row-pattern dictionary whose column offsets fit a window
  *                    plan runs the TWO-kernel iteration (csrc/cg2.cuh: direction update folded into the SpMV's
  *                    gather, x lagging one update, 9 vector passes instead of 11); "cg2_ok" (read-only) tells
- *                    whether the matrix qualifies; "cg2_blocks" caps the blocks per SM of its first kernel
+ *                    whether the matrix qualifies; "cg2_stages" (2..4, default 3) sets the depth of its TMA ring
  *   "spmm_schedule"  0 (default) | 1: k > 1 on a matrix with grid structure (few fixed column offsets) visits rows
  *                    patch by patch for L1 reuse of the gathered rows (spmm_sched_kernel)
  *   "trace"          n > 0: the loop kernels stamp %globaltimer into an 8-slot record per iteration for the
@@ -130,6 +130,18 @@ CGB200_API int cgb200_spmv(cgb200_handle h, const void *x, void *y, int k, int l
  * Blocks until x is complete. */
 CGB200_API int cgb200_solve(cgb200_handle h, const void *b, void *x, int k, int max_iterations,
                  double tol, int *iterations, double *relres, double *delta_hist, int layout);
+
+/* Jacobi-preconditioned CG -- the reference's PCG (helmFE_var.py:546-586) with M an inverse diagonal, which the
+ * reference applies as a sparse matrix with one entry per row (:559-563); its report names preconditioning as
+ * the path's own future work.  z = dinv*r ; rho = r.z ; p = z + (rho/rho_prev) p ; alpha = rho/(p.q).
+ *   dinv   n values of the matrix dtype (host or device pointer), shared by all right-hand sides;
+ *          NULL: 1 / diag(A) of the resident matrix, extracted on the device
+ *   tol    ABSOLUTE, on sqrt|r.r| as the reference stops (:579-583); 0: exactly max_iterations iterations
+ * Vectors in the cg() layout (RHS c at c*n); the k systems are solved one after the other.
+ * Optional outputs: iterations[k] (iterations performed; the reference returns the index of the last one, i.e.
+ * one less), resnorm[k] = sqrt|r.r| at exit, rr_hist = (max_iterations+1) * k * (1|2) doubles of r.r. */
+CGB200_API int cgb200_solve_pcg(cgb200_handle h, const void *dinv, const void *b, void *x, int k, int max_iterations,
+                                double tol, int *iterations, double *resnorm, double *rr_hist);
 
 /* Milliseconds of the last cgb200_solve() on this handle, from CUDA events on its
  * stream: [0] inputs to HBM (+ layout change), [1] initialisation, [2] iterations,

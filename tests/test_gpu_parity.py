@@ -640,16 +640,23 @@ def test_trace_timeline(gpu):
     A, b = system("poisson", 64, np.float64)
     with gpu.Matrix.from_scipy(A) as M:
         M.set_option("solver", 1)
-        M.set_option("trace", 32)
-        M.solve(b, max_iterations=32)
-        tr = M.read_trace(32).astype(np.int64)
-        M.set_option("trace", 0)
-        x, _ = M.solve(b, max_iterations=32)
-    ev = tr[:, :7]
+        tr = {}
+        for cg2 in (0, 1):
+            M.set_option("cg2", cg2)
+            M.set_option("trace", 32)
+            M.solve(b, max_iterations=32)
+            tr[cg2] = M.read_trace(32).astype(np.int64)
+            M.set_option("trace", 0)
+            x, _ = M.solve(b, max_iterations=32)
+    ev = tr[0][:, :7]                                     # three kernels per iteration
     assert (ev > 0).all()
     assert (np.diff(ev, axis=1) >= 0).all()              # events of one iteration are in order
     assert (ev[1:, 0] >= ev[:-1, 6]).all()               # the next SpMV starts after the direction update started
-    assert (tr[:, 7] == 0).all()                         # no halo on one GPU
+    assert (tr[0][:, 7] == 0).all()                      # no halo on one GPU
+    ev = tr[1][:, :6]                                     # two kernels per iteration: no direction-update kernel
+    assert (ev > 0).all() and (tr[1][:, 6:] == 0).all()
+    assert (np.diff(ev, axis=1) >= 0).all()
+    assert (ev[1:, 0] >= ev[:-1, 5]).all()               # the next dir_spmv starts after the residual update finished
 
 
 # ---------------------------------------------------------------------------------------
