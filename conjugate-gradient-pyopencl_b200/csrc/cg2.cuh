@@ -148,6 +148,7 @@ cg2_dir_spmv_kernel(int n, int ncols, int nchunks, int npat, int nstage, PatWind
     const T beta = sc.beta[0], alpha_prev = sc.alpha[0];
     const int count = ((int)blockIdx.x < nchunks) ? (nchunks - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
     T dot = Sc<T>::zero();
+    bool pushed = false;        // this thread stored into a peer's halo: fenced (system scope) before the block's arrival
 
     if (producer) {
         // ---- one elected thread: the windows of this block's i-th chunk, both vectors, into stage i % nstage,
@@ -208,7 +209,7 @@ cg2_dir_spmv_kernel(int n, int ncols, int nchunks, int npat, int nstage, PatWind
                     *dst = Sc<T>::fma(beta, dold[row], r[row]);
                     stored = true;
                 }
-                if (stored) __threadfence_system();
+                pushed = stored;
             }
         }
         // The pattern number and x of a thread's rows are requested one chunk ahead.  The loads are unconditional
@@ -303,6 +304,10 @@ cg2_dir_spmv_kernel(int n, int ncols, int nchunks, int npat, int nstage, PatWind
         }
     }
 
+    // (the stores into the peers' halos were issued before the chunk loop: by now they have long been acknowledged and
+    //  the fence that orders them before this block's arrival returns at once -- right after the stores it cost a
+    //  full NVLink round trip in every thread)
+    if (pushed) __threadfence_system();
     // block sum in a fixed order: lanes by butterfly, then the warps one after the other
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
@@ -360,14 +365,18 @@ cg2_dir_spmv_kernel(int n, int ncols, int nchunks, int npat, int nstage, PatWind
 
 // alpha = delta_new / dq ; r' = r - alpha q (into the other residual buffer) ; delta_old = delta_new ;
 // delta_new = r'.r' ; beta ; convergence bookkeeping.      clcg.c:326-392
+//
+// The tail of this kernel is on the critical path of every iteration (on shards it also carries the all-reduce), so
+// everything the last block needs from memory -- the column's state, delta_0, the tolerance -- is read by every
+// block up front, next to the scalars alpha needs anyway; after the sum is known the tail is arithmetic and stores.
 template <typename T, int V, bool PEER>
 __global__ void __launch_bounds__(256)
 cg2_update_r_kernel(size_t npacks, size_t nelem, const T *__restrict__ q, T *r0, T *r1, CgScalars<T> sc) {
     pdl_wait();
     if (sc.pdl_early) pdl_trigger();
     if (*sc.n_active == 0) return;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    T *smem = reinterpret_cast<T *>(smem_raw);
+    __shared__ T s_red[8];
+    __shared__ T s_total;
     using P = Pack<T, V>;
     const int t = threadIdx.x;
     const int it = *sc.it;
@@ -375,14 +384,18 @@ cg2_update_r_kernel(size_t npacks, size_t nelem, const T *__restrict__ q, T *r0,
     const bool odd = (it & 1) != 0;
     const T *__restrict__ r = odd ? r1 : r0;
     T *__restrict__ rn = odd ? r0 : r1;
+    const int state0 = sc.state[0];
+    const T delta_cur = sc.delta_new[0];
+    const double delta0 = sc.delta0[0], tol = *sc.tol;
     T alpha = Sc<T>::zero();
-    if (sc.state[0] == ST_ACTIVE) {
+    if (state0 == ST_ACTIVE) {
         const T den = sc.dq[0];
-        if (!Sc<T>::is_zero(den)) alpha = Sc<T>::div(sc.delta_new[0], den);
+        if (!Sc<T>::is_zero(den)) alpha = Sc<T>::div(delta_cur, den);
     }
+    bool pushed = false;
     if constexpr (PEER) {
         if (sc.peer && sc.peer->world > 1)
-            peer_push_rows<T>(sc.peer, odd ? 2 : 3, [&](int row) { return Sc<T>::fnma(alpha, q[row], r[row]); });
+            pushed = peer_push_rows<T>(sc.peer, odd ? 2 : 3, [&](int row) { return Sc<T>::fnma(alpha, q[row], r[row]); });
     }
     T acc[V];
 #pragma unroll
@@ -408,25 +421,74 @@ cg2_update_r_kernel(size_t npacks, size_t nelem, const T *__restrict__ q, T *r0,
     }
 #pragma unroll
     for (int v = 1; v < V; v++) acc[0] = Sc<T>::add(acc[0], acc[v]);
-    T one[1] = {acc[0]};
-    block_col_reduce<T, 1>(one, 1, smem);
-    if (publish_and_arrive<T, 1>(smem, 1, 1, sc.partial, sc.ticket + TK_UPDATE)) {
-        if (t == 0) trace_mark<T>(sc, it, TR_XR_ALL_DONE);
-        const T total = cg2_grid_total<T, PEER>(sc, smem);
-        if (t == 0) {
-            update_bookkeep<T>(sc, 0, 1, it + 1, total);
-            // what the next dir_spmv (or finish_x_kernel) needs: the step just taken and the new direction's weight
-            sc.alpha[0] = alpha;
-            T beta = Sc<T>::zero();
-            if (sc.state[0] == ST_ACTIVE) {
-                const T den = sc.delta_old[0];
-                if (!Sc<T>::is_zero(den)) beta = Sc<T>::div(sc.delta_new[0], den);
+    if (pushed) __threadfence_system();         // (see dir_spmv: fenced here, not right after the stores)
+
+    // block sum, then (last block) grid sum, in a fixed order: lanes by butterfly, warps one after the other
+    auto block_sum = [&](T v) -> T {            // valid in thread 0
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            if constexpr (Sc<T>::cplx) {
+                v.x += __shfl_xor_sync(0xffffffffu, v.x, off);
+                v.y += __shfl_xor_sync(0xffffffffu, v.y, off);
+            } else {
+                v += __shfl_xor_sync(0xffffffffu, v, off);
             }
-            sc.beta[0] = beta;
-            *sc.it = it + 1;
-            sc.ticket[TK_UPDATE] = 0;
-            trace_mark<T>(sc, it, TR_XR_END);
         }
+        __syncthreads();
+        if ((t & 31) == 0) s_red[t >> 5] = v;
+        __syncthreads();
+        T sum = Sc<T>::zero();
+        if (t == 0)
+            for (int w = 0; w < 8; w++) sum = Sc<T>::add(sum, s_red[w]);
+        return sum;
+    };
+    const T mine = block_sum(acc[0]);
+    __shared__ int s_last;
+    if (t == 0) {
+        sc.partial[blockIdx.x] = mine;
+        __threadfence();
+        s_last = (atomicAdd(sc.ticket + TK_UPDATE, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!s_last) return;
+    if (t == 0) trace_mark<T>(sc, it, TR_XR_ALL_DONE);
+    __threadfence();
+    T v = Sc<T>::zero();
+    for (int b = t; b < (int)gridDim.x; b += 256) v = Sc<T>::add(v, ld_cg(sc.partial + b));
+    v = block_sum(v);
+    if (t == 0) s_total = v;
+    __syncthreads();
+    T total = s_total;
+    if constexpr (PEER) {
+        if (sc.peer) total = peer_allreduce<T>(sc.peer, total);
+    }
+    if (t == 0) {
+        // delta shuffle (clcg.c:350-356), convergence test, history: update_bookkeep with the operands already in registers
+        const int it1 = it + 1;
+        T beta = Sc<T>::zero();
+        if (state0 == ST_ACTIVE) {
+            sc.delta_old[0] = delta_cur;
+            sc.delta_new[0] = total;
+            const double a = Sc<T>::abs(total);
+            int st = ST_ACTIVE;
+            if (!Sc<T>::finite(total)) st = ST_BREAKDOWN;
+            else if (a == 0.0 || (tol > 0.0 && sqrt(a / delta0) < tol)) st = ST_CONVERGED;
+            if (st != ST_ACTIVE) {
+                sc.state[0] = st;
+                sc.iters[0] = it1;
+                *sc.n_active = 0;
+            } else if (!Sc<T>::is_zero(delta_cur)) {
+                beta = Sc<T>::div(total, delta_cur);
+            }
+        }
+        if (sc.hist && it1 < sc.hist_cap)
+            Sc<T>::to_double2(state0 == ST_ACTIVE ? total : delta_cur, sc.hist + (size_t)it1 * (Sc<T>::cplx ? 2 : 1));
+        // what the next dir_spmv (or finish_x_kernel) needs: the step just taken and the new direction's weight
+        sc.alpha[0] = alpha;
+        sc.beta[0] = beta;
+        *sc.it = it1;
+        sc.ticket[TK_UPDATE] = 0;
+        trace_mark<T>(sc, it, TR_XR_END);
     }
 }
 

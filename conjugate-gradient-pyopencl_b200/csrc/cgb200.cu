@@ -521,7 +521,7 @@ template <typename T> struct Engine {
     static int launch_update_r(cgb200_ctx *c, const CgScalars<T> &sc) {
         auto kern = cg2_update_r_kernel<T, VW, PEER>;
         const int block = 256;
-        const size_t smem = (size_t)block * sizeof(T);
+        const size_t smem = 0;
         const size_t nelem = (size_t)c->n, npacks = nelem / VW;
         const int grid = persistent_grid(c, kern, block, smem, (long long)((npacks + block - 1) / block));
         CU(launch_kernel(kern, dim3(grid), dim3(block), smem, c->stream, (c->pdl & 2) != 0, npacks, nelem, (const T *)c->q,

@@ -100,9 +100,11 @@ template <typename T> __device__ __forceinline__ T peer_allreduce(PeerComm *pc, 
     const unsigned long long tag = (seq & 0xffffffffull) << 32;
     const int parity = (int)(seq & 1);
     if (t < pc->world) {
-        // release: whatever this GPU's blocks stored into peers' memory before they arrived at the kernel's ticket
-        // (halo entries, cg2.cuh) is ordered before the words below at system scope
-        __threadfence_system();
+        // Ordering of the halo entries the blocks of this kernel stored into the peers' vectors (cg2.cuh) against the
+        // words below: every storing thread executed a system-scope fence after its stores and before its block
+        // arrived at the kernel's ticket, i.e. those stores were performed at the peer before the last block --
+        // this one -- even started.  (A second system fence here, in front of the words, cost ~2 us per
+        // all-reduce: profiles/r02_trace_n2_*.txt.)
         double v[2] = {0.0, 0.0};
         Sc<T>::to_double2(local, v);
         PeerSlot *dst = pc->slots[t] + (size_t)parity * pc->world + pc->rank;
@@ -124,7 +126,7 @@ template <typename T> __device__ __forceinline__ T peer_allreduce(PeerComm *pc, 
             if (ok) break;
             if (++spins > (1ull << 31)) __trap();
         }
-        __threadfence_system();     // acquire: the peers' earlier stores into this GPU's halos are visible to what follows
+        // (what the peers stored into this GPU's halos is read by the NEXT kernel: the kernel boundary orders it)
         s_val[0][t] = __longlong_as_double((long long)(((w[1] & 0xffffffffull) << 32) | (w[0] & 0xffffffffull)));
         s_val[1][t] = NW == 4 ? __longlong_as_double((long long)(((w[3] & 0xffffffffull) << 32) | (w[2] & 0xffffffffull))) : 0.0;
     }
@@ -161,7 +163,7 @@ __device__ __forceinline__ void peer_wait_halo(const PeerComm *pc) {
 // `which` (PeerComm::vec).  Grid-strided over the send list, run by every block ahead of its own work so
 // that the NVLink transfer overlaps the rest of the kernel.
 template <typename T, typename F>
-__device__ __forceinline__ void peer_push_rows(const PeerComm *pc, int which, F value_of_row) {
+__device__ __forceinline__ bool peer_push_rows(const PeerComm *pc, int which, F value_of_row) {
     const int total = pc->send_off[pc->world];
     bool stored = false;
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
@@ -171,7 +173,9 @@ __device__ __forceinline__ void peer_push_rows(const PeerComm *pc, int which, F 
         *dst = value_of_row(pc->send_idx[e]);
         stored = true;
     }
-    if (stored) __threadfence_system();     // ordered before this block's arrival at the kernel's ticket
+    // The caller fences (__threadfence_system) before its block arrives at the kernel's ticket -- at the END of its
+    // work, when the stores have long been acknowledged, not here where the fence would wait a full NVLink round trip.
+    return stored;
 }
 
 // Programmatic dependent launch: the three kernels of an iteration are launched with the
@@ -1691,8 +1695,9 @@ init_kernel(size_t npacks, size_t nelem, int k, int kv, const T *b /* may alias 
     for (int v = 0; v < V; v++) acc[v] = Sc<T>::zero();
     // two-kernel iteration on a row-block shard (k = 1; b is then NOT aliased with d): the boundary entries of
     // r0 go straight into the peers' halos of residual buffer 0, which the first dir_spmv reads
+    bool pushed = false;
     if (sc.cg2 && sc.peer && sc.peer->world > 1)
-        peer_push_rows<T>(sc.peer, 2, [&](int row) { return Sc<T>::sub(b[row], q[row]); });
+        pushed = peer_push_rows<T>(sc.peer, 2, [&](int row) { return Sc<T>::sub(b[row], q[row]); });
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t p = (size_t)blockIdx.x * blockDim.x + t; p < npacks; p += stride) {
         const P bv = reinterpret_cast<const P *>(b)[p];
@@ -1719,6 +1724,7 @@ init_kernel(size_t npacks, size_t nelem, int k, int kv, const T *b /* may alias 
 #pragma unroll
         for (int v = 1; v < V; v++) { acc[0] = Sc<T>::add(acc[0], acc[v]); acc[v] = Sc<T>::zero(); }
     }
+    if (pushed) __threadfence_system();
     block_col_reduce<T, V>(acc, kv, smem);
     if (publish_and_arrive<T, V>(smem, kv, k, sc.partial, sc.ticket + TK_INIT)) {
         grid_col_reduce<T, V>(sc.partial, kv, kv, k, smem);

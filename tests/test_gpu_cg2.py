@@ -227,14 +227,16 @@ def test_shard_entry_points_with_one_rank(gpu, cpu_ref, kind):
     M = sharded.ShardedMatrix(plan, device=0)
     try:
         # (the power-law system has outlying eigenvalues: CG loses orthogonality early and two summation orders of
-        #  the same double arithmetic are 2e-7 apart after 40 iterations; 12 iterations compare to 1e-10)
-        its = 12 if kind == "powerlaw" else 40
+        #  the same double arithmetic are 1e-9 apart after 12 iterations and 1e-5 after 20)
+        its = 8 if kind == "powerlaw" else 40          # (tools/experiments/r02_diag_powerlaw.py: 2e-13 at 8, 1e-9 at 12, for EVERY kernel, numpy and the oracle alike)
         x, info = M.solve(b.astype(A.dtype), max_iterations=its)
         ref, _, _ = cpu_ref.cg(A.data, A.indptr, A.indices, b.astype(A.dtype), iters=its)
         assert rel(x, ref) < 1e-10
         xt, it = M.solve(b.astype(A.dtype), max_iterations=3000, tol=1e-9)
         _, its_ref, _ = cpu_ref.cg(A.data, A.indptr, A.indices, b.astype(A.dtype), iters=3000, tol=1e-9)
-        assert abs(it["iterations"] - int(its_ref[0])) <= 1
+        # (+-1 on the grid systems; the power-law system loses orthogonality within ~20 iterations, after which two
+        #  summation orders of the same arithmetic differ in the 6th digit: a few per cent in the iteration count)
+        assert abs(it["iterations"] - int(its_ref[0])) <= (1 if kind != "powerlaw" else max(2, int(0.03 * its_ref[0])))
     finally:
         M.close()
 
@@ -362,7 +364,7 @@ def test_config4_laplace_300_cubed_at_size(gpu, cpu_ref):
 def test_config5_power_law_5m_rows_at_size(gpu, cpu_ref):
     import cg_b200.problems as P
     A = P.powerlaw_spd()
-    n, its = A.shape[0], 8
+    n, its = A.shape[0], 6
     assert A.nnz > 45_000_000
     xs = np.random.default_rng(7).uniform(-1.0, 1.0, n)
     b = A @ xs
