@@ -27,6 +27,8 @@ SIGNATURES = {
     "cg": (_vp, [_i, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i]),
     "cgd": (_vp, [_i, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i]),
     "cgb200_create": (_i, [ctypes.POINTER(_vp), _i, _ll, _vp, _vp, _vp, _i, _i]),
+    "cgb200_create_grid": (_i, [ctypes.POINTER(_vp), _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "cgb200_read_matrix": (_i, [_vp, _vp, _vp, _vp]),
     "cgb200_update": (_i, [_vp, _vp, _vp, _vp]),
     "cgb200_destroy": (_i, [_vp]),
     "cgb200_set_stream": (_i, [_vp, _vp]),

@@ -1486,8 +1486,9 @@ static int upload_matrix(cgb200_ctx *c, const void *aValues, const int *aPointer
         if (len > 32) in_long_rows += len;
     }
     c->matrix_ok = 0;
-    CU(cudaMemcpyAsync(c->d_vals, aValues, (size_t)nnz * vs, cudaMemcpyDefault, c->stream));
-    CU(cudaMemcpyAsync(c->d_cols, aCols, (size_t)nnz * sizeof(int), cudaMemcpyDefault, c->stream));
+    // (device-side assembly, assemble.cuh, hands in the handle's own buffers: nothing to copy then)
+    if (aValues != c->d_vals) CU(cudaMemcpyAsync(c->d_vals, aValues, (size_t)nnz * vs, cudaMemcpyDefault, c->stream));
+    if (aCols != c->d_cols) CU(cudaMemcpyAsync(c->d_cols, aCols, (size_t)nnz * sizeof(int), cudaMemcpyDefault, c->stream));
     CU(cudaMemcpyAsync(c->d_rowptr, rp.data(), ((size_t)n + 1) * sizeof(int), cudaMemcpyHostToDevice, c->stream));
     if (nnz > 0) {
         int *d_bad = c->d_flag;
@@ -1558,11 +1559,15 @@ int cgb200_device_count(void) {
 
 // extra_cols / row_boundary: the row block of a shard has n_halo more columns than rows, and its halo-touching
 // rows are scheduled last (shard.cuh); a plain handle passes 0 / NULL.
+struct GridSpec;       // assemble.cuh
+static int grid_fill(cgb200_ctx *c, const GridSpec *spec);
+
 static int create_ctx(cgb200_handle *out, int n, long long nnz, const void *aValues, const int *aPointers,
-                      const int *aCols, int dtype, int device, int extra_cols, const unsigned char *row_boundary) {
+                      const int *aCols, int dtype, int device, int extra_cols, const unsigned char *row_boundary,
+                      const GridSpec *grid = nullptr) {
     if (!out) return fail(CGB200_ERR_ARG, "out is NULL");
     *out = nullptr;
-    if (n <= 0 || nnz < 0 || !aPointers || (nnz > 0 && (!aValues || !aCols)))
+    if (n <= 0 || nnz < 0 || (!grid && (!aPointers || (nnz > 0 && (!aValues || !aCols)))))
         return fail(CGB200_ERR_ARG, "bad matrix arguments (n=%d nnz=%lld)", n, nnz);
     if (nnz > 0x7fffffffLL) return fail(CGB200_ERR_UNSUPPORTED, "nnz > 2^31-1 (int32 row offsets, as the reference)");
     const size_t vs = dtype_size(dtype);
@@ -1609,7 +1614,13 @@ static int create_ctx(cgb200_handle *out, int n, long long nnz, const void *aVal
     CUB(cudaMemsetAsync(c->d_cols + nnz, 0, 16 * sizeof(int), c->stream));
     CUB(cudaStreamSynchronize(c->stream));
 #undef CUB
-    {
+    if (grid) {
+        // the CSR arrays are GENERATED in the handle's buffers by a kernel (no host assembly, no PCIe upload), then
+        // go through the same validation / schedule / pattern-dictionary set-up as uploaded ones
+        int rc = grid_fill(c, grid);
+        if (rc >= 0) rc = upload_matrix(c, c->d_vals, c->d_rowptr, c->d_cols);
+        if (rc < 0) return bail(rc);
+    } else {
         const int rc = upload_matrix(c, aValues, aPointers, aCols);
         if (rc < 0) return bail(rc);
     }
@@ -1941,3 +1952,4 @@ double *cgd(int size, int nonZeros, const double *aValues, const double *b, cons
 }  // extern "C"
 
 #include "shard.cuh"
+#include "assemble.cuh"

@@ -4,7 +4,7 @@
 //   z = M r ; rho = r.z ; p = z + (rho/rho_prev) p ; q = A p ; alpha = rho / p.q ; x += alpha p ; r -= alpha q ;
 //   stop when sqrt|r.r| < tol (an ABSOLUTE tolerance, :579-583)
 //
-// arranged like the engine's CG loop (the arrangement of oracle/cpu_ref_impl.h::cpu_ref_pcg): the SpMV fused with
+// arranged like the engine's CG loop (the arrangement the tests' C checker of this path follows): the SpMV fused with
 // p.q is the CG kernel unchanged (CSR or row-pattern dictionary); the x/r update also forms z = dinv*r on the
 // fly and reduces BOTH r.z and r.r in the same pass; the direction update recomputes z instead of reading a
 // stored copy.  z is never written: the preconditioner costs one extra read of dinv in each vector kernel

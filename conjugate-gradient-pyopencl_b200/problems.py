@@ -16,7 +16,7 @@ import numpy as np
 import scipy.sparse as sp
 
 __all__ = [
-    "poisson2d", "helmholtz_fe", "rhs_a", "laplace3d", "powerlaw_spd",
+    "poisson2d", "helmholtz_fe", "local_rect", "rhs_a", "laplace3d", "powerlaw_spd",
     "csr_arrays", "algorithmic_bytes", "flops_per_iteration", "DTYPES",
 ]
 
@@ -56,7 +56,7 @@ def poisson2d(N: int) -> sp.csr_matrix:
     return _canonical(A.tocsr())
 
 
-def helmholtz_fe(N: int, omega: float = 12.0, rho: float = 0.15, C=None) -> sp.csr_matrix:
+def helmholtz_fe(N: int, omega: float = 12.0, rho: float = 0.15, C=None, h=None) -> sp.csr_matrix:
     """P1 finite-element Helmholtz matrix S = K - (1+i rho) M_k - i B_k on an N x N grid.
 
     Same discretisation as `helmFE_var(N, omega, C, rho, N, N)`
@@ -73,8 +73,9 @@ def helmholtz_fe(N: int, omega: float = 12.0, rho: float = 0.15, C=None) -> sp.c
     if C is None:
         C = np.ones((N - 1, N - 1))
     C = np.asarray(C, dtype=np.float64)
-    h = 1.0 / (N - 1.0)
-    h2 = h ** 2
+    if h is None:
+        h = 1.0 / (N - 1.0)                        # (an explicit h: a small instance with the mesh width of a big grid,
+    h2 = h ** 2                                    #  from which assemble.helmholtz_fe reads the row classes)
     k = omega / C                                  # (m, j): cell with SW node (j, m)
     kk = np.zeros((N + 1, N + 1))                  # k^2, zero-padded ring: kk[m+1, j+1]
     kk[1:N, 1:N] = k * k
@@ -145,6 +146,16 @@ def helmholtz_fe(N: int, omega: float = 12.0, rho: float = 0.15, C=None) -> sp.c
     A = sp.coo_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))),
                       shape=(N * N, N * N))
     return _canonical(A.tocsr())
+
+
+def local_rect(N, k, eps, eta, L, Nhoriz, Nvert) -> sp.csr_matrix:
+    """The subdomain operator `local_rect(N, k, eps, eta, L, Nhoriz, Nvert)` of the reference's drivers
+    (p_helmholtz.py:1342-1542) on the host: the class table of assemble.local_rect_table expanded with numpy."""
+    try:
+        from . import assemble
+    except ImportError:
+        import assemble
+    return _canonical(assemble.expand(assemble.local_rect_table(N, k, eps, eta, L), Nhoriz, Nvert, 1, np.complex128))
 
 
 def rhs_a(N: int, omega: float) -> np.ndarray:

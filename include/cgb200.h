@@ -172,6 +172,20 @@ CGB200_API int cgb200_debug_read_patterns(cgb200_handle h, int which, void *out,
  * [8] max row length [9] device ordinal */
 CGB200_API int cgb200_info(cgb200_handle h, long long out[10]);
 
+/* Device-side assembly of a constant-coefficient operator on a box grid (csrc/assemble.cuh) -- what the reference's
+ * drivers build with O(n) Python loops on the host: local_rect (p_helmholtz.py:1342-1542), helmFE_var with a constant
+ * wave speed (helmFE_var.py:9-331), Poisson (p_helmholtz.py:1545-1585).  Node (x, y, z) is row (z*ny + y)*nx + x; a
+ * row is determined by the CLASS of its node, (cz*3 + cy)*3 + cx with c = 0 first / 1 interior / 2 last node of the
+ * direction (the `if m == 0 and j == 0 ...` ladder of local_rect).
+ *   class_len[27]           entries of each class's row (classes that cannot occur on the grid are ignored)
+ *   class_dxyz[27][32][3]   neighbour offsets (dx, dy, dz) in {-1, 0, 1}, sorted by (dz, dy, dx) = ascending column
+ *   class_val[27][32]       coefficients, matrix dtype
+ * The CSR arrays are generated straight into HBM by one kernel (nothing of size n on the host or over PCIe) and the
+ * handle is set up like an uploaded matrix.  cgb200_read_matrix copies the arrays out (any pointer may be NULL). */
+CGB200_API int cgb200_create_grid(cgb200_handle *out, int dtype, int device, int nx, int ny, int nz,
+                                  const int *class_len, const int *class_dxyz, const void *class_val);
+CGB200_API int cgb200_read_matrix(cgb200_handle h, void *aValues, int *aPointers, int *aCols);
+
 /* cg()/cgd() with the value type and the device spelled out (device < 0: the calling
  * thread's current CUDA device, or $CGB200_DEVICE).  This is what the pyopencl twin
  * of the reference, cl.py:44-200 `CG` / :203-360 `conjugate_gradient_multi_gpu`

@@ -159,7 +159,23 @@ def clref_fixtures():
         np.savez_compressed(os.path.join(OUT, f"clref_{name}.npz"), **out)
 
 
+def local_rect_fixture():
+    """local_rect_9x7.npz / local_rect_12x12.npz -- what the reference's own `local_rect` (p_helmholtz.py:1342-1542, lifted
+    with `ast` like Poisson) returns for a non-square and a square subdomain, with the call's parameters: the golden
+    arrays of the device-side assembly (conjugate-gradient-pyopencl_b200/assemble.py, csrc/assemble.cuh)."""
+    local_rect = lift(os.path.join(REF, "p_helmholtz.py"), "local_rect", {"zeros": np.zeros, "scipy": scipy})
+    for tag, (N, k, eps, eta, L, Nh, Nv) in (("9x7", (24, 20.0, 20.0, 20.0, 1.0, 9, 7)),
+                                             ("12x12", (40, 12.5, 3.0, 12.5, 2.0, 12, 12))):
+        A = canon(local_rect(N, k, eps, eta, L, Nh, Nv))
+        np.savez_compressed(os.path.join(OUT, f"local_rect_{tag}.npz"), data=A.data, indices=A.indices.astype(np.int32),
+                            indptr=A.indptr.astype(np.int32), params=np.array([N, k, eps, eta, L, Nh, Nv], dtype=np.float64))
+
+
 if __name__ == "__main__":
+    if "--local-rect-only" in sys.argv:
+        local_rect_fixture()
+        sys.exit(0)
     main()
     pcg_fixture()
     clref_fixtures()
+    local_rect_fixture()

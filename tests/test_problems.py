@@ -109,3 +109,57 @@ def test_constant_coefficient_grid_operators_have_a_handful_of_distinct_rows(gol
         assert P.row_patterns(A) == 9 and P.row_patterns(A.astype(np.complex64)) == 9
     R = P.powerlaw_spd(n=3000, nnz_target=30000, max_row=400)
     assert P.row_patterns(R) == R.shape[0]
+
+
+# ---------------------------------------------------------------------------------------
+# class tables of the device-side assembly (conjugate-gradient-pyopencl_b200/assemble.py): the numpy expansion of a table
+# is the checker of csrc/assemble.cuh, so it is pinned here against the reference's own generators
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag", ["9x7", "12x12"])
+def test_local_rect_class_table_reproduces_the_reference_fixture_bit_for_bit(golden_dir, tag):
+    """tests/golden/local_rect_*.npz: what the reference's `local_rect` (p_helmholtz.py:1342-1542) returned in the build
+    container (oracle/make_golden.py::local_rect_fixture)."""
+    import cg_b200.problems as P
+    z = np.load(os.path.join(golden_dir, f"local_rect_{tag}.npz"))
+    N, k, eps, eta, L, Nh, Nv = z["params"]
+    A = P.local_rect(N, k, eps, eta, L, int(Nh), int(Nv))
+    assert np.array_equal(A.indptr, z["indptr"]) and np.array_equal(A.indices, z["indices"])
+    assert np.array_equal(A.data.view(np.float64), z["data"].view(np.float64))
+    assert abs(A - A.T).max() == 0 and P.row_patterns(A) == 9              # complex symmetric, one pattern per node class
+
+
+@pytest.mark.reference
+def test_local_rect_class_table_against_the_reference_function():
+    import ast
+    import scipy
+    import cg_b200.problems as P
+    path = os.path.join("/root/reference", "p_helmholtz.py")
+    tree = ast.parse(open(path).read())
+    fn = next(n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "local_rect")
+    env = {"zeros": np.zeros, "scipy": scipy}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), path, "exec"), env)
+    rng = np.random.default_rng(5)
+    for Nh, Nv in ((4, 4), (5, 9), (16, 3), (11, 11)):
+        N, k, eps, eta, L = int(rng.integers(8, 60)), float(rng.uniform(1, 40)), float(rng.uniform(0, 30)), float(rng.uniform(1, 40)), float(rng.uniform(0.5, 2))
+        R = scipy.sparse.csr_matrix(env["local_rect"](N, k, eps, eta, L, Nh, Nv))
+        R.sum_duplicates()
+        R.sort_indices()
+        A = P.local_rect(N, k, eps, eta, L, Nh, Nv)
+        assert np.array_equal(A.indptr, R.indptr) and np.array_equal(A.indices, R.indices)
+        assert np.array_equal(A.data.view(np.float64), R.data.view(np.float64))
+
+
+def test_class_tables_of_the_other_operators_expand_to_the_host_generators():
+    import cg_b200.problems as P
+    from cg_b200 import assemble
+    same = lambda A, B: (np.array_equal(A.indptr, B.indptr) and np.array_equal(A.indices, B.indices)
+                         and np.array_equal(np.ascontiguousarray(A.data).view(np.float64), np.ascontiguousarray(B.data).view(np.float64)))
+    for N in (4, 7, 33):
+        assert same(assemble.expand(assemble.poisson2d_table(), N, N, 1, np.float64), P.poisson2d(N))
+        T = assemble.table_from_template(P.helmholtz_fe(5, h=1.0 / (N - 1.0)), (5, 5))
+        assert same(assemble.expand(T, N, N, 1, np.complex128), P.helmholtz_fe(N))
+    assert same(assemble.expand(assemble.laplace3d_table(), 6, 6, 5, np.float64), P.laplace3d(6, nz=5))
+    assert same(assemble.expand(assemble.laplace3d_table(), 4, 4, 4, np.float64), P.laplace3d(4))
+    # grids with a direction of 2 or 3 points (no interior / one interior node)
+    assert same(assemble.expand(assemble.poisson2d_table(), 2, 2, 1, np.float64),
+                assemble.expand(assemble.table_from_template(P.poisson2d(4), (4, 4)), 2, 2, 1, np.float64))
