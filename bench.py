@@ -52,6 +52,9 @@ WORKLOADS = {
     # not a BASELINE config: what ONE of 8 GPUs holds of C4 (38 of the 300 z-planes), to tune the shard-sized
     # kernels on a single GPU
     "c4slab8": dict(desc="one eighth of C4: 3-D 7-point Laplacian 300x300x38", dtype="f64", k=1),
+    # ... and one quarter of it (76 planes): on TWO GPUs every rank holds exactly what a rank of the 8-GPU run of C4
+    # holds, so the shard-sized kernels and the exchange can be tuned at a quarter of the GPU time
+    "c4slab4": dict(desc="one quarter of C4: 3-D 7-point Laplacian 300x300x76", dtype="f64", k=1),
 }
 
 
@@ -91,8 +94,8 @@ def make_problem_uncached(name, dtype, k):
     elif name == "c4":
         A = P.laplace3d(300)
         b = np.ones(A.shape[0])
-    elif name == "c4slab8":
-        A = P.laplace3d(300, nz=38)
+    elif name in ("c4slab8", "c4slab4"):
+        A = P.laplace3d(300, nz=38 if name == "c4slab8" else 76)
         b = np.ones(A.shape[0])
     elif name == "c5":
         A = P.powerlaw_spd()
@@ -423,14 +426,15 @@ def run_row_block(args, wl, dtype, rank, local_rank, world):
     import cg_b200.problems as P
     from cg_b200 import sharded
     np_t, _, v_bytes, cplx = P.DTYPES[dtype]
-    if args.workload in ("c3", "c4"):
+    if args.workload in ("c3", "c4", "c4slab4", "c4slab8"):
         N3 = 128 if args.workload == "c3" else 300
-        n = N3 ** 3
-        planes = [(N3 * p) // world for p in range(world + 1)]          # whole z-planes per rank
+        NZ = {"c4slab4": 76, "c4slab8": 38}.get(args.workload, N3)
+        n = N3 * N3 * NZ
+        planes = [(NZ * p) // world for p in range(world + 1)]          # whole z-planes per rank
         bounds = np.array([pl * N3 * N3 for pl in planes], dtype=np.int64)
         rb, re = int(bounds[rank]), int(bounds[rank + 1])
-        Al = P.laplace3d(N3, dtype=np_t, rows=(rb, re))
-        nnz = 7 * n - 6 * N3 * N3
+        Al = P.laplace3d(N3, dtype=np_t, rows=(rb, re), nz=NZ)
+        nnz = 7 * n - 2 * N3 * N3 - 4 * N3 * NZ
         plan = sharded.plan_row_block(Al.indptr, Al.indices, Al.data, bounds, rank)
         b_owned = np.ones(re - rb, dtype=np_t)
         shape = (n, nnz)

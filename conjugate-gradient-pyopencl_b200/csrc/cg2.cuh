@@ -10,7 +10,7 @@
 //              (spmv.cl:13-49), the row's owner stores dn into the OTHER direction buffer, the pending
 //              x += alpha_prev d (axpy.cl, clcg.c:331-337) rides along because d is in flight anyway, and
 //              the partial sums of dn.q (vdot.cl) are fused in.    reads r d x, writes q dn x  (6 passes)
-//   update_r   alpha = delta_new/(d.q);  r' = r - alpha q  into the OTHER residual buffer;  partial r'.r'
+//   update_r   alpha = delta_new/(d.q);  r -= alpha q  in place;  partial r.r
 //              (axpy.cl + vdot.cl, clcg.c:326-386); bookkeeping (delta shuffle, beta, convergence,
 //              clcg.c:350-356,389-391) by the last block.         reads q r, writes r'       (3 passes)
 //
@@ -32,12 +32,15 @@
 // r + beta d by 256-thread blocks, 3 per SM -- 885 us on C4, bound by ~7 dependent memory round trips per
 // chunk with only 3 blocks to overlap them.)
 //
-// Row-block shards.  Ping-pong buffers for d (the SpMV reads the old one everywhere while owners write the
-// new one) and for r make every kernel read-only on its inputs, so the entries a peer needs can be
-// recomputed and stored straight into the peer's halo (NVLink) by a prologue of the SAME kernel that
-// produces them: dir_spmv pushes dn, update_r pushes r'.  No push kernel, no side stream, no flags: the
-// all-reduce at the tail of every kernel already orders "all my blocks are done" before "peers proceed",
-// and the next kernel that reads a halo is at least one all-reduce later.
+// Row-block shards.  The direction has two buffers (the SpMV reads the old one everywhere while the owners write the
+// new one), so dir_spmv is read-only on its inputs and the entries of dn a peer needs can be recomputed and stored
+// straight into the peer's memory (NVLink) by a dedicated warp of the SAME kernel, ahead of everything else: they go
+// into the halo of the peer's RESIDUAL vector while the halos of both direction buffers stay zero, so that the
+// peer's gather r[j] + beta d[j] yields exactly dn[j] there.  An arrival flag (numbered by the all-reduce count, as
+// in kernels.cuh) tells the peer's TMA producer when its boundary chunks -- scheduled last -- may be loaded.
+// No push kernel, no side stream, one exchange per iteration.  (First version, in git: r in two buffers as well and
+// the boundary entries of r' pushed by update_r, flag-free; on one eighth of the 300^3 system the six vectors then
+// no longer fit the 126 MB L2 and both kernels ran 30 % slower than alone, profiles/r02_trace_n8_pingpong.txt.)
 #pragma once
 
 namespace cgb {
@@ -88,7 +91,8 @@ __device__ __forceinline__ T cg2_grid_total(const CgScalars<T> &sc, T *red) {
 // dir_spmv is warp-specialised: DIR_CONSUMERS threads own the rows of a chunk (PAT_CHUNK / DIR_CONSUMERS rows
 // each, independent accumulation chains), one more warp does nothing but feed the ring of stages with TMA.
 constexpr int DIR_CONSUMERS = 512;
-constexpr int DIR_THREADS = DIR_CONSUMERS + 32;
+constexpr int DIR_THREADS = DIR_CONSUMERS + 32;         // + the TMA producer warp
+constexpr int DIR_THREADS_PEER = DIR_THREADS + 32;      // + the warp that stores dn into the peers' halos (row-block shards)
 constexpr int DIR_MAX_STAGES = 4;
 
 __device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
@@ -103,12 +107,13 @@ __device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
 //   s_pos      [npat][STRIDE] int   staging position of every pattern entry
 //   s_len      [npat] int
 template <typename T, int STRIDE, bool PEER>
-__global__ void __launch_bounds__(DIR_THREADS, 1)
-cg2_dir_spmv_kernel(int n, int ncols, int nchunks, int npat, int nstage, PatWindows win, const unsigned short *__restrict__ pat,
-                    const unsigned *__restrict__ chunk_mask, const int *__restrict__ p_len, const int *__restrict__ p_spos,
-                    const T *__restrict__ p_val, T *__restrict__ x, T *__restrict__ q, T *r0, T *r1, T *d0, T *d1,
-                    CgScalars<T> sc) {
+__global__ void __launch_bounds__(PEER ? DIR_THREADS_PEER : DIR_THREADS, 1)
+cg2_dir_spmv_kernel(int n, int ncols, int nchunks, int nchunks_interior, const int *__restrict__ chunks, int npat, int nstage,
+                    PatWindows win, const unsigned short *__restrict__ pat, const unsigned *__restrict__ chunk_mask,
+                    const int *__restrict__ p_len, const int *__restrict__ p_spos, const T *__restrict__ p_val,
+                    T *__restrict__ x, T *__restrict__ q, const T *__restrict__ r, T *d0, T *d1, CgScalars<T> sc) {
     constexpr int NT = DIR_CONSUMERS;
+    constexpr int NTHREADS = PEER ? DIR_THREADS_PEER : DIR_THREADS;
     constexpr int RPT = PAT_CHUNK / NT;                                        // rows per consumer thread and chunk
     constexpr int VPT = VecW<T>::value;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -120,14 +125,15 @@ cg2_dir_spmv_kernel(int n, int ncols, int nchunks, int npat, int nstage, PatWind
     int *s_pos = reinterpret_cast<int *>(stage0 + (size_t)nstage * 2 * win.total);
     int *s_len = s_pos + npat * STRIDE;
     const int t = threadIdx.x;
-    const bool producer = t >= NT;
+    const bool producer = t >= NT && t < NT + 32;
+    const bool pusher = PEER && t >= NT + 32;
     // the table is part of the matrix, not the previous kernel's output: staged before the grid dependency wait
-    for (int i = t; i < npat * STRIDE; i += DIR_THREADS) {
+    for (int i = t; i < npat * STRIDE; i += NTHREADS) {
         const int id = i / STRIDE, j = i % STRIDE;
         s_val[i] = p_val[id * PAT_MAXLEN + j];
         s_pos[i] = p_spos[id * PAT_MAXLEN + j];
     }
-    for (int i = t; i < npat; i += DIR_THREADS) s_len[i] = p_len[i];
+    for (int i = t; i < npat; i += NTHREADS) s_len[i] = p_len[i];
     if (t == 0) {
         for (int s = 0; s < nstage; s++) {
             mbar_init(&full[s], 1);
@@ -142,13 +148,14 @@ cg2_dir_spmv_kernel(int n, int ncols, int nchunks, int npat, int nstage, PatWind
     const int it = *sc.it;
     if (sc.trace && blockIdx.x == 0 && t == 0) trace_mark<T>(sc, it, TR_SPMV_START);
     const bool odd = (it & 1) != 0;
-    const T *__restrict__ r = odd ? r1 : r0;
     const T *__restrict__ dold = odd ? d1 : d0;
     T *__restrict__ dnew = odd ? d0 : d1;
     const T beta = sc.beta[0], alpha_prev = sc.alpha[0];
+    // the block's i-th chunk is number chunks[blockIdx + i*grid] of the schedule (row-block shards: the chunks that
+    // read halo entries come last), or blockIdx + i*grid itself
     const int count = ((int)blockIdx.x < nchunks) ? (nchunks - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    auto chunk_of = [&](int i) { const int ci = (int)blockIdx.x + i * (int)gridDim.x; return chunks ? chunks[ci] : ci; };
     T dot = Sc<T>::zero();
-    bool pushed = false;        // this thread stored into a peer's halo: fenced (system scope) before the block's arrival
 
     if (producer) {
         // ---- one elected thread: the windows of this block's i-th chunk, both vectors, into stage i % nstage,
@@ -157,9 +164,11 @@ cg2_dir_spmv_kernel(int n, int ncols, int nchunks, int npat, int nstage, PatWind
         {
             const bool elected = t == NT;      // (the other lanes walk the loop with it and meet it at __syncwarp)
             const long long ncols_pad = ((long long)ncols + VPT - 1) / VPT * VPT;      // (every vector has >= 256 bytes of slack)
-            unsigned wmask = (elected && count > 0) ? chunk_mask[blockIdx.x] : 0u;
+            int ch_next = (elected && count > 0) ? chunk_of(0) : 0;
+            unsigned wmask = (elected && count > 0) ? chunk_mask[ch_next] : 0u;
             int s = 0;                          // stage i % nstage and the parity of its use, tracked without divisions
             unsigned use_parity = 1;            // ((i / nstage) - 1) & 1
+            bool halo_ready = !(PEER && sc.peer && sc.peer->world > 1);
             for (int i = 0; i < count; i++, s++) {
                 __syncwarp();
                 if (s == nstage) {
@@ -167,10 +176,21 @@ cg2_dir_spmv_kernel(int n, int ncols, int nchunks, int npat, int nstage, PatWind
                     use_parity ^= 1u;
                 }
                 if (!elected) continue;
-                const int ch = (int)blockIdx.x + i * (int)gridDim.x;
+                const int ch = ch_next;
                 const long long c0 = (long long)ch * PAT_CHUNK;
                 const unsigned wm = wmask;
-                if (i + 1 < count) wmask = chunk_mask[ch + (int)gridDim.x];             // requested one chunk ahead
+                if (i + 1 < count) {                                                    // requested one chunk ahead
+                    ch_next = chunk_of(i + 1);
+                    wmask = chunk_mask[ch_next];
+                }
+                if constexpr (PEER) {
+                    // the first chunk of this block that reads halo entries: the peers' stores of this iteration must have landed
+                    if (!halo_ready && (int)blockIdx.x + i * (int)gridDim.x >= nchunks_interior) {
+                        peer_wait_halo(sc.peer);
+                        halo_ready = true;
+                        if (sc.trace) trace_mark<T>(sc, it, TR_HALO_READY);
+                    }
+                }
                 if (i >= nstage) mbar_wait(&empty[s], use_parity);
                 T *Sr = stage0 + (size_t)s * 2 * win.total, *Sd = Sr + win.total;
                 unsigned bytes = 0;
@@ -194,34 +214,68 @@ cg2_dir_spmv_kernel(int n, int ncols, int nchunks, int npat, int nstage, PatWind
                 }
             }
         }
-    } else {
+    } else if (pusher) {
+        // ---- row-block shards: this warp stores dn = r + beta d of the rows the peers reference into the halos of
+        // their residual vectors, 8 entries in flight per lane, then raises the arrival flags.  It shares nothing
+        // with the rest of the block: the consumers start on the interior chunks at once.
         if constexpr (PEER) {
-            if (sc.peer && sc.peer->world > 1) {
-                // (grid-strided over the send list by the consumer threads of all blocks)
-                const PeerComm *pc = sc.peer;
+            const PeerComm *pc = sc.peer;
+            if (pc && pc->world > 1) {
                 const int total = pc->send_off[pc->world];
-                bool stored = false;
-                for (int e = blockIdx.x * NT + t; e < total; e += gridDim.x * NT) {
-                    int p = 0;
-                    while (e >= pc->send_off[p + 1]) p++;
-                    const int row = pc->send_idx[e];
-                    T *dst = reinterpret_cast<T *>(pc->vec[odd ? 0 : 1][p]) + pc->remote_off[p] + (e - pc->send_off[p]);
-                    *dst = Sc<T>::fma(beta, dold[row], r[row]);
-                    stored = true;
+                const int lane = t & 31, nl = (int)gridDim.x * 32;
+                for (int e0 = (int)blockIdx.x * 32 + lane; e0 < total; e0 += 8 * nl) {
+                    int row[8];
+#pragma unroll
+                    for (int u = 0; u < 8; u++) {
+                        const int e = e0 + u * nl;
+                        row[u] = e < total ? pc->send_idx[e] : -1;
+                    }
+                    T val[8];
+#pragma unroll
+                    for (int u = 0; u < 8; u++)
+                        if (row[u] >= 0) val[u] = Sc<T>::fma(beta, dold[row[u]], r[row[u]]);
+#pragma unroll
+                    for (int u = 0; u < 8; u++) {
+                        const int e = e0 + u * nl;
+                        if (row[u] >= 0) {
+                            int p = 0;
+                            while (e >= pc->send_off[p + 1]) p++;
+                            reinterpret_cast<T *>(pc->vec[2][p])[pc->remote_off[p] + (e - pc->send_off[p])] = val[u];
+                        }
+                    }
                 }
-                pushed = stored;
+                __threadfence_system();
+                __syncwarp();
+                if (lane == 0) {
+                    // the last warp to get here (over all blocks) tells every peer that receives from this rank
+                    const unsigned prev = atomicAdd(&sc.peer->push_ticket[0], 1u);
+                    if (prev == gridDim.x - 1) {
+                        sc.peer->push_ticket[0] = 0;
+                        __threadfence_system();
+                        for (int p = 0; p < pc->world; p++)
+                            if (pc->send_off[p + 1] > pc->send_off[p]) st_release_sys_u64(pc->halo_flag[p] + pc->rank, pc->seq + 1);
+                    }
+                }
             }
         }
+    } else {
         // The pattern number and x of a thread's rows are requested one chunk ahead.  The loads are unconditional
         // (clamped row) and nothing touches their result before the next chunk, so that the wait for a stage
         // below never waits for THEM (a select on the loaded value right after the load did exactly that: 37 % of
         // the stall samples of the first version, profiles/r02_ncu_dir_spmv_c4_v3.txt).
+        // (Tried and reverted, in git: a thread owning the PAIR of rows 2t, 2t + 1 with 16-byte accesses for x, q, dn and
+        //  every even-positioned neighbour -- 7 shared-memory loads per row instead of 18.  On a 300-wide grid 43 % of
+        //  the warps hold a pair whose rows have different patterns -- the first / last node of a grid line -- and run
+        //  both the pair path and the per-row path: 46.5 instead of 41 us on the 38-plane slab, 324 instead of 280 on C4.)
         unsigned short id_cur[RPT];
         T x_cur[RPT];
         const long long last_row = (long long)n - 1;
+        // (chunk numbers come from the schedule: the one after next is requested now, so that its rows' loads can be
+        //  issued a whole chunk before they are needed)
+        int ch_cur = count > 0 ? chunk_of(0) : 0, ch_nxt = count > 1 ? chunk_of(1) : 0;
 #pragma unroll
         for (int s = 0; s < RPT; s++) {
-            const long long row = min((long long)blockIdx.x * PAT_CHUNK + t + s * NT, last_row);
+            const long long row = min((long long)ch_cur * PAT_CHUNK + t + s * NT, last_row);
             id_cur[s] = pat[row];
             x_cur[s] = ld_stream_bytes(x + row);
         }
@@ -239,13 +293,13 @@ cg2_dir_spmv_kernel(int n, int ncols, int nchunks, int npat, int nstage, PatWind
         unsigned parity = 0;
 
         for (int i = 0; i < count; i++) {
-            const int ch = (int)blockIdx.x + i * (int)gridDim.x;
-            const int c0 = ch * PAT_CHUNK;
+            const int c0 = ch_cur * PAT_CHUNK;
+            const int ch_nxt2 = i + 2 < count ? chunk_of(i + 2) : 0;
             unsigned short id_nxt[RPT];
             T x_nxt[RPT];
 #pragma unroll
             for (int s = 0; s < RPT; s++) {
-                const long long row = min((long long)c0 + (long long)gridDim.x * PAT_CHUNK + t + s * NT, last_row);
+                const long long row = min((long long)ch_nxt * PAT_CHUNK + t + s * NT, last_row);
                 id_nxt[s] = pat[row];
                 x_nxt[s] = ld_stream_bytes(x + row);
             }
@@ -297,6 +351,8 @@ cg2_dir_spmv_kernel(int n, int ncols, int nchunks, int npat, int nstage, PatWind
             }
             __syncwarp();
             if ((t & 31) == 0) mbar_arrive(&empty[st]);          // this warp has read everything it needs from the stage
+            ch_cur = ch_nxt;
+            ch_nxt = ch_nxt2;
             if (++st == nstage) {
                 st = 0;
                 parity ^= 1u;
@@ -304,10 +360,6 @@ cg2_dir_spmv_kernel(int n, int ncols, int nchunks, int npat, int nstage, PatWind
         }
     }
 
-    // (the stores into the peers' halos were issued before the chunk loop: by now they have long been acknowledged and
-    //  the fence that orders them before this block's arrival returns at once -- right after the stores it cost a
-    //  full NVLink round trip in every thread)
-    if (pushed) __threadfence_system();
     // block sum in a fixed order: lanes by butterfly, then the warps one after the other
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
@@ -333,7 +385,7 @@ cg2_dir_spmv_kernel(int n, int ncols, int nchunks, int npat, int nstage, PatWind
         __shared__ T s_total;
         __threadfence();
         T v = Sc<T>::zero();
-        for (int b = t; b < (int)gridDim.x; b += DIR_THREADS) v = Sc<T>::add(v, ld_cg(sc.partial + b));
+        for (int b = t; b < (int)gridDim.x; b += NTHREADS) v = Sc<T>::add(v, ld_cg(sc.partial + b));
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) {
             if constexpr (Sc<T>::cplx) {
@@ -347,7 +399,7 @@ cg2_dir_spmv_kernel(int n, int ncols, int nchunks, int npat, int nstage, PatWind
         __syncthreads();
         if (t == 0) {
             T sum = Sc<T>::zero();
-            for (int w = 0; w < DIR_THREADS / 32; w++) sum = Sc<T>::add(sum, red[w]);
+            for (int w = 0; w < NTHREADS / 32; w++) sum = Sc<T>::add(sum, red[w]);
             s_total = sum;
         }
         __syncthreads();
@@ -363,15 +415,15 @@ cg2_dir_spmv_kernel(int n, int ncols, int nchunks, int npat, int nstage, PatWind
     }
 }
 
-// alpha = delta_new / dq ; r' = r - alpha q (into the other residual buffer) ; delta_old = delta_new ;
-// delta_new = r'.r' ; beta ; convergence bookkeeping.      clcg.c:326-392
+// alpha = delta_new / dq ; r -= alpha q ; delta_old = delta_new ; delta_new = r.r ; beta ; convergence bookkeeping.
+//                                                                                                 clcg.c:326-392
 //
 // The tail of this kernel is on the critical path of every iteration (on shards it also carries the all-reduce), so
 // everything the last block needs from memory -- the column's state, delta_0, the tolerance -- is read by every
 // block up front, next to the scalars alpha needs anyway; after the sum is known the tail is arithmetic and stores.
 template <typename T, int V, bool PEER>
 __global__ void __launch_bounds__(256)
-cg2_update_r_kernel(size_t npacks, size_t nelem, const T *__restrict__ q, T *r0, T *r1, CgScalars<T> sc) {
+cg2_update_r_kernel(size_t npacks, size_t nelem, const T *__restrict__ q, T *__restrict__ r, CgScalars<T> sc) {
     pdl_wait();
     if (sc.pdl_early) pdl_trigger();
     if (*sc.n_active == 0) return;
@@ -381,9 +433,6 @@ cg2_update_r_kernel(size_t npacks, size_t nelem, const T *__restrict__ q, T *r0,
     const int t = threadIdx.x;
     const int it = *sc.it;
     if (sc.trace && blockIdx.x == 0 && t == 0) trace_mark<T>(sc, it, TR_XR_START);
-    const bool odd = (it & 1) != 0;
-    const T *__restrict__ r = odd ? r1 : r0;
-    T *__restrict__ rn = odd ? r0 : r1;
     const int state0 = sc.state[0];
     const T delta_cur = sc.delta_new[0];
     const double delta0 = sc.delta0[0], tol = *sc.tol;
@@ -391,11 +440,6 @@ cg2_update_r_kernel(size_t npacks, size_t nelem, const T *__restrict__ q, T *r0,
     if (state0 == ST_ACTIVE) {
         const T den = sc.dq[0];
         if (!Sc<T>::is_zero(den)) alpha = Sc<T>::div(delta_cur, den);
-    }
-    bool pushed = false;
-    if constexpr (PEER) {
-        if (sc.peer && sc.peer->world > 1)
-            pushed = peer_push_rows<T>(sc.peer, odd ? 2 : 3, [&](int row) { return Sc<T>::fnma(alpha, q[row], r[row]); });
     }
     T acc[V];
 #pragma unroll
@@ -409,19 +453,18 @@ cg2_update_r_kernel(size_t npacks, size_t nelem, const T *__restrict__ q, T *r0,
             rv.v[v] = Sc<T>::fnma(alpha, qv.v[v], rv.v[v]);
             acc[v] = Sc<T>::fma(rv.v[v], rv.v[v], acc[v]);
         }
-        reinterpret_cast<P *>(rn)[p] = rv;
+        reinterpret_cast<P *>(r)[p] = rv;
     }
     if (V > 1 && blockIdx.x == 0) {
         const size_t e = npacks * V + t;
         if (e < nelem) {
             const T rv = Sc<T>::fnma(alpha, q[e], r[e]);
-            rn[e] = rv;
+            r[e] = rv;
             acc[0] = Sc<T>::fma(rv, rv, acc[0]);
         }
     }
 #pragma unroll
     for (int v = 1; v < V; v++) acc[0] = Sc<T>::add(acc[0], acc[v]);
-    if (pushed) __threadfence_system();         // (see dir_spmv: fenced here, not right after the stores)
 
     // block sum, then (last block) grid sum, in a fixed order: lanes by butterfly, warps one after the other
     auto block_sum = [&](T v) -> T {            // valid in thread 0

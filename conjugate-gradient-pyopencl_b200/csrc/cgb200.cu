@@ -506,10 +506,11 @@ template <typename T> struct Engine {
             const int per = (c->pat_chunks + grid - 1) / grid;
             grid = (c->pat_chunks + per - 1) / per;
             c->spmv_grid_last = grid;
-            CU(launch_kernel(kern, dim3(grid), dim3(DIR_THREADS), smem, c->stream, (c->pdl & 1) != 0, c->n, c->n + c->extra_cols,
-                             c->pat_chunks, c->npat, nstage, c->win, (const unsigned short *)c->d_pat,
-                             (const unsigned *)c->d_chunk_mask, (const int *)c->d_plen, (const int *)c->d_pspos,
-                             (const T *)c->d_pval, (T *)c->x, (T *)c->q, (T *)c->r, (T *)c->r2, (T *)c->d, (T *)c->d2, sc));
+            CU(launch_kernel(kern, dim3(grid), dim3(PEER ? DIR_THREADS_PEER : DIR_THREADS), smem, c->stream, (c->pdl & 1) != 0, c->n,
+                             c->n + c->extra_cols, c->pat_chunks, c->pat_chunks_interior, (const int *)c->d_pat_chunks, c->npat,
+                             nstage, c->win, (const unsigned short *)c->d_pat, (const unsigned *)c->d_chunk_mask,
+                             (const int *)c->d_plen, (const int *)c->d_pspos, (const T *)c->d_pval, (T *)c->x, (T *)c->q,
+                             (const T *)c->r, (T *)c->d, (T *)c->d2, sc));
             c->launches++;
             return 0;
         };
@@ -525,7 +526,7 @@ template <typename T> struct Engine {
         const size_t nelem = (size_t)c->n, npacks = nelem / VW;
         const int grid = persistent_grid(c, kern, block, smem, (long long)((npacks + block - 1) / block));
         CU(launch_kernel(kern, dim3(grid), dim3(block), smem, c->stream, (c->pdl & 2) != 0, npacks, nelem, (const T *)c->q,
-                         (T *)c->r, (T *)c->r2, sc));
+                         (T *)c->r, sc));
         c->launches++;
         return 0;
     }
@@ -991,8 +992,8 @@ template <typename T> struct Engine {
         CU(cudaMemcpyAsync((void *)sc.tol, &tol, sizeof(double), cudaMemcpyHostToDevice, c->stream));
 
         CU(cudaEventRecord(c->ev[0], c->stream));
-        // inputs: b -> d (temporarily; the two-kernel iteration parks it in the spare residual buffer), x0 -> x
-        void *b_dev = cg2 ? c->r2 : c->d;
+        // inputs: b -> d (temporarily), x0 -> x
+        void *b_dev = c->d;
         if (k == 1 || layout == CGB200_LAYOUT_ROWMAJOR) {
             CU(cudaMemcpyAsync(b_dev, b, bytes, cudaMemcpyDefault, c->stream));
             CU(cudaMemcpyAsync(c->x, x, bytes, cudaMemcpyDefault, c->stream));

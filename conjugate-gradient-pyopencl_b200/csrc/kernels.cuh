@@ -61,8 +61,8 @@ struct PeerComm {
     int send_off[PEER_MAX + 1];                 // this rank's send list is segmented by destination rank
     int recv_from[PEER_MAX];                    // 1 if rank p sends halo entries to this rank
     unsigned int push_ticket[PEER_MAX];
-    // two-kernel iteration (cg2.cuh): rank p's direction buffers d0, d1 and residual buffers r0, r1, each
-    // [owned | halo]; the producing kernels store the entries rank p references straight into its halos
+    // two-kernel iteration (cg2.cuh): rank p's direction buffers d0, d1 and residual vector r (index 2), each
+    // [owned | halo]; dir_spmv stores the entries of the new direction rank p references into the halo of its r
     void *vec[4][PEER_MAX];
     const int *send_idx;                        // this rank's owned rows to send, segmented by destination (send_off)
 };
@@ -1693,11 +1693,7 @@ init_kernel(size_t npacks, size_t nelem, int k, int kv, const T *b /* may alias 
     T acc[V];
 #pragma unroll
     for (int v = 0; v < V; v++) acc[v] = Sc<T>::zero();
-    // two-kernel iteration on a row-block shard (k = 1; b is then NOT aliased with d): the boundary entries of
-    // r0 go straight into the peers' halos of residual buffer 0, which the first dir_spmv reads
-    bool pushed = false;
-    if (sc.cg2 && sc.peer && sc.peer->world > 1)
-        pushed = peer_push_rows<T>(sc.peer, 2, [&](int row) { return Sc<T>::sub(b[row], q[row]); });
+
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t p = (size_t)blockIdx.x * blockDim.x + t; p < npacks; p += stride) {
         const P bv = reinterpret_cast<const P *>(b)[p];
@@ -1724,7 +1720,6 @@ init_kernel(size_t npacks, size_t nelem, int k, int kv, const T *b /* may alias 
 #pragma unroll
         for (int v = 1; v < V; v++) { acc[0] = Sc<T>::add(acc[0], acc[v]); acc[v] = Sc<T>::zero(); }
     }
-    if (pushed) __threadfence_system();
     block_col_reduce<T, V>(acc, kv, smem);
     if (publish_and_arrive<T, V>(smem, kv, k, sc.partial, sc.ticket + TK_INIT)) {
         grid_col_reduce<T, V>(sc.partial, kv, kv, k, smem);

@@ -194,6 +194,15 @@ template <typename T> struct ShardEngine {
         if (sh->world == 1) sc.defer = 0;
         const bool cg2 = E::use_cg2(c, 1) && (sh->world == 1 || sh->p2p);
         sc.cg2 = cg2 ? 1 : 0;
+        // Programmatic dependent launch: on for the two-kernel iteration (dir_spmv's prologue -- pattern table, barriers --
+        // overlaps the tail of update_r: 64.1 -> 62.1 us per iteration on 38-plane shards); off for the three-kernel
+        // iteration on shards, where it never gained anything
+        struct PdlGuard {
+            cgb200_ctx *c;
+            int saved;
+            ~PdlGuard() { c->pdl = saved; }
+        } pdl_guard{c, c->pdl};
+        if (!cg2 && sh->world > 1 && !getenv("CGB200_PDL")) c->pdl = 0;
         if (sh->p2p && c->spmv_variant != 0 && c->spmv_variant != 6)
             return fail(CGB200_ERR_UNSUPPORTED, "peer-memory collectives need the default SpMV schedule (spmv_variant 0)");
         const typename E::VecGeom g = E::geom(c, 1);
@@ -208,7 +217,13 @@ template <typename T> struct ShardEngine {
         TRY(exchange(sh, (T *)c->d));
         TRY(E::template spmv<false>(c, 1, (const T *)c->d, (T *)c->q, sc));
         TRY(join_push(sh));
-        void *b_dev = cg2 ? c->r2 : c->d;             // (the two-kernel iteration's init must not alias b with d)
+        void *b_dev = c->d;
+        if (cg2 && sh->n_halo > 0) {
+            // two-kernel iteration: the halos of BOTH direction buffers stay zero for the whole solve (the peers store the
+            // new direction's boundary entries into the halo of r, and r[j] + beta * 0 is what the gather forms there)
+            CU(cudaMemsetAsync((T *)c->d + sh->n_owned, 0, (size_t)sh->n_halo * sizeof(T), c->stream));
+            CU(cudaMemsetAsync((T *)c->d2 + sh->n_owned, 0, (size_t)sh->n_halo * sizeof(T), c->stream));
+        }
         CU(cudaMemcpyAsync(b_dev, b, bytes, cudaMemcpyDefault, c->stream));
         if (g.V == 1) TRY(E::template launch_init<1>(c, 1, g, (const T *)b_dev, (const T *)c->q, (T *)c->r, (T *)c->d, sc));
         else TRY(E::template launch_init<E::VW>(c, 1, g, (const T *)b_dev, (const T *)c->q, (T *)c->r, (T *)c->d, sc));
@@ -335,7 +350,6 @@ int cgb200_shard_create(cgb200_shard *out, int rank, int world, const void *nccl
     int rc = create_ctx(&sh->m, n_owned, nnz, aValues, aPointers, aColsLocal, dtype, device, n_halo,
                         world > 1 ? row_boundary : nullptr);
     if (rc < 0) return bail(rc);
-    if (world > 1 && !getenv("CGB200_PDL")) sh->m->pdl = 0;   // see DESIGN.md 6: no measured gain in shards
     DeviceGuard guard(device);
     sh->send_counts.assign(world, 0);
     sh->recv_counts.assign(world, 0);
@@ -450,6 +464,7 @@ int cgb200_shard_p2p_import(cgb200_shard sh, const void *all_blobs, const long l
         }
         pc.slots[p] = (PeerSlot *)buf;
         pc.halo_flag[p] = (unsigned long long *)((char *)buf + P2P_SLOTS_BYTES);
+        // PeerComm::vec: 0, 1 the direction buffers, 2 the residual vector (vec_block order: d, d2, r, r2)
         for (int i = 0; i < 4; i++) pc.vec[i][p] = (char *)vecs + blobs[p].off[i];
         pc.d_peer[p] = pc.vec[0][p];
         pc.remote_off[p] = remote_off[p];

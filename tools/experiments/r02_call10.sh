@@ -1,0 +1,14 @@
+#!/bin/bash
+# 2 GPUs: single-residual protocol; per-rank sizes of the 8-GPU run via the 76-plane system
+set -u
+O=gpurun_out
+mkdir -p $O
+export PYTHONUNBUFFERED=1
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29521 tools/shard_check.py --parity-only > $O/r02_shard_check_2gpu.json 2> $O/r02_shard_check_2gpu.err; echo "shard_check 2 rc=$?"; tail -c 400 $O/r02_shard_check_2gpu.json; grep -i "error\|assert\|Traceback" $O/r02_shard_check_2gpu.err | head -5
+for opt in "cg2=1" "cg2=0"; do
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29523 bench.py --workload c4slab4 --gpus 2 --steps 5 --warmup 3 --opt trace=256 --opt $opt > $O/r02_bench_slab4_$opt.json 2> $O/r02_bench_slab4_$opt.err; echo "bench slab4 $opt rc=$?"; cut -c1-160 $O/r02_bench_slab4_$opt.json; tail -2 $O/r02_bench_slab4_$opt.err | cut -c1-300
+python tools/trace_report.py $O/trace_c4slab4_n2_r*.npy
+done
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29524 bench.py --gpus 2 --steps 5 --warmup 3 --opt trace=256 > $O/r02_bench_n2.json 2> $O/r02_bench_n2.err; echo "bench n2 rc=$?"; cut -c1-160 $O/r02_bench_n2.json
+python tools/trace_report.py $O/trace_c4_n2_r*.npy
+timeout 900 python -m pytest tests/test_gpu_cg2.py -m "gpu and not fullsize" -q > $O/r02_pytest_cg2.log 2>&1; echo "pytest cg2 rc=$?"; tail -4 $O/r02_pytest_cg2.log

@@ -1,0 +1,13 @@
+#!/bin/bash
+set -u
+O=gpurun_out
+mkdir -p $O
+export PYTHONUNBUFFERED=1
+export CGB200_PROBLEM_CACHE=/tmp/cgb200_problems
+timeout 900 python -m pytest tests/test_gpu_cg2.py -m "gpu and not fullsize" -q > $O/r02_pytest_cg2.log 2>&1; echo "pytest cg2 rc=$?"; tail -4 $O/r02_pytest_cg2.log
+timeout 600 python tools/kbench.py --workload c4slab8 --set cg2=1 --set cg2=0 > $O/r02_kbench_slab.json 2> $O/r02_kbench_slab.err; echo "kbench slab rc=$?"; cut -c1-560 $O/r02_kbench_slab.json; tail -3 $O/r02_kbench_slab.err
+timeout 900 python tools/kbench.py --workload c4 --set cg2=1 > $O/r02_kbench_c4.json 2> $O/r02_kbench_c4.err; echo "kbench c4 rc=$?"; cut -c1-560 $O/r02_kbench_c4.json; tail -3 $O/r02_kbench_c4.err
+timeout 600 python tools/kbench.py --workload c2 --set cg2=1,solver=1 --set cg2=0,solver=1 > $O/r02_kbench_c2.json 2> $O/r02_kbench_c2.err; echo "kbench c2 rc=$?"; cut -c1-560 $O/r02_kbench_c2.json; tail -3 $O/r02_kbench_c2.err
+timeout 600 python tools/kbench.py --workload c2 --dtype c64 --set cg2=1,solver=1 --set cg2=0,solver=1 > $O/r02_kbench_c2c64.json 2> $O/r02_kbench_c2c64.err; echo "kbench c2 c64 rc=$?"; cut -c1-560 $O/r02_kbench_c2c64.json
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:cg2_dir_spmv -s 20 -c 1 -f -o $O/r02_dir_spmv_slab \
+    python tools/kbench.py --workload c4slab8 --reps 1 --set cg2=1 > $O/r02_ncu_dir_slab.log 2>&1; echo "ncu dir slab rc=$?"
