@@ -88,6 +88,111 @@ __device__ __forceinline__ T cg2_grid_total(const CgScalars<T> &sc, T *red) {
     return total;
 }
 
+// The tail of a dir_spmv kernel: block sum of the consumers' partial dn.q in a fixed order (lanes by butterfly, then the
+// warps one after the other), the last block to arrive sums the blocks' partials the same way, all-reduces over the
+// GPUs (row-block shards) and publishes d.q.  `red` has 32 slots.
+template <typename T, bool PEER, int NTHREADS, int NT>
+__device__ __forceinline__ void dir_finish(T dot, T *red, const CgScalars<T> &sc, int it) {
+    const int t = threadIdx.x;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        if constexpr (Sc<T>::cplx) {
+            dot.x += __shfl_xor_sync(0xffffffffu, dot.x, off);
+            dot.y += __shfl_xor_sync(0xffffffffu, dot.y, off);
+        } else {
+            dot += __shfl_xor_sync(0xffffffffu, dot, off);
+        }
+    }
+    if ((t & 31) == 0) red[t >> 5] = dot;
+    __syncthreads();
+    if (t == 0) {
+        T sum = Sc<T>::zero();
+        for (int w = 0; w < NT / 32; w++) sum = Sc<T>::add(sum, red[w]);
+        red[0] = sum;
+    }
+    __syncthreads();
+    if (publish_and_arrive<T, 1>(red, 1, 1, sc.partial, sc.ticket + TK_SPMV)) {
+        if (t == 0 && sc.trace) trace_mark<T>(sc, it, TR_SPMV_ALL_DONE);
+        // sum of the per-block partials in a fixed order (grid_col_reduce wants a power-of-two block): strided
+        // loads issued together, lanes by butterfly, then the warps one after the other
+        __shared__ T s_total;
+        __threadfence();
+        T v = Sc<T>::zero();
+        for (int b = t; b < (int)gridDim.x; b += NTHREADS) v = Sc<T>::add(v, ld_cg(sc.partial + b));
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            if constexpr (Sc<T>::cplx) {
+                v.x += __shfl_xor_sync(0xffffffffu, v.x, off);
+                v.y += __shfl_xor_sync(0xffffffffu, v.y, off);
+            } else {
+                v += __shfl_xor_sync(0xffffffffu, v, off);
+            }
+        }
+        if ((t & 31) == 0) red[t >> 5] = v;
+        __syncthreads();
+        if (t == 0) {
+            T sum = Sc<T>::zero();
+            for (int w = 0; w < NTHREADS / 32; w++) sum = Sc<T>::add(sum, red[w]);
+            s_total = sum;
+        }
+        __syncthreads();
+        T total = s_total;
+        if constexpr (PEER) {
+            if (sc.peer) total = peer_allreduce<T>(sc.peer, total);
+        }
+        if (t == 0) {
+            sc.dq[0] = total;
+            sc.ticket[TK_SPMV] = 0;
+            if (sc.trace) trace_mark<T>(sc, it, TR_SPMV_END);
+        }
+    }
+}
+
+// Row-block shards: ONE warp per block stores dn = r + beta d of the rows the peers reference into the halos of their
+// residual vectors, 8 entries in flight per lane, then raises the arrival flags.  It shares nothing with the rest of
+// the block: the consumers start on the interior chunks at once.
+template <typename T>
+__device__ __forceinline__ void dir_push_halo(const CgScalars<T> &sc, T beta, const T *__restrict__ dold, const T *__restrict__ r) {
+    const int t = threadIdx.x;
+    const PeerComm *pc = sc.peer;
+    if (!pc || pc->world <= 1) return;
+    const int total = pc->send_off[pc->world];
+    const int lane = t & 31, nl = (int)gridDim.x * 32;
+    for (int e0 = (int)blockIdx.x * 32 + lane; e0 < total; e0 += 8 * nl) {
+        int row[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const int e = e0 + u * nl;
+            row[u] = e < total ? pc->send_idx[e] : -1;
+        }
+        T val[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++)
+            if (row[u] >= 0) val[u] = Sc<T>::fma(beta, dold[row[u]], r[row[u]]);
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const int e = e0 + u * nl;
+            if (row[u] >= 0) {
+                int p = 0;
+                while (e >= pc->send_off[p + 1]) p++;
+                reinterpret_cast<T *>(pc->vec[2][p])[pc->remote_off[p] + (e - pc->send_off[p])] = val[u];
+            }
+        }
+    }
+    __threadfence_system();
+    __syncwarp();
+    if (lane == 0) {
+        // the last warp to get here (over all blocks) tells every peer that receives from this rank
+        const unsigned prev = atomicAdd(&sc.peer->push_ticket[0], 1u);
+        if (prev == gridDim.x - 1) {
+            sc.peer->push_ticket[0] = 0;
+            __threadfence_system();
+            for (int p = 0; p < pc->world; p++)
+                if (pc->send_off[p + 1] > pc->send_off[p]) st_release_sys_u64(pc->halo_flag[p] + pc->rank, pc->seq + 1);
+        }
+    }
+}
+
 // dir_spmv is warp-specialised: DIR_CONSUMERS threads own the rows of a chunk (PAT_CHUNK / DIR_CONSUMERS rows
 // each, independent accumulation chains), one more warp does nothing but feed the ring of stages with TMA.
 constexpr int DIR_CONSUMERS = 512;
@@ -215,49 +320,7 @@ cg2_dir_spmv_kernel(int n, int ncols, int nchunks, int nchunks_interior, const i
             }
         }
     } else if (pusher) {
-        // ---- row-block shards: this warp stores dn = r + beta d of the rows the peers reference into the halos of
-        // their residual vectors, 8 entries in flight per lane, then raises the arrival flags.  It shares nothing
-        // with the rest of the block: the consumers start on the interior chunks at once.
-        if constexpr (PEER) {
-            const PeerComm *pc = sc.peer;
-            if (pc && pc->world > 1) {
-                const int total = pc->send_off[pc->world];
-                const int lane = t & 31, nl = (int)gridDim.x * 32;
-                for (int e0 = (int)blockIdx.x * 32 + lane; e0 < total; e0 += 8 * nl) {
-                    int row[8];
-#pragma unroll
-                    for (int u = 0; u < 8; u++) {
-                        const int e = e0 + u * nl;
-                        row[u] = e < total ? pc->send_idx[e] : -1;
-                    }
-                    T val[8];
-#pragma unroll
-                    for (int u = 0; u < 8; u++)
-                        if (row[u] >= 0) val[u] = Sc<T>::fma(beta, dold[row[u]], r[row[u]]);
-#pragma unroll
-                    for (int u = 0; u < 8; u++) {
-                        const int e = e0 + u * nl;
-                        if (row[u] >= 0) {
-                            int p = 0;
-                            while (e >= pc->send_off[p + 1]) p++;
-                            reinterpret_cast<T *>(pc->vec[2][p])[pc->remote_off[p] + (e - pc->send_off[p])] = val[u];
-                        }
-                    }
-                }
-                __threadfence_system();
-                __syncwarp();
-                if (lane == 0) {
-                    // the last warp to get here (over all blocks) tells every peer that receives from this rank
-                    const unsigned prev = atomicAdd(&sc.peer->push_ticket[0], 1u);
-                    if (prev == gridDim.x - 1) {
-                        sc.peer->push_ticket[0] = 0;
-                        __threadfence_system();
-                        for (int p = 0; p < pc->world; p++)
-                            if (pc->send_off[p + 1] > pc->send_off[p]) st_release_sys_u64(pc->halo_flag[p] + pc->rank, pc->seq + 1);
-                    }
-                }
-            }
-        }
+        if constexpr (PEER) dir_push_halo<T>(sc, beta, dold, r);
     } else {
         // The pattern number and x of a thread's rows are requested one chunk ahead.  The loads are unconditional
         // (clamped row) and nothing touches their result before the next chunk, so that the wait for a stage
@@ -360,59 +423,7 @@ cg2_dir_spmv_kernel(int n, int ncols, int nchunks, int nchunks_interior, const i
         }
     }
 
-    // block sum in a fixed order: lanes by butterfly, then the warps one after the other
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-        if constexpr (Sc<T>::cplx) {
-            dot.x += __shfl_xor_sync(0xffffffffu, dot.x, off);
-            dot.y += __shfl_xor_sync(0xffffffffu, dot.y, off);
-        } else {
-            dot += __shfl_xor_sync(0xffffffffu, dot, off);
-        }
-    }
-    if ((t & 31) == 0) red[t >> 5] = dot;
-    __syncthreads();
-    if (t == 0) {
-        T sum = Sc<T>::zero();
-        for (int w = 0; w < NT / 32; w++) sum = Sc<T>::add(sum, red[w]);
-        red[0] = sum;
-    }
-    __syncthreads();
-    if (publish_and_arrive<T, 1>(red, 1, 1, sc.partial, sc.ticket + TK_SPMV)) {
-        if (t == 0 && sc.trace) trace_mark<T>(sc, it, TR_SPMV_ALL_DONE);
-        // sum of the per-block partials in a fixed order (grid_col_reduce wants a power-of-two block): strided
-        // loads issued together, lanes by butterfly, then the warps one after the other
-        __shared__ T s_total;
-        __threadfence();
-        T v = Sc<T>::zero();
-        for (int b = t; b < (int)gridDim.x; b += NTHREADS) v = Sc<T>::add(v, ld_cg(sc.partial + b));
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            if constexpr (Sc<T>::cplx) {
-                v.x += __shfl_xor_sync(0xffffffffu, v.x, off);
-                v.y += __shfl_xor_sync(0xffffffffu, v.y, off);
-            } else {
-                v += __shfl_xor_sync(0xffffffffu, v, off);
-            }
-        }
-        if ((t & 31) == 0) red[t >> 5] = v;
-        __syncthreads();
-        if (t == 0) {
-            T sum = Sc<T>::zero();
-            for (int w = 0; w < NTHREADS / 32; w++) sum = Sc<T>::add(sum, red[w]);
-            s_total = sum;
-        }
-        __syncthreads();
-        T total = s_total;
-        if constexpr (PEER) {
-            if (sc.peer) total = peer_allreduce<T>(sc.peer, total);
-        }
-        if (t == 0) {
-            sc.dq[0] = total;
-            sc.ticket[TK_SPMV] = 0;
-            if (sc.trace) trace_mark<T>(sc, it, TR_SPMV_END);
-        }
-    }
+    dir_finish<T, PEER, NTHREADS, NT>(dot, red, sc, it);
 }
 
 // alpha = delta_new / dq ; r -= alpha q ; delta_old = delta_new ; delta_new = r.r ; beta ; convergence bookkeeping.

@@ -27,6 +27,7 @@
 #include "../../include/clcg.h"
 #include "kernels.cuh"
 #include "cg2.cuh"
+#include "cg2_march.cuh"
 #include "pcg.cuh"
 
 using namespace cgb;
@@ -86,6 +87,13 @@ struct cgb200_ctx {
     int cg2 = 1;                 // option: use the two-kernel iteration when the matrix allows it (k = 1)
     int cg2_ok = 0;              // the dictionary's offsets fit the window plan
     int cg2_stages = 0;          // option: stages of dir_spmv's TMA ring (0: 3, or what fits)
+    int march = 1;               // option: use the plane-marching dir_spmv when the offsets allow it (cg2_march.cuh)
+    MarchPlan mplan;             // ... and its plan (mplan.ok)
+    void *d_march_runs = nullptr;
+    int *d_mcodes = nullptr;     // [npat][PAT_MAXLEN] (rel + 1) << 24 | stage position of every pattern entry
+    int win_ok = 0;              // the window plan (cg2_dir_spmv_kernel) applies
+    int march_lz = 0;            // option: planes per run (0: chosen for balance)
+    int halo_low = 0;            // row-block shards: halo entries received from LOWER ranks (they come first in the halo)
     void *d_dinv = nullptr;      // [n] inverse diagonal of the preconditioned solve (caller's, or 1/diag(A))
     int dinv_is_jacobi = 0;      // d_dinv currently holds 1/diag(A) of the resident matrix
     int *d_pspos = nullptr;      // [npat][PAT_MAXLEN] staging position of every pattern entry
@@ -408,8 +416,119 @@ template <typename T> struct Engine {
         return ns;
     }
     static int pat_stride(const cgb200_ctx *c) { return c->max_row <= 8 ? 8 : (c->max_row <= 16 ? 16 : 32); }
+    // Plan of the plane-marching dir_spmv (cg2_march.cuh).  offs: the distinct column offsets of the dictionary.
+    // Applies when they are  {near} u {+P + near'} u {-P + near''}  (+ the halo aliases of a row-block shard) with
+    // |near| < 512 <= P, whole planes (P | n) and a chunk length that divides P.  Fails softly (mplan.ok = 0).
+    static size_t march_smem_bytes(const cgb200_ctx *c, int stride, int nstage) {
+        return 128 + (size_t)(32 + c->npat * stride) * sizeof(T) + (size_t)nstage * march_stage_bytes<T>(c->mplan) +
+               (size_t)c->npat * stride * sizeof(int) + (size_t)c->npat * sizeof(int) + 16;
+    }
+    static int march_stages(const cgb200_ctx *c, int stride) {
+        int ns = c->cg2_stages > 0 ? std::min(c->cg2_stages, MARCH_MAX_STAGES) : MARCH_MAX_STAGES;
+        while (ns >= 3 && march_smem_bytes(c, stride, ns) > 226 * 1024) ns--;
+        return ns;
+    }
+    static int plan_march(cgb200_ctx *c, const std::set<int> &offs, const std::vector<int> &len, const std::vector<int> &off,
+                          std::vector<int> *codes) {
+        MarchPlan &mp = c->mplan;
+        memset(&mp, 0, sizeof(mp));
+        const int NEAR = 512;
+        const long long n = c->n;
+        int near_lo = 0, near_hi = 0;
+        long long P = 0;
+        for (int o : offs) {
+            if (o > -NEAR && o < NEAR) {
+                near_lo = std::min(near_lo, o);
+                near_hi = std::max(near_hi, o);
+            } else if (o >= NEAR && (P == 0 || o < P)) {
+                P = o;
+            }
+        }
+        if (P == 0) {                         // all far offsets negative?  then -P is the largest one below -NEAR
+            for (int o : offs)
+                if (o <= -NEAR && (P == 0 || -(long long)o < P)) P = -(long long)o;
+        }
+        if (P == 0 || n % P != 0) return 0;
+        // the far groups sit around +-P; the near extent must cover their spread
+        const int n_low = c->halo_low, n_high = c->extra_cols - c->halo_low;
+        if (c->extra_cols && ((n_low != 0 && n_low != P) || (n_high != 0 && n_high != P) || n / P < 2)) return 0;
+        const long long alias_low = n_low ? (long long)n : -1;                 // bottom-plane rows -> low halo plane
+        const long long alias_high = n_high ? (long long)n_low + P : -1;       // top-plane rows -> high halo plane
+        auto classify = [&](long long o, int *rel, int *b) -> bool {
+            if (o > -NEAR && o < NEAR) { *rel = 0; *b = (int)o; return true; }
+            if (o - P > -NEAR && o - P < NEAR) { *rel = 1; *b = (int)(o - P); return true; }
+            if (o + P > -NEAR && o + P < NEAR) { *rel = -1; *b = (int)(o + P); return true; }
+            if (alias_low >= 0 && o - alias_low > -NEAR && o - alias_low < NEAR) { *rel = -1; *b = (int)(o - alias_low); return true; }
+            if (alias_high >= 0 && o - alias_high > -NEAR && o - alias_high < NEAR) { *rel = 1; *b = (int)(o - alias_high); return true; }
+            return false;
+        };
+        int b_lo = near_lo, b_hi = near_hi;
+        for (int o : offs) {
+            int rel, b;
+            if (!classify(o, &rel, &b)) return 0;
+            b_lo = std::min(b_lo, b);
+            b_hi = std::max(b_hi, b);
+        }
+        int ch = 0;
+        for (int d = 1024; d >= 256; d -= 8)
+            if (P % d == 0) { ch = d; break; }
+        if (!ch) return 0;
+        auto floor_to = [](long long v, int m) { return (int)(v >= 0 ? v - v % m : v - ((v % m) + m) % m); };
+        mp.ch = ch;
+        mp.m = (int)(P / ch);
+        mp.nplanes = (int)(n / P);
+        mp.lo0 = floor_to(b_lo, VW);
+        mp.stage_el = (int)((((long long)ch + b_hi - mp.lo0) + VW - 1) / VW * VW);
+        mp.has_low = n_low ? 1 : 0;
+        mp.has_high = n_high ? 1 : 0;
+        mp.low_src = n;
+        mp.high_src = n + n_low;
+        if (mp.stage_el >= (1 << 24)) return 0;
+        if (march_stages(c, pat_stride(c)) < 4) return 0;
+        // codes of the pattern entries: (rel + 1) << 24 | position in the stage; padding: the row's own entry
+        const int npat = c->npat;
+        codes->assign((size_t)npat * PAT_MAXLEN, (1 << 24) | (unsigned)(-mp.lo0));
+        for (int p = 0; p < npat; p++)
+            for (int j = 0; j < len[p]; j++) {
+                int rel = 0, b = 0;
+                classify(off[(size_t)p * PAT_MAXLEN + j], &rel, &b);
+                (*codes)[(size_t)p * PAT_MAXLEN + j] = ((rel + 1) << 24) | (b - mp.lo0);
+            }
+        // runs: every strip is cut into segments of lz planes.  A run of L planes loads L + 2 pieces, so long runs are
+        // cheap -- but the runs must spread evenly over the SMs: the cost of a choice is (rounds of runs) x (lz + what
+        // the two extra loads cost, ~0.35 of a computed piece each)
+        const int grid = c->sm_count;
+        int best_lz = mp.nplanes;
+        double best = 1e300;
+        for (int segs = 1; segs <= mp.nplanes; segs++) {
+            const int lz = (mp.nplanes + segs - 1) / segs;
+            const long long nruns = (long long)mp.m * ((mp.nplanes + lz - 1) / lz);
+            const long long rounds = (nruns + grid - 1) / grid;
+            const double cost = (double)rounds * (lz + 0.7);
+            if (cost < best - 1e-9) {
+                best = cost;
+                best_lz = lz;
+            }
+        }
+        if (c->march_lz > 0) best_lz = std::min(c->march_lz, mp.nplanes);
+        std::vector<MarchRun> inner, outer;
+        for (int z0 = 0; z0 < mp.nplanes; z0 += best_lz) {
+            const int L = std::min(best_lz, mp.nplanes - z0);
+            const bool touches = (z0 == 0 && mp.has_low) || (z0 + L == mp.nplanes && mp.has_high);
+            for (int s = 0; s < mp.m; s++) (touches ? outer : inner).push_back(MarchRun{s, z0, L, 0});
+        }
+        inner.insert(inner.end(), outer.begin(), outer.end());      // the runs that read a halo plane come last
+        mp.nruns = (int)inner.size();
+        if (c->d_march_runs) cudaFree(c->d_march_runs);
+        c->d_march_runs = nullptr;
+        CU(cudaMalloc(&c->d_march_runs, inner.size() * sizeof(MarchRun)));
+        CU(cudaMemcpy(c->d_march_runs, inner.data(), inner.size() * sizeof(MarchRun), cudaMemcpyHostToDevice));
+        mp.ok = 1;
+        return 0;
+    }
     static int build_windows(cgb200_ctx *c) {
         c->cg2_ok = 0;
+        c->mplan.ok = 0;
         const int npat = c->npat;
         std::vector<int> len(npat), off((size_t)npat * PAT_MAXLEN);
         CU(cudaMemcpy(len.data(), c->d_plen, (size_t)npat * sizeof(int), cudaMemcpyDeviceToHost));
@@ -418,9 +537,19 @@ template <typename T> struct Engine {
         offs.insert(0);
         for (int p = 0; p < npat; p++)
             for (int j = 0; j < len[p]; j++) offs.insert(off[(size_t)p * PAT_MAXLEN + j]);
+        {
+            std::vector<int> codes;
+            TRY(plan_march(c, offs, len, off, &codes));
+            if (c->mplan.ok) {
+                if (!c->d_mcodes) CU(cudaMalloc(&c->d_mcodes, (size_t)PAT_MAXCOUNT * PAT_MAXLEN * sizeof(int)));
+                CU(cudaMemcpy(c->d_mcodes, codes.data(), codes.size() * sizeof(int), cudaMemcpyHostToDevice));
+                c->cg2_ok = 1;
+            }
+        }
         auto floor_to = [](long long v, int m) { return (int)(v >= 0 ? v - v % m : v - ((v % m) + m) % m); };
         PatWindows w;
         memset(&w, 0, sizeof(w));
+        c->win_ok = 0;
         int cur_lo = 0, cur_hi = 0;
         bool open = false;
         std::vector<std::pair<int, int>> groups;
@@ -484,15 +613,50 @@ template <typename T> struct Engine {
             c->n, c->pat_chunks, (const unsigned short *)c->d_pat, c->d_pat_mask, c->d_chunk_mask);
         CU(cudaStreamSynchronize(c->stream));
         c->launches++;
+        c->win_ok = 1;
         c->cg2_ok = 1;
         return 0;
     }
     // ---- the two-kernel iteration ------------------------------------------------
+    // march: 0 off, 2 always (when the plan applies), 1 by size.  Measured (profiles/r02_kbench_*): the plane-marching
+    // kernel wins when the vectors stream from HBM (300^3: 242 vs 258 us), the window kernel wins when they sit in the L2
+    // (one eighth of it: 37.7 vs 40.5 us; 1024^2 Helmholtz: 22.0 vs 22.8 us) where the extra pieces at the ends of a run and
+    // the coarser balance cost more than the smaller stages give.
+    static bool use_march(const cgb200_ctx *c) {
+        if (!c->mplan.ok || !c->march) return false;
+        return c->march >= 2 || !c->win_ok || (double)c->n * sizeof(T) >= 48e6;
+    }
     static bool use_cg2(const cgb200_ctx *c, int k) {
-        return k == 1 && c->cg2 && c->cg2_ok && c->pat_ok && c->pattern && c->d_tiles && c->spmv_variant == 0;
+        return k == 1 && c->cg2 && c->cg2_ok && (use_march(c) || c->win_ok) && c->pat_ok && c->pattern && c->d_tiles &&
+               c->spmv_variant == 0;
+    }
+    template <bool PEER>
+    static int launch_dir_march(cgb200_ctx *c, const CgScalars<T> &sc) {
+        const int stride = pat_stride(c);
+        const int nstage = march_stages(c, stride);
+        const size_t smem = march_smem_bytes(c, stride, nstage);
+        auto launch = [&](auto kern) -> int {
+            const void *key = (const void *)kern;
+            if (c->occ.find(key) == c->occ.end()) {
+                CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+                c->occ[key] = 1;
+            }
+            const int grid = std::min(c->sm_count, c->mplan.nruns);
+            c->spmv_grid_last = grid;
+            CU(launch_kernel(kern, dim3(grid), dim3(PEER ? DIR_THREADS_PEER : DIR_THREADS), smem, c->stream, (c->pdl & 1) != 0, c->n,
+                             c->n + c->extra_cols, c->mplan, nstage, (const MarchRun *)c->d_march_runs, c->npat,
+                             (const unsigned short *)c->d_pat, (const int *)c->d_plen, (const int *)c->d_mcodes,
+                             (const T *)c->d_pval, (T *)c->x, (T *)c->q, (const T *)c->r, (T *)c->d, (T *)c->d2, sc));
+            c->launches++;
+            return 0;
+        };
+        if (stride == 8) return launch(cg2_dir_march_kernel<T, 8, PEER>);
+        if (stride == 16) return launch(cg2_dir_march_kernel<T, 16, PEER>);
+        return launch(cg2_dir_march_kernel<T, 32, PEER>);
     }
     template <bool PEER>
     static int launch_dir_spmv(cgb200_ctx *c, const CgScalars<T> &sc) {
+        if (use_march(c)) return launch_dir_march<PEER>(c, sc);
         const int stride = pat_stride(c);
         const int nstage = cg2_stages(c, stride);
         const size_t smem = cg2_smem_bytes(c, stride, nstage);
@@ -1565,7 +1729,7 @@ static int grid_fill(cgb200_ctx *c, const GridSpec *spec);
 
 static int create_ctx(cgb200_handle *out, int n, long long nnz, const void *aValues, const int *aPointers,
                       const int *aCols, int dtype, int device, int extra_cols, const unsigned char *row_boundary,
-                      const GridSpec *grid = nullptr) {
+                      const GridSpec *grid = nullptr, int halo_low = 0) {
     if (!out) return fail(CGB200_ERR_ARG, "out is NULL");
     *out = nullptr;
     if (n <= 0 || nnz < 0 || (!grid && (!aPointers || (nnz > 0 && (!aValues || !aCols)))))
@@ -1585,6 +1749,7 @@ static int create_ctx(cgb200_handle *out, int n, long long nnz, const void *aVal
     c->nnz = nnz;
     c->vsize = vs;
     c->extra_cols = extra_cols;
+    c->halo_low = halo_low;
     if (row_boundary) c->row_boundary.assign(row_boundary, row_boundary + n);
     auto bail = [&](int rc) {
         cgb200_destroy(c);
@@ -1659,7 +1824,7 @@ int cgb200_destroy(cgb200_handle c) {
     if (c->d_trace) cudaFree(c->d_trace);
     if (c->d_runs) cudaFree(c->d_runs);
     for (void *b : {c->d_pat, c->d_pat_table, c->d_pat_build, c->d_plen, c->d_poff, c->d_pval, (void *)c->d_pat_chunks,
-                    (void *)c->d_pspos, (void *)c->d_pat_mask, (void *)c->d_chunk_mask, c->d_dinv})
+                    (void *)c->d_pspos, (void *)c->d_pat_mask, (void *)c->d_chunk_mask, c->d_dinv, c->d_march_runs, (void *)c->d_mcodes})
         if (b) cudaFree(b);
     if (c->d_tiles) cudaFree(c->d_tiles);
     if (c->d_long) cudaFree(c->d_long);
@@ -1707,6 +1872,9 @@ static int *option_slot(cgb200_handle c, const char *key) {
     if (!strcmp(key, "pattern_regs")) return &c->pattern_regs;
     if (!strcmp(key, "cg2")) return &c->cg2;
     if (!strcmp(key, "cg2_stages")) return &c->cg2_stages;
+    if (!strcmp(key, "march")) return &c->march;
+    if (!strcmp(key, "march_lz")) return &c->march_lz;
+    if (!strcmp(key, "march_ok")) return &c->mplan.ok;      // read-only: the plane-marching dir_spmv applies
     if (!strcmp(key, "cg2_ok")) return &c->cg2_ok;          // read-only: the dictionary's offsets fit the window plan
     if (!strcmp(key, "patterns")) return &c->npat;        // read-only: distinct row patterns found (0: CSR kernels in use)
     if (!strcmp(key, "spmm_schedule")) return &c->spmm_schedule;
@@ -1724,7 +1892,8 @@ int cgb200_set_option(cgb200_handle c, const char *key, long long value) {
         value != 16 && value != 32)
         return fail(CGB200_ERR_ARG, "lanes_per_row must be 0 or a power of two <= 32");
     if (!strcmp(key, "graph_chunk") && value < 1) return fail(CGB200_ERR_ARG, "graph_chunk must be >= 1");
-    if (!strcmp(key, "patterns") || !strcmp(key, "cg2_ok")) return fail(CGB200_ERR_ARG, "'%s' is read-only", key);
+    if (!strcmp(key, "patterns") || !strcmp(key, "cg2_ok") || !strcmp(key, "march_ok"))
+        return fail(CGB200_ERR_ARG, "'%s' is read-only", key);
     if (!strcmp(key, "trace")) {
         if (value < 0 || value > (1 << 20)) return fail(CGB200_ERR_ARG, "trace: 0 .. 2^20 iterations");
         DeviceGuard guard(c->device);
@@ -1737,6 +1906,10 @@ int cgb200_set_option(cgb200_handle c, const char *key, long long value) {
     }
     *slot = (int)value;
     drop_graph(c);
+    if (!strcmp(key, "march_lz") && c->pat_ok) {        // the runs of the plane-marching kernel are cut at set-up: cut them again
+        DeviceGuard guard(c->device);
+        TRY(DISPATCH(c, E::build_windows(c)));
+    }
     return CGB200_OK;
 }
 

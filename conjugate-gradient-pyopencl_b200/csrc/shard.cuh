@@ -347,8 +347,10 @@ int cgb200_shard_create(cgb200_shard *out, int rank, int world, const void *nccl
         return rc;
     };
     // (the halo-touching rows, when given, are scheduled last: the exchange hides behind the interior rows)
+    int halo_low = 0;           // the halo is sorted by global index: what lower ranks send comes first
+    for (int p = 0; p < rank && world > 1; p++) halo_low += recv_counts[p];
     int rc = create_ctx(&sh->m, n_owned, nnz, aValues, aPointers, aColsLocal, dtype, device, n_halo,
-                        world > 1 ? row_boundary : nullptr);
+                        world > 1 ? row_boundary : nullptr, nullptr, halo_low);
     if (rc < 0) return bail(rc);
     DeviceGuard guard(device);
     sh->send_counts.assign(world, 0);

@@ -104,7 +104,11 @@ CGB200_API int cgb200_set_stream(cgb200_handle h, void *cuda_stream);
  *   "cg2"            1 (default): k = 1 on a matrix with a row-pattern dictionary whose column offsets fit a window
  *                    plan runs the TWO-kernel iteration (csrc/cg2.cuh: direction update folded into the SpMV's
  *                    gather, x lagging one update, 9 vector passes instead of 11); "cg2_ok" (read-only) tells
- *                    whether the matrix qualifies; "cg2_stages" (2..4, default 3) sets the depth of its TMA ring
+ *                    whether the matrix qualifies; "cg2_stages" sets the depth of its TMA ring (default: what fits);
+ *                    "march" 1 (default): grid operators with one far offset +-P whose vectors are too big for the L2
+ *                    run the plane-marching variant (csrc/cg2_march.cuh: each piece of the vectors is staged once per
+ *                    strip instead of three times); 2: whenever it applies; 0: never;
+ *                    "march_ok" (read-only) tells whether it applies, "march_lz" overrides the planes per run
  *   "spmm_schedule"  0 (default) | 1: k > 1 on a matrix with grid structure (few fixed column offsets) visits rows
  *                    patch by patch for L1 reuse of the gathered rows (spmm_sched_kernel)
  *   "trace"          n > 0: the loop kernels stamp %globaltimer into an 8-slot record per iteration for the

@@ -78,6 +78,57 @@ def test_two_kernel_iteration_matches_three_kernel_path_and_oracle(gpu, cpu_ref,
         assert abs(int(it2.iterations[0]) - int(it3.iterations[0])) <= max(2, int(0.02 * it3.iterations[0]))
 
 
+@pytest.mark.parametrize("dname", ["f64", "c128", "f32", "c64"])
+@pytest.mark.parametrize("kind", ["lap3d_32", "lap3d_40x7", "poisson600", "helm520"])
+def test_plane_marching_dir_spmv_matches_the_window_kernel_and_the_oracle(gpu, cpu_ref, dname, kind):
+    """csrc/cg2_march.cuh: operators whose far offsets are +-P with a chunk length that divides P are walked plane by
+    plane (each piece of r and d staged once per strip).  Same FMAs in the same order as the window-staging kernel;
+    only the association of the d.q partial sums differs (other rows per block)."""
+    import cg_b200.problems as P
+    dt = DT[dname]
+    cplx = np.dtype(dt).kind == "c"
+    if kind == "lap3d_32":            # plane 1024 = one chunk per plane
+        A = P.laplace3d(32)
+    elif kind == "lap3d_40x7":        # plane 1600 = two chunks of 800 per plane, 7 planes
+        A = P.laplace3d(40, nz=7)
+    elif kind == "poisson600":        # 2-D: the "plane" is a grid line of 600
+        A = P.poisson2d(600)
+    else:
+        if not cplx:
+            pytest.skip("the Helmholtz operator is complex")
+        A = P.helmholtz_fe(520)       # lines of 520, offsets +-1, +-520, +-521
+    if cplx and kind != "helm520":
+        A = (A + 0.3j * sp.eye(A.shape[0])).tocsr()
+    A = A.astype(dt)
+    A.sort_indices()
+    n = A.shape[0]
+    rng = np.random.default_rng(21)
+    b = rand(rng, n, dt)
+    x0 = (0.1 * rand(rng, n, dt)).astype(dt)
+    its = 40
+    with gpu.Matrix.from_scipy(A) as M:
+        M.set_option("solver", 1)
+        assert M.get_option("march_ok") == 1, kind
+        M.set_option("march", 2)      # (by default only systems too big for the L2 take this kernel)
+        xm, im = M.solve(b, x=x0.copy(), max_iterations=its, history=True)
+        M.set_option("march", 0)
+        if M.get_option("cg2_ok") and kind != "helm520":
+            xw, iw = M.solve(b, x=x0.copy(), max_iterations=its, history=True)
+            assert rel(xm, xw) < (1e-4 if dname in ("f32", "c64") else 1e-11)
+        M.set_option("cg2", 0)
+        x3, i3 = M.solve(b, x=x0.copy(), max_iterations=its, history=True)
+        M.set_option("cg2", 1)
+        M.set_option("march", 2)
+        for lz in (1, 2, 5):          # any cut of the strips into runs: the same rows, another association of the d.q sums
+            M.set_option("march_lz", lz)
+            xl, _ = M.solve(b, x=x0.copy(), max_iterations=its)
+            assert rel(xl, xm) < (1e-4 if dname in ("f32", "c64") else 1e-11), lz
+    ref, w = oracle_pair(cpu_ref, dname, A.data, A.indptr, A.indices, b, x0=x0, iters=its)
+    check_parity(xm, ref, w, dname)
+    single = dname in ("f32", "c64")
+    assert rel(im.delta_hist[:20], i3.delta_hist[:20]) < (1e-3 if single else 1e-12)
+
+
 @pytest.mark.parametrize("n", [37, 255, 1023, 1024, 1025, 2049])
 def test_two_kernel_iteration_small_and_ragged_sizes(gpu, cpu_ref, n):
     # 1-D Laplacian + shift: 3 patterns, sizes around the chunk length

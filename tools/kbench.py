@@ -67,7 +67,7 @@ def main():
         print(json.dumps(out), flush=True)
         for key in opts:      # back to defaults for the next set
             M.set_option(key, {"cg2": 1, "pattern": 1, "pdl": 1, "use_graph": 1, "pdl_early": 1, "graph_chunk": 16,
-                               "defer_len": 16, "auto_irregular": 1, "vec_carveout": -1}.get(key, 0))
+                               "defer_len": 16, "auto_irregular": 1, "vec_carveout": -1, "march": 1}.get(key, 0))
     M.close()
 
 

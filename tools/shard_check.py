@@ -45,6 +45,16 @@ for name, A, b, tolv in (("lap3d24", P.laplace3d(24), np.ones(24 ** 3), 1e-10),
     M.set_option("use_graph", 0)
     x, info = M.solve(b[rb:re].astype(A.dtype), max_iterations=60)
     cg2 = M.get_option("cg2_ok")
+    if cg2 and M.get_option("march_ok"):
+        # the plane-marching dir_spmv (halo planes as the pieces below / above the owned planes) vs the window kernel
+        M.set_option("march", 2)
+        xm, _ = M.solve(b[rb:re].astype(A.dtype), max_iterations=60)
+        M.set_option("march", 0)
+        xw, _ = M.solve(b[rb:re].astype(A.dtype), max_iterations=60)
+        M.set_option("march", 1)
+        em = float(np.linalg.norm(xm - xw) / np.linalg.norm(xw))
+        log(name, "plane-marching vs window dir_spmv:", em)
+        assert em < 1e-10, em
     if cg2:
         # the two-kernel iteration (halo stores from inside the producing kernels) vs the three-kernel one
         # (halo_push_kernel on a side stream + arrival flags): same FMAs, other association of the dot sums
@@ -87,7 +97,7 @@ for name, A, b, tolv in (("lap3d24", P.laplace3d(24), np.ones(24 ** 3), 1e-10),
     assert np.array_equal(x2, x2p) and info2["iterations"] == info2p["iterations"]
     _, its_ref, _ = cpu_ref.cg(A.data, A.indptr, A.indices, b.astype(A.dtype), iters=5000, tol=1e-9)
     out[name] = dict(err60=err, iters=info2["iterations"], iters_oracle=int(its_ref[0]), n_halo=plan.n_halo, info=M.info(),
-                     two_kernel=int(cg2))
+                     two_kernel=int(cg2), march_ok=int(M.get_option("march_ok")))
     assert err < tolv, (name, err)
     assert abs(info2["iterations"] - int(its_ref[0])) <= 1, (name, info2, its_ref)
     M.close()
