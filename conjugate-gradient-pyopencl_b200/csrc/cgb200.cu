@@ -74,14 +74,10 @@ struct cgb200_ctx {
     int sm_count = 0;
     int max_row = 0;
     double mean_row = 0;
-    int grid_nx = 0, grid_ny = 0;   // lexicographic grid strides detected in the column offsets (0: none), see detect_grid
-    void *d_runs = nullptr;        // row schedule of spmm_sched_kernel for sched_R row groups per block
-    int sched_R = 0, sched_units = 0, spmm_schedule = 0;   // measured slower than the plain row order: off
     // row-pattern dictionary (k = 1), see spmv_pattern_kernel
     void *d_pat = nullptr, *d_pat_table = nullptr, *d_pat_build = nullptr, *d_plen = nullptr, *d_poff = nullptr, *d_pval = nullptr;
     int *d_pat_chunks = nullptr;
     int npat = 0, pat_ok = 0, pattern = 1, pat_chunks = 0, pat_chunks_interior = 0;
-    int pattern_regs = 0;        // experiment: the last pattern kept in registers (spmv_pattern_regs_kernel), unmeasured
     // two-kernel iteration (cg2.cuh): window plan of the pattern dictionary's column offsets
     PatWindows win;
     int cg2 = 1;                 // option: use the two-kernel iteration when the matrix allows it (k = 1)
@@ -123,6 +119,12 @@ struct cgb200_ctx {
     void *x = nullptr, *r = nullptr, *d = nullptr, *q = nullptr, *stage = nullptr;
     void *r2 = nullptr, *d2 = nullptr;   // second residual / direction buffer of the two-kernel iteration (k = 1)
     void *vec_block = nullptr;           // r, r2, d, d2 live in ONE allocation (one CUDA-IPC handle for the peers)
+    // CGB200_GUARD=1 (a debugging aid; compute-sanitizer is not available on every pool): every work vector gets a
+    // 4 KB zone filled with a byte pattern in front of it and behind it, cgb200_check_guards counts the bytes a kernel
+    // changed there.  x_base / q_base / vec_base are what cudaFree gets.
+    int guard = 0;
+    void *x_base = nullptr, *q_base = nullptr, *vec_base = nullptr;
+    size_t x_bytes = 0, q_bytes = 0, vec_bytes = 0;
     size_t vec_off[4] = {0, 0, 0, 0};    // byte offsets of d, d2, r, r2 in vec_block (PeerComm::vec order)
     void *scal_mem = nullptr;   // device block the CgScalars arrays are carved from
     void *partial = nullptr;
@@ -144,6 +146,9 @@ struct cgb200_ctx {
     int spmv_grid_last = 0;
 };
 
+constexpr size_t GUARD_BYTES = 4096;
+constexpr int GUARD_BYTE = 0xA5;
+
 static size_t dtype_size(int dt) {
     switch (dt) {
     case CGB200_F32: return 4;
@@ -162,11 +167,12 @@ static void drop_graph(cgb200_ctx *c) {
 
 static void free_workspace(cgb200_ctx *c) {
     drop_graph(c);
-    void **bufs[] = {&c->x, &c->vec_block, &c->q, &c->stage, &c->scal_mem, &c->partial};
+    void **bufs[] = {&c->x_base, &c->vec_base, &c->q_base, &c->stage, &c->scal_mem, &c->partial};
     for (void **b : bufs) {
         if (*b) cudaFree(*b);
         *b = nullptr;
     }
+    c->x = c->q = c->vec_block = nullptr;
     c->r = c->r2 = c->d = c->d2 = nullptr;
     c->ws_k = 0;
 }
@@ -290,11 +296,20 @@ template <typename T> struct Engine {
         if (c->ws_k >= k && c->x) return 0;
         free_workspace(c);
         const size_t bytes = (size_t)c->n * k * sizeof(T) + 64;
-        CU(cudaMalloc(&c->x, bytes));
+        c->guard = getenv("CGB200_GUARD") && atoi(getenv("CGB200_GUARD")) != 0;
+        const size_t gz = c->guard ? GUARD_BYTES : 0;
+        auto guarded_alloc = [&](void **base, void **ptr, size_t *nbytes, size_t payload) -> int {
+            CU(cudaMalloc(base, payload + 2 * gz));
+            if (gz) CU(cudaMemset(*base, GUARD_BYTE, payload + 2 * gz));
+            *ptr = (char *)*base + gz;
+            *nbytes = payload;
+            return 0;
+        };
+        TRY(guarded_alloc(&c->x_base, &c->x, &c->x_bytes, bytes));
         {   // d, d2, r, r2 ([owned | halo] each; the second buffers only for k = 1) in one block
             const size_t each = (((size_t)(c->n + c->extra_cols) * k * sizeof(T) + 256) + 255) & ~(size_t)255;
             const int nvec = k == 1 ? 4 : 2;
-            CU(cudaMalloc(&c->vec_block, each * nvec));
+            TRY(guarded_alloc(&c->vec_base, &c->vec_block, &c->vec_bytes, each * nvec));
             CU(cudaMemset(c->vec_block, 0, each * nvec));
             char *base = (char *)c->vec_block;
             for (int i = 0; i < 4; i++) c->vec_off[i] = 0;
@@ -306,7 +321,7 @@ template <typename T> struct Engine {
                 c->vec_off[2] = each;
             }
         }
-        CU(cudaMalloc(&c->q, bytes));
+        TRY(guarded_alloc(&c->q_base, &c->q, &c->q_bytes, bytes));
         if (k > 1) CU(cudaMalloc(&c->stage, bytes));
         CU(cudaMalloc(&c->scal_mem, scalars_bytes(k)));
         CU(cudaMemset(c->scal_mem, 0, scalars_bytes(k)));
@@ -724,16 +739,6 @@ template <typename T> struct Engine {
             c->launches++;
             return 0;
         };
-        if (c->pattern_regs && stride == 8 && !sc.peer && !c->d_pat_chunks) {      // experiment, see spmv_pattern_regs_kernel
-            auto kern = spmv_pattern_regs_kernel<T, DOT>;
-            const int grid = persistent_grid(c, kern, PAT_THREADS, smem, c->pat_chunks);
-            c->spmv_grid_last = grid;
-            CU(launch_kernel(kern, dim3(grid), dim3(PAT_THREADS), smem, c->stream, DOT && (c->pdl & 1), c->n, c->pat_chunks,
-                             c->npat, (const unsigned short *)c->d_pat, (const int *)c->d_plen, (const int *)c->d_poff,
-                             (const T *)c->d_pval, x, y, sc));
-            c->launches++;
-            return 0;
-        }
         if (sc.peer) {
             if (stride == 8) return launch(spmv_pattern_kernel<T, DOT, 8, true>);
             if (stride == 16) return launch(spmv_pattern_kernel<T, DOT, 16, true>);
@@ -745,9 +750,7 @@ template <typename T> struct Engine {
     }
     // ---- CSR-stream schedule -------------------------------------------------
     static int build_tiles(cgb200_ctx *c, const std::vector<int> &rp) {
-        using C = StreamCfg<T>;
-        const int cap = std::min<int>(C::CAP, RowTileCfg::CAP), rowcap = std::min<int>(C::RMAX, RowTileCfg::NT);
-        (void)sizeof(C);
+        const int cap = RowTileCfg::CAP, rowcap = RowTileCfg::NT;
         std::vector<SpmvTile> tiles;
         std::vector<LongRow> longs;
         int slots = 0;
@@ -798,23 +801,6 @@ template <typename T> struct Engine {
         }
         return 0;
     }
-    template <bool DOT>
-    static int spmv_stream(cgb200_ctx *c, const T *x, T *y, const CgScalars<T> &sc) {
-        using C = StreamCfg<T>;
-        auto kern = spmv_stream_kernel<T, DOT>;
-        const size_t smem = (size_t)(C::TILE + C::THREADS) * sizeof(T);
-        const int grid = persistent_grid(c, kern, C::THREADS, smem, c->ntiles);
-        c->spmv_grid_last = grid;
-        kern<<<grid, C::THREADS, smem, c->stream>>>(c->ntiles, (const SpmvTile *)c->d_tiles, (const T *)c->d_vals,
-                                                    c->d_rowptr, c->d_cols, x, y, (T *)c->d_chunk_sum, sc);
-        c->launches++;
-        if (c->nlong > 0) {
-            combine_long_rows_kernel<T><<<(c->nlong + 127) / 128, 128, 0, c->stream>>>(
-                c->nlong, (const LongRow *)c->d_long, (const T *)c->d_chunk_sum, y);
-            c->launches++;
-        }
-        return 0;
-    }
     template <int S, bool DOT>
     static int spmv_tma(cgb200_ctx *c, const T *x, T *y, const CgScalars<T> &sc) {
         using K = TmaCfg<T, S>;
@@ -857,59 +843,12 @@ template <typename T> struct Engine {
         }
         return 0;
     }
-    // Row schedule for grids (see spmm_sched_kernel): patches of PY x PZ lines, cut into runs of XS rows.
-    static int build_row_schedule(cgb200_ctx *c, int R) {
-        if (c->d_runs && c->sched_R == R) return 0;
-        if (c->d_runs) cudaFree(c->d_runs);
-        c->d_runs = nullptr;
-        c->sched_R = R;
-        c->sched_units = 0;
-        const long long nx = c->grid_nx, ny = c->grid_ny, n = c->n;
-        const long long nz = (n + nx * ny - 1) / (nx * ny);
-        int PY = R, PZ = 1;
-        if (nz > 1) {
-            PY = 1;
-            while (PY * PY < R) PY *= 2;
-            PZ = std::max(1, R / PY);
-        }
-        const int XS = 16;
-        std::vector<RowRun> runs;
-        for (long long z0 = 0; z0 < nz; z0 += PZ)
-            for (long long y0 = 0; y0 < ny; y0 += PY)
-                for (long long x0 = 0; x0 < nx; x0 += XS) {
-                    for (int g = 0; g < R; g++) {
-                        const long long yy = y0 + g % PY, zz = z0 + g / PY;
-                        RowRun rr = {0, 0};
-                        if (g < PY * PZ && yy < ny && zz < nz) {
-                            const long long start = x0 + nx * (yy + ny * zz);
-                            const long long len = std::min<long long>(std::min<long long>(XS, nx - x0), n - start);
-                            if (len > 0) rr = RowRun{(int)start, (int)len};
-                        }
-                        runs.push_back(rr);
-                    }
-                }
-        c->sched_units = (int)(runs.size() / R);
-        CU(cudaMalloc(&c->d_runs, std::max<size_t>(1, runs.size()) * sizeof(RowRun)));
-        CU(cudaMemcpy(c->d_runs, runs.data(), runs.size() * sizeof(RowRun), cudaMemcpyHostToDevice));
-        return 0;
-    }
     // (no programmatic dependent launch for the SpMM: it has no matrix-only prologue to overlap, and its blocks
     //  becoming resident beside the direction update's cost 30 % of the C3 iteration -- 1136 -> 1476 us, measured)
     template <int V, int G, bool DOT>
     static int launch_spmm(cgb200_ctx *c, int k, const T *x, T *y, const CgScalars<T> &sc) {
         const int block = 256;
         const size_t smem = (size_t)block * V * sizeof(T);
-        if (c->spmm_schedule && c->grid_nx > 0) {
-            auto kern = spmm_sched_kernel<T, V, G, DOT>;
-            TRY(build_row_schedule(c, block / G));
-            const int grid = persistent_grid(c, kern, block, smem, c->sched_units);
-            c->spmv_grid_last = grid;
-            CU(launch_kernel(kern, dim3(grid), dim3(block), smem, c->stream, /*pdl*/ false, c->n, k, c->sched_units,
-                             (const RowRun *)c->d_runs, (const T *)c->d_vals, (const int *)c->d_rowptr,
-                             (const int *)c->d_cols, x, y, sc));
-            c->launches++;
-            return 0;
-        }
         auto kern = spmm_kernel<T, V, G, DOT>;
         const long long work = ((long long)c->n + (block / G) - 1) / (block / G);
         const int grid = persistent_grid(c, kern, block, smem, work);
@@ -937,13 +876,7 @@ template <typename T> struct Engine {
             if (variant == 0 && c->irregular && c->auto_irregular && !sc.peer) variant = 3;
             switch (variant) {
             case 1: return spmv1<DOT>(c, x, y, sc);
-            case 2: return spmv_stream<DOT>(c, x, y, sc);
-            case 4: return spmv_tma<3, DOT>(c, x, y, sc);
-            case 5: return spmv_tma<4, DOT>(c, x, y, sc);
             case 3: return spmv_tma<2, DOT>(c, x, y, sc);
-            case 7: return spmv_tma_rows<3, DOT>(c, x, y, sc);
-            case 8: return spmv_tma_rows<4, DOT>(c, x, y, sc);
-            case 9: return spmv_tma_rows<6, DOT>(c, x, y, sc);
             default: return spmv_tma_rows<2, DOT>(c, x, y, sc); // 0 (auto), 6
             }
         }
@@ -1576,42 +1509,6 @@ static uint64_t hash_bytes(const void *ptr, size_t bytes, uint64_t seed) {
 }
 
 
-// Looks at the column offsets (col - row) of a sample of rows.  A matrix assembled on a lexicographically
-// numbered grid has very few distinct ones: {+-1, +-NX} in 2-D, {+-1, +-NX, +-NX*NY} in 3-D.  The strides only
-// steer the ORDER in which the SpMM kernel visits rows (locality); nothing depends on them being right.
-static void detect_grid(cgb200_ctx *c, const std::vector<int> &rp) {
-    c->grid_nx = c->grid_ny = 0;
-    if (c->d_runs) cudaFree(c->d_runs);
-    c->d_runs = nullptr;
-    c->sched_R = 0;
-    const int n = c->n;
-    if (n < 4096 || c->max_row < 3 || c->max_row > 9) return;
-    std::set<long long> offs;
-    std::vector<int> buf((size_t)c->max_row);
-    const int samples = 257;
-    for (int s = 0; s < samples; s++) {
-        const int i = (int)((long long)s * (n - 1) / (samples - 1));
-        const int len = rp[i + 1] - rp[i];
-        if (len <= 0) continue;
-        if (cudaMemcpy(buf.data(), c->d_cols + rp[i], (size_t)len * sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) {
-            cudaGetLastError();
-            return;
-        }
-        for (int j = 0; j < len; j++) offs.insert((long long)buf[j] - i);
-        if (offs.size() > 9) return;
-    }
-    std::vector<long long> pos;
-    for (long long o : offs)
-        if (o > 0) pos.push_back(o);
-    if (pos.size() == 2 && pos[0] == 1 && pos[1] >= 8) {
-        c->grid_nx = (int)pos[1];
-        c->grid_ny = (int)((n + pos[1] - 1) / pos[1]);
-    } else if (pos.size() == 3 && pos[0] == 1 && pos[1] >= 8 && pos[2] % pos[1] == 0) {
-        c->grid_nx = (int)pos[1];
-        c->grid_ny = (int)(pos[2] / pos[1]);
-    }
-}
-
 // 1 in *bad when some column index lies outside [0, ncols).  One pass over the index array at upload (C4: 0.75 GB,
 // ~0.15 ms): a bad index then is CGB200_ERR_ARG instead of a sticky device fault for the whole process.
 __global__ void __launch_bounds__(256) check_cols_kernel(long long nnz, const int *__restrict__ cols, int ncols, int *bad) {
@@ -1654,7 +1551,9 @@ static int upload_matrix(cgb200_ctx *c, const void *aValues, const int *aPointer
     // (device-side assembly, assemble.cuh, hands in the handle's own buffers: nothing to copy then)
     if (aValues != c->d_vals) CU(cudaMemcpyAsync(c->d_vals, aValues, (size_t)nnz * vs, cudaMemcpyDefault, c->stream));
     if (aCols != c->d_cols) CU(cudaMemcpyAsync(c->d_cols, aCols, (size_t)nnz * sizeof(int), cudaMemcpyDefault, c->stream));
-    CU(cudaMemcpyAsync(c->d_rowptr, rp.data(), ((size_t)n + 1) * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    // (straight from the caller's array: a copy out of the pageable `rp` costs 20-30 ms at 27 M rows)
+    if (aPointers != c->d_rowptr)
+        CU(cudaMemcpyAsync(c->d_rowptr, aPointers, ((size_t)n + 1) * sizeof(int), cudaMemcpyDefault, c->stream));
     if (nnz > 0) {
         int *d_bad = c->d_flag;
         CU(cudaMemsetAsync(d_bad, 0, sizeof(int), c->stream));
@@ -1686,7 +1585,6 @@ static int upload_matrix(cgb200_ctx *c, const void *aValues, const int *aPointer
     }
     TRY(DISPATCH(c, E::build_tiles(c, rp)));
     c->rowptr_hash = rh;
-    detect_grid(c, rp);
     TRY(DISPATCH(c, E::build_patterns(c)));
     c->matrix_ok = 1;
     return 0;
@@ -1822,7 +1720,6 @@ int cgb200_destroy(cgb200_handle c) {
     free_workspace(c);
     if (c->d_hist) cudaFree(c->d_hist);
     if (c->d_trace) cudaFree(c->d_trace);
-    if (c->d_runs) cudaFree(c->d_runs);
     for (void *b : {c->d_pat, c->d_pat_table, c->d_pat_build, c->d_plen, c->d_poff, c->d_pval, (void *)c->d_pat_chunks,
                     (void *)c->d_pspos, (void *)c->d_pat_mask, (void *)c->d_chunk_mask, c->d_dinv, c->d_march_runs, (void *)c->d_mcodes})
         if (b) cudaFree(b);
@@ -1869,7 +1766,6 @@ static int *option_slot(cgb200_handle c, const char *key) {
     if (!strcmp(key, "auto_irregular")) return &c->auto_irregular;
     if (!strcmp(key, "l2_keep")) return &c->l2_keep;
     if (!strcmp(key, "pattern")) return &c->pattern;
-    if (!strcmp(key, "pattern_regs")) return &c->pattern_regs;
     if (!strcmp(key, "cg2")) return &c->cg2;
     if (!strcmp(key, "cg2_stages")) return &c->cg2_stages;
     if (!strcmp(key, "march")) return &c->march;
@@ -1877,7 +1773,6 @@ static int *option_slot(cgb200_handle c, const char *key) {
     if (!strcmp(key, "march_ok")) return &c->mplan.ok;      // read-only: the plane-marching dir_spmv applies
     if (!strcmp(key, "cg2_ok")) return &c->cg2_ok;          // read-only: the dictionary's offsets fit the window plan
     if (!strcmp(key, "patterns")) return &c->npat;        // read-only: distinct row patterns found (0: CSR kernels in use)
-    if (!strcmp(key, "spmm_schedule")) return &c->spmm_schedule;
     if (!strcmp(key, "pdl_early")) return &c->pdl_early;
     if (!strcmp(key, "vec_carveout")) return &c->vec_carveout;
     if (!strcmp(key, "trace")) return &c->trace_iters;
@@ -1967,6 +1862,23 @@ int cgb200_solve_pcg(cgb200_handle c, const void *dinv, const void *b, void *x, 
     if (c->extra_cols) return fail(CGB200_ERR_UNSUPPORTED, "preconditioned CG is not available on a row-block shard");
     DeviceGuard guard(c->device);
     return DISPATCH(c, E::solve_pcg_api(c, dinv, b, x, k, max_iterations, tol, iterations, resnorm, rr_hist));
+}
+
+long long cgb200_check_guards(cgb200_handle c) {
+    if (!c) return fail(CGB200_ERR_ARG, "NULL handle");
+    if (!c->guard || !c->x_base) return fail(CGB200_ERR_ARG, "no guard zones: set CGB200_GUARD=1 before the first solve on the handle");
+    DeviceGuard guard(c->device);
+    CU(cudaStreamSynchronize(c->stream));
+    long long bad = 0;
+    std::vector<unsigned char> z(GUARD_BYTES);
+    struct { void *base; size_t payload; } bufs[] = {{c->x_base, c->x_bytes}, {c->q_base, c->q_bytes}, {c->vec_base, c->vec_bytes}};
+    for (auto &b : bufs)
+        for (int side = 0; side < 2; side++) {
+            const char *src = (const char *)b.base + (side ? GUARD_BYTES + b.payload : 0);
+            CU(cudaMemcpy(z.data(), src, GUARD_BYTES, cudaMemcpyDeviceToHost));
+            for (unsigned char v : z) bad += v != GUARD_BYTE;
+        }
+    return bad;
 }
 
 int cgb200_time_kernel(cgb200_handle c, int which, int k, int reps, double *ms_avg) {

@@ -544,19 +544,14 @@ spmv1_kernel(int n, const T *__restrict__ vals, const int *__restrict__ rowptr,
 }
 
 // ---------------------------------------------------------------------------
-// SpMV, one right-hand side, "CSR-stream": the schedule for short or irregular rows.
+// CSR-stream tiles (the schedule of the TMA-fed kernels below).
 //
-// The non-zeros are cut, at matrix set-up, into tiles of at most TILE entries that hold
-// whole rows (a row longer than a tile is cut into chunks).  A block
-//   1. streams the tile's values and column indices with fully coalesced 128-bit loads
-//      (every lane busy whatever the row lengths are), gathers x[col] and leaves the
-//      products in shared memory;
-//   2. sums each row's products out of shared memory -- one thread per row when rows
-//      are short, a power-of-two group of lanes per row when the tile holds few rows.
-// Load balance is per non-zero, not per row, so power-law matrices cost the same per
-// entry as stencils.  A long row's chunk sums go to `chunk_sum` and are added up by
-// combine_long_rows_kernel; the fused d.q term of such a row uses linearity,
-// d_i * (partial row sum), so it needs no second pass.
+// The non-zeros are cut, at matrix set-up, into tiles of at most RowTileCfg::CAP entries that hold whole rows (a
+// row longer than a tile is cut into chunks).  Load balance is per non-zero, not per row, so power-law matrices
+// cost the same per entry as stencils.  A long row's chunk sums go to `chunk_sum` and are added up by
+// combine_long_rows_kernel; the fused d.q term of such a row uses linearity, d_i * (partial row sum), so it needs
+// no second pass.  (The plain-load variant of round 1, spmv_stream_kernel, measured slower than both TMA-fed
+// kernels on every config and is gone; it is in git.)
 // ---------------------------------------------------------------------------
 struct SpmvTile {
     int r0;   // first row
@@ -565,132 +560,10 @@ struct SpmvTile {
     int p1;   // one past the last non-zero
 };
 
-template <typename T> struct StreamCfg {
-    static constexpr int VPT = VecW<T>::value;                 // values per 128-bit load
-    static constexpr int U = (sizeof(T) == 16) ? 4 : (sizeof(T) == 4 ? 2 : 4);   // loads in flight per thread
-    static constexpr int THREADS = 256;
-    static constexpr int TILE = THREADS * VPT * U;             // products held in shared memory
-    static constexpr int CAP = TILE - 4;                       // non-zeros per tile (16-byte aligned windows may start 3 entries early)
-    static constexpr int RMAX = 512;                           // rows per tile (their row offsets are staged in shared memory)
-};
-
-template <int VPT> struct ColPack;
-template <> struct ColPack<1> { int c[1]; };
-template <> struct alignas(8) ColPack<2> { int c[2]; };
-template <> struct alignas(16) ColPack<4> { int c[4]; };
-
-template <typename T, bool DOT>
-__global__ void __launch_bounds__(256)
-spmv_stream_kernel(int ntiles, const SpmvTile *__restrict__ tiles, const T *__restrict__ vals,
-                   const int *__restrict__ rowptr, const int *__restrict__ cols,
-                   const T *__restrict__ x, T *__restrict__ y, T *__restrict__ chunk_sum,
-                   CgScalars<T> sc) {
-    using C = StreamCfg<T>;
-    constexpr int VPT = C::VPT, U = C::U, NT = C::THREADS;
-    using VP = Pack<T, VPT>;
-    using CP = ColPack<VPT>;
-    if (DOT) {
-        if (*sc.n_active == 0) return;
-    }
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    T *prod = reinterpret_cast<T *>(smem_raw);                 // [TILE]
-    T *red = prod + C::TILE;                                   // [NT] block-reduction scratch
-    const int t = threadIdx.x;
-    T dot[1] = {Sc<T>::zero()};
-
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const SpmvTile tl = tiles[tile];
-        const int base = tl.p0 - (tl.p0 % VPT);
-        // ---- 1. stream A, gather x, products to shared memory
-        VP av[U];
-        CP cv[U];
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            const int j0 = base + (t + u * NT) * VPT;
-            if (j0 < tl.p1) {
-                av[u] = ld_stream_bytes(reinterpret_cast<const VP *>(vals + j0));
-                cv[u] = ld_stream_bytes(reinterpret_cast<const CP *>(cols + j0));
-            }
-        }
-        T xv[U][VPT];
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            const int j0 = base + (t + u * NT) * VPT;
-#pragma unroll
-            for (int e = 0; e < VPT; e++) {
-                const int j = j0 + e;
-                if (j >= tl.p0 && j < tl.p1) xv[u][e] = __ldg(x + cv[u].c[e]);
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            const int j0 = base + (t + u * NT) * VPT;
-#pragma unroll
-            for (int e = 0; e < VPT; e++) {
-                const int j = j0 + e;
-                if (j >= tl.p0 && j < tl.p1) prod[j - base] = Sc<T>::mul(av[u].v[e], xv[u][e]);
-            }
-        }
-        __syncthreads();
-
-        if (tl.r1 >= 0) {
-            // ---- 2. row sums
-            const int rows = tl.r1 - tl.r0;
-            int lpr = 1;
-            while (lpr < 32 && rows * lpr * 2 <= NT) lpr *= 2;
-            const int g = t / lpr, lane = t % lpr, groups = NT / lpr;
-            for (int rr0 = 0; rr0 < rows; rr0 += groups) {
-                const int rr = rr0 + g;
-                const bool valid = rr < rows;
-                T sum = Sc<T>::zero();
-                if (valid) {
-                    const int lo = __ldg(rowptr + tl.r0 + rr) - base;
-                    const int hi = __ldg(rowptr + tl.r0 + rr + 1) - base;
-                    for (int j = lo + lane; j < hi; j += lpr) sum = Sc<T>::add(sum, prod[j]);
-                }
-                for (int off = lpr >> 1; off > 0; off >>= 1) {
-                    if constexpr (Sc<T>::cplx) {
-                        sum.x += __shfl_xor_sync(0xffffffffu, sum.x, off);
-                        sum.y += __shfl_xor_sync(0xffffffffu, sum.y, off);
-                    } else {
-                        sum += __shfl_xor_sync(0xffffffffu, sum, off);
-                    }
-                }
-                if (valid && lane == 0) {
-                    const int row = tl.r0 + rr;
-                    y[row] = sum;
-                    if (DOT) dot[0] = Sc<T>::fma(__ldg(x + row), sum, dot[0]);
-                }
-            }
-        } else {
-            // ---- 2'. chunk of a long row: one sum for the whole tile
-            T part[1] = {Sc<T>::zero()};
-            for (int j = tl.p0 - base + t; j < tl.p1 - base; j += NT) part[0] = Sc<T>::add(part[0], prod[j]);
-            block_col_reduce<T, 1>(part, 1, red);
-            if (t == 0) {
-                chunk_sum[-(tl.r1 + 1)] = red[0];
-                if (DOT) dot[0] = Sc<T>::fma(__ldg(x + tl.r0), red[0], dot[0]);
-            }
-        }
-        __syncthreads();   // prod is rewritten by the next tile
-    }
-
-    if (DOT) {
-        block_col_reduce<T, 1>(dot, 1, red);
-        if (publish_and_arrive<T, 1>(red, 1, 1, sc.partial, sc.ticket + TK_SPMV)) {
-            grid_col_reduce<T, 1>(sc.partial, 1, 1, 1, red);
-            if (t == 0) {
-                sc.dq[0] = red[0];
-                sc.ticket[TK_SPMV] = 0;
-            }
-        }
-    }
-}
-
 // ---------------------------------------------------------------------------
 // SpMV, one right-hand side, CSR-stream fed by the TMA engine.
 //
-// Same tiles and the same two phases as spmv_stream_kernel, but the matrix stream never
+// Two phases per tile (products to shared memory, then row sums), and the matrix stream never
 // passes through registers: one elected thread issues 1-D bulk async copies
 // (cp.async.bulk global -> shared, completion counted in bytes on an mbarrier) for the
 // tile's values, column indices and row offsets into an S-stage ring, S tiles ahead of
@@ -1452,81 +1325,6 @@ spmv_pattern_kernel(int n, int nchunks, int nchunks_interior, const int *__restr
     }
 }
 
-// EXPERIMENT (option "pattern_regs", off: written after this round's GPU budget was spent, not yet run on hardware).
-// ncu on spmv_pattern_kernel (C4): L1TEX throughput 85 %, of which a third is the table look-up -- 17 shared-memory
-// reads per row (length, 8 offsets, 8 values) that return the same values for nearly every row of a warp -- and one
-// gather in nine is the padding entry.  Here a thread keeps the pattern it used last in registers and re-reads the
-// table only when the pattern number changes, and gathers exactly `len` entries.  Rows of <= 8 entries, one GPU.
-template <typename T, bool DOT>
-__global__ void __launch_bounds__(PAT_THREADS)
-spmv_pattern_regs_kernel(int n, int nchunks, int npat, const unsigned short *__restrict__ pat, const int *__restrict__ p_len,
-                         const int *__restrict__ p_off, const T *__restrict__ p_val, const T *__restrict__ x,
-                         T *__restrict__ y, CgScalars<T> sc) {
-    constexpr int STRIDE = 8;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    T *red = reinterpret_cast<T *>(smem_raw);                                  // [PAT_THREADS]
-    T *s_val = red + PAT_THREADS;                                              // [npat][STRIDE]
-    int *s_off = reinterpret_cast<int *>(s_val + npat * STRIDE);               // [npat][STRIDE]
-    int *s_len = s_off + npat * STRIDE;                                        // [npat]
-    const int t = threadIdx.x;
-    for (int i = t; i < npat * STRIDE; i += PAT_THREADS) {
-        const int id = i / STRIDE, j = i % STRIDE;
-        s_val[i] = p_val[id * PAT_MAXLEN + j];
-        s_off[i] = p_off[id * PAT_MAXLEN + j];
-    }
-    for (int i = t; i < npat; i += PAT_THREADS) s_len[i] = p_len[i];
-    __syncthreads();
-    pdl_wait();
-    if (sc.pdl_early) pdl_trigger();
-    if (DOT) {
-        if (*sc.n_active == 0) return;
-    }
-    const unsigned long long keep = l2_policy(sc.l2_keep != 0);
-    T dot[1] = {Sc<T>::zero()};
-    int cid = -1, clen = 0;
-    int coff[STRIDE];
-    T cval[STRIDE];
-#pragma unroll
-    for (int u = 0; u < STRIDE; u++) {
-        coff[u] = 0;
-        cval[u] = Sc<T>::zero();
-    }
-    for (int ci = (int)blockIdx.x; ci < nchunks; ci += (int)gridDim.x) {
-        const int row_end = min(n, (ci + 1) * PAT_CHUNK);
-        for (int row = ci * PAT_CHUNK + t; row < row_end; row += PAT_THREADS) {
-            const int id = pat[row];
-            if (id != cid) {             // rare: the interior pattern covers almost every row of a grid
-                cid = id;
-                clen = s_len[id];
-#pragma unroll
-                for (int u = 0; u < STRIDE; u++) {
-                    coff[u] = s_off[id * STRIDE + u];
-                    cval[u] = s_val[id * STRIDE + u];
-                }
-            }
-            const T *xrow = x + row;
-            T xv[STRIDE];
-#pragma unroll
-            for (int u = 0; u < STRIDE; u++) xv[u] = u < clen ? __ldg(xrow + coff[u]) : Sc<T>::zero();
-            T sum = Sc<T>::zero();
-#pragma unroll
-            for (int u = 0; u < STRIDE; u++) sum = Sc<T>::fma(cval[u], xv[u], sum);   // padding: coefficient 0, same result
-            st_hint_bytes(y + row, sum, keep);
-            if (DOT) dot[0] = Sc<T>::fma(__ldg(xrow), sum, dot[0]);
-        }
-    }
-    if (DOT) {
-        block_col_reduce<T, 1>(dot, 1, red);
-        if (publish_and_arrive<T, 1>(red, 1, 1, sc.partial, sc.ticket + TK_SPMV)) {
-            grid_col_reduce<T, 1>(sc.partial, 1, 1, 1, red);
-            if (t == 0) {
-                sc.dq[0] = red[0];
-                sc.ticket[TK_SPMV] = 0;
-            }
-        }
-    }
-}
-
 // ---------------------------------------------------------------------------
 // SpMM, k right-hand sides in row-major [n][k]: G lanes per row, lane cp owns the
 // V-wide column pack cp (one 128-bit gather per non-zero per lane when
@@ -1567,89 +1365,6 @@ spmm_kernel(int n, int k, const T *__restrict__ vals, const int *__restrict__ ro
 #pragma unroll 4
             for (int j = lo; j < hi; j++) {
                 const T a = __ldg(vals + j);   // one address for the G lanes of the row: a broadcast
-                const int c = __ldg(cols + j);
-                const P xv = *reinterpret_cast<const P *>(x + (size_t)c * k + (size_t)cp * V);
-#pragma unroll
-                for (int v = 0; v < V; v++) acc[v] = Sc<T>::fma(a, xv.v[v], acc[v]);
-            }
-            P out;
-#pragma unroll
-            for (int v = 0; v < V; v++) out.v[v] = acc[v];
-            *reinterpret_cast<P *>(y + (size_t)row * k + (size_t)cp * V) = out;
-            if (DOT) {
-                const P xo = *reinterpret_cast<const P *>(x + (size_t)row * k + (size_t)cp * V);
-#pragma unroll
-                for (int v = 0; v < V; v++) dot[v] = Sc<T>::fma(xo.v[v], acc[v], dot[v]);
-            }
-        }
-    }
-
-    if (DOT) {
-        block_col_reduce<T, V>(dot, G, smem);
-        if (publish_and_arrive<T, V>(smem, kv, k, sc.partial, sc.ticket + TK_SPMV)) {
-            grid_col_reduce<T, V>(sc.partial, G, kv, k, smem);
-            if (t < kv) {
-#pragma unroll
-                for (int v = 0; v < V; v++) sc.dq[t * V + v] = smem[t * V + v];
-            }
-            if (t == 0) sc.ticket[TK_SPMV] = 0;
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------
-// SpMM with a row SCHEDULE, for matrices whose columns sit at a few fixed offsets from the diagonal
-// (finite-difference / finite-element grids numbered lexicographically).
-//
-// spmm_kernel hands consecutive rows to consecutive blocks, so the only reuse an SM's L1 sees is the
-// +-1 neighbour: of the 7 k-wide rows of x a 7-point row gathers, 5 come from L2, and at k = 32 the
-// kernel is bound by L2 -> SM traffic (5 x the vector), not by HBM.  Here a block instead owns a patch of
-// PY x PZ grid lines and marches along them: the R = PY*PZ row groups of the block work on rows
-// start_g + s at step s, so the x rows gathered as "+1" at one step are the centre of the next and the
-// "-1" of the one after, and the +-NX / +-NX*NY neighbours inside the patch are gathered by the same
-// block in the same step.  What still comes from L2 is the next slice (R rows) plus the patch faces:
-// 2 x the vector for a 4 x 4 patch instead of 5 x.  The schedule (RowRun per group per unit) is built on
-// the host from the detected strides; ANY schedule gives the same bits, rows are independent.
-// ---------------------------------------------------------------------------
-struct RowRun {
-    int start;   // first row of the run
-    int len;     // consecutive rows (0: idle group)
-};
-
-template <typename T, int V, int G, bool DOT>
-__global__ void __launch_bounds__(256)
-spmm_sched_kernel(int n, int k, int nunits, const RowRun *__restrict__ runs, const T *__restrict__ vals,
-                  const int *__restrict__ rowptr, const int *__restrict__ cols, const T *__restrict__ x,
-                  T *__restrict__ y, CgScalars<T> sc) {
-    pdl_wait();
-    if (sc.pdl_early) pdl_trigger();
-    if (DOT) {
-        if (*sc.n_active == 0) return;
-    }
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    T *smem = reinterpret_cast<T *>(smem_raw);
-    using P = Pack<T, V>;
-    const int t = threadIdx.x;
-    const int cp = t % G, grp = t / G;
-    const int kv = k / V;
-    const bool active = cp < kv;
-    const int R = blockDim.x / G;
-    T dot[V];
-#pragma unroll
-    for (int v = 0; v < V; v++) dot[v] = Sc<T>::zero();
-
-    for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
-        const RowRun run = runs[(size_t)u * R + grp];
-        if (!active) continue;
-        for (int s = 0; s < run.len; s++) {
-            const int row = run.start + s;
-            const int lo = __ldg(rowptr + row), hi = __ldg(rowptr + row + 1);
-            T acc[V];
-#pragma unroll
-            for (int v = 0; v < V; v++) acc[v] = Sc<T>::zero();
-#pragma unroll 4
-            for (int j = lo; j < hi; j++) {
-                const T a = __ldg(vals + j);
                 const int c = __ldg(cols + j);
                 const P xv = *reinterpret_cast<const P *>(x + (size_t)c * k + (size_t)cp * V);
 #pragma unroll

@@ -439,8 +439,9 @@ int cgb200_shard_p2p_export(cgb200_shard sh, void *out_blob) {
     P2pBlob blob;
     memset(&blob, 0, sizeof(blob));
     CU(cudaIpcGetMemHandle(&blob.buf, sh->p2p_buf));
-    CU(cudaIpcGetMemHandle(&blob.vecs, c->vec_block));
-    for (int i = 0; i < 4; i++) blob.off[i] = (long long)c->vec_off[i];
+    CU(cudaIpcGetMemHandle(&blob.vecs, c->vec_base));          // (an IPC handle names the whole allocation)
+    const long long lead = (const char *)c->vec_block - (const char *)c->vec_base;
+    for (int i = 0; i < 4; i++) blob.off[i] = lead + (long long)c->vec_off[i];
     memcpy(out_blob, &blob, sizeof(blob));
     return CGB200_OK;
 }
@@ -457,7 +458,7 @@ int cgb200_shard_p2p_import(cgb200_shard sh, const void *all_blobs, const long l
     const P2pBlob *blobs = (const P2pBlob *)all_blobs;
     sh->max_send = 0;
     for (int p = 0; p < sh->world; p++) {
-        void *buf = sh->p2p_buf, *vecs = c->vec_block;
+        void *buf = sh->p2p_buf, *vecs = c->vec_base;
         if (p != sh->rank) {
             CU(cudaIpcOpenMemHandle(&buf, blobs[p].buf, cudaIpcMemLazyEnablePeerAccess));
             sh->opened.push_back(buf);

@@ -73,13 +73,13 @@ CGB200_API int cgb200_destroy(cgb200_handle h);
 CGB200_API int cgb200_set_stream(cgb200_handle h, void *cuda_stream);
 
 /* Tuning knobs (the reference's are compile-time macros, clcg.c:37-43).
- *   "spmv_variant"   [k = 1 only]
- *                    0 auto (= 6)
- *                    1 CSR-vector: lanes_per_row lanes per row
- *                    2 CSR-stream: tiles of non-zeros, products staged in shared memory, plain loads
- *                    3/4/5 CSR-stream fed by TMA bulk copies through a 2/3/4-stage mbarrier ring: every gather of a
- *                          tile in flight at once, balanced row sums (the schedule for power-law matrices)
- *                    6/7/8/9 row-direct CSR-stream fed by TMA (2/3/4/6 stages, no product buffer)
+ *   "spmv_variant"   [k = 1, CSR kernels]
+ *                    0 auto: 6, or 3 for matrices whose row lengths vary wildly ("auto_irregular")
+ *                    1 CSR-vector: lanes_per_row lanes per row (the simplest kernel; also the fallback without a schedule)
+ *                    3 CSR-stream fed by TMA bulk copies through a 2-stage mbarrier ring: every gather of a tile in
+ *                      flight at once, balanced row sums (the schedule for power-law matrices)
+ *                    6 row-direct CSR-stream fed by TMA (no product buffer)
+ *                    (2, 4, 5, 7, 8, 9 of round 1 -- plain-load stream, deeper rings -- measured slower everywhere and were removed)
  *   "solver"         0 auto: one cooperative launch for the whole solve when an iteration's working set
  *                      fits the L2 (2 grid barriers per iteration), else three kernels per iteration
  *                    1 three kernels per iteration in CUDA graphs     2 single cooperative launch
@@ -100,7 +100,6 @@ CGB200_API int cgb200_set_stream(cgb200_handle h, void *cuda_stream);
  *                    -1 by size (on when the three vectors fit half the L2)
  *   "pattern"        1 (default): k = 1 runs from the row-pattern dictionary when the matrix has <= 4096 distinct rows
  *                    ("patterns", read-only, tells how many were found; 0 = CSR kernels in use)
- *   "pattern_regs"   0 (default) | 1: EXPERIMENT, not yet run on hardware -- the last pattern kept in registers
  *   "cg2"            1 (default): k = 1 on a matrix with a row-pattern dictionary whose column offsets fit a window
  *                    plan runs the TWO-kernel iteration (csrc/cg2.cuh: direction update folded into the SpMV's
  *                    gather, x lagging one update, 9 vector passes instead of 11); "cg2_ok" (read-only) tells
@@ -109,8 +108,6 @@ CGB200_API int cgb200_set_stream(cgb200_handle h, void *cuda_stream);
  *                    run the plane-marching variant (csrc/cg2_march.cuh: each piece of the vectors is staged once per
  *                    strip instead of three times); 2: whenever it applies; 0: never;
  *                    "march_ok" (read-only) tells whether it applies, "march_lz" overrides the planes per run
- *   "spmm_schedule"  0 (default) | 1: k > 1 on a matrix with grid structure (few fixed column offsets) visits rows
- *                    patch by patch for L1 reuse of the gathered rows (spmm_sched_kernel)
  *   "trace"          n > 0: the loop kernels stamp %globaltimer into an 8-slot record per iteration for the
  *                    first n iterations of a solve; read it with cgb200_read_trace()
  */
@@ -169,6 +166,11 @@ CGB200_API int cgb200_read_trace(cgb200_handle h, unsigned long long *out, int i
 /* Debug aid: the row-pattern dictionary as it sits in device memory.  which: 0 the 16-bit pattern number of
  * every row [n], 1 pattern lengths [patterns], 2 column offsets and 3 values [patterns][32]. */
 CGB200_API int cgb200_debug_read_patterns(cgb200_handle h, int which, void *out, size_t bytes);
+
+/* Debugging aid for pools where compute-sanitizer cannot run: with CGB200_GUARD=1 in the environment when a handle's
+ * work vectors are allocated, each of them sits between two 4 KB zones filled with a byte pattern; this returns
+ * the number of bytes a kernel changed there since (0 = no out-of-bounds store), or < 0 on failure. */
+CGB200_API long long cgb200_check_guards(cgb200_handle h);
 
 /* Facts about a handle, for benches and tests:
  * [0] n [1] nnz [2] dtype [3] lanes_per_row [4] persistent grid of the SpMV kernel

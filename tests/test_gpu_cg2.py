@@ -612,3 +612,36 @@ def test_config2_assembled_on_the_device_at_size(gpu):
     finally:
         M.close()
     print(f"assembly of config 2: device {t_dev * 1e3:.1f} ms (handle ready), vectorised host generator {t_host * 1e3:.1f} ms")
+
+
+def test_no_kernel_stores_outside_its_vectors(gpu, monkeypatch):
+    """compute-sanitizer is closed on this GPU pool, so the out-of-bounds-store check is the engine's own: with
+    CGB200_GUARD=1 every work vector sits between two 4 KB pattern zones (`cgb200_check_guards`).  Ragged sizes (the last
+    chunk / pack partly empty), every iteration variant, multi-RHS, PCG, complex values."""
+    import cg_b200.problems as P
+    monkeypatch.setenv("CGB200_GUARD", "1")
+    L = gpu._lib.lib()
+    cases = [(P.laplace3d(23), np.float64), (P.laplace3d(40, nz=7), np.float64), (P.poisson2d(600), np.float32),
+             (P.helmholtz_fe(70), np.complex128), (P.helmholtz_fe(520), np.complex64), (P.laplace3d(32), np.float64),
+             (sp.diags([-1.0, 2.5, -1.0], [-1, 0, 1], shape=(1025, 1025), format="csr"), np.float64),
+             (P.powerlaw_spd(n=9001, nnz_target=120000, max_row=2500), np.float64)]
+    for A, dt in cases:
+        A = sp.csr_matrix(A).astype(dt)
+        A.sort_indices()
+        n = A.shape[0]
+        b = rand(np.random.default_rng(n), n, dt)
+        with gpu.Matrix.from_scipy(A) as M:
+            M.set_option("solver", 1)
+            for opts in ({"cg2": 1, "march": 2}, {"cg2": 1, "march": 0}, {"cg2": 0}, {"cg2": 0, "pattern": 0}):
+                for key, v in opts.items():
+                    M.set_option(key, v)
+                M.solve(b, max_iterations=20)
+                M.solve(b, max_iterations=3)                     # (fewer than a graph chunk: plain launches)
+            M.solve_pcg(b, max_iterations=10)
+            assert L.cgb200_check_guards(M._h) == 0, (n, dt)
+        with gpu.Matrix.from_scipy(A) as M:                        # multi-RHS workspace
+            M.set_option("solver", 1)
+            M.solve(np.concatenate([b, b[::-1], 2 * b]), k=3, max_iterations=12)
+            M.set_option("solver", 2)
+            M.solve(np.concatenate([b, b[::-1], 2 * b]), k=3, max_iterations=12)
+            assert L.cgb200_check_guards(M._h) == 0, (n, dt, "k=3")

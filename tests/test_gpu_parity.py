@@ -177,7 +177,7 @@ def test_spmv_stream_schedule_irregular_rows(gpu, cpu_ref, dname):
         assert M.get_option("spmv_variant") == 0
         tol = 2e-5 if dname in ("f32", "c64") else 1e-13
         alpha = np.sum(x.astype(wide) ** 2) / np.sum(x.astype(wide) * exact)     # unconjugated, as vdot.cl:15
-        for variant in (0, 1, 2, 3, 4, 5, 6, 7, 8, 9):
+        for variant in (0, 1, 3, 6):
             M.set_option("spmv_variant", variant)
             y = M.spmv(x)
             assert rel(y, exact) < tol, variant
@@ -750,11 +750,10 @@ def test_native_oclcgex_executable(gpu, tmp_path):
 
 @pytest.mark.parametrize("dname", ["f64", "c64"])
 @pytest.mark.parametrize("kind,k", [("lap3d", 32), ("lap3d", 8), ("lap3d", 3), ("lap3d", 2), ("poisson", 4), ("poisson", 32)])
-def test_spmm_row_schedule_on_grids(gpu, cpu_ref, dname, kind, k):
-    """k > 1 on a matrix with grid structure: rows are visited patch by patch (spmm_sched_kernel).  Rows are
-    independent, so y has the same bits as with the plain row order; the CG iterate (whose dot products are
-    summed in a different block order) agrees with the oracle as usual.  Grids whose size is not a multiple of
-    the patch, more row groups than patch lines, a matrix without grid structure."""
+def test_spmm_on_grids(gpu, cpu_ref, dname, kind, k):
+    """k > 1 on grid matrices: y against the exact product, the CG iterate against the oracle; a matrix without
+    grid structure likewise.  (Round 1's patch-by-patch row schedule, spmm_sched_kernel, measured 1.25-1.9 x slower than
+    the plain row order and was removed.)"""
     import cg_b200.problems as P
     dt = DT[dname]
     A = (P.laplace3d(21) if kind == "lap3d" else P.poisson2d(83)).astype(dt)
@@ -763,13 +762,9 @@ def test_spmm_row_schedule_on_grids(gpu, cpu_ref, dname, kind, k):
     rng = np.random.default_rng(k)
     X = np.concatenate([rand(rng, n, dt) for _ in range(k)])
     with gpu.Matrix.from_scipy(A) as M:
-        M.set_option("spmm_schedule", 1)
         M.set_option("solver", 1)                 # three kernels per iteration: the SpMM kernel fused with d.q
         y1 = M.spmv(X, k=k)
         x1, _ = M.solve(X, k=k, max_iterations=25)
-        M.set_option("spmm_schedule", 0)
-        y0 = M.spmv(X, k=k)
-    assert np.array_equal(y0, y1)
     exact = np.concatenate([A @ X[c * n:(c + 1) * n] for c in range(k)])
     assert rel(y1, exact) < (2e-6 if dname == "c64" else 1e-14)
     ref, wide = oracle_pair(cpu_ref, dname, A.data, A.indptr, A.indices, X, k=k, iters=25)
