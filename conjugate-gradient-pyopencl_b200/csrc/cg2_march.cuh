@@ -34,26 +34,26 @@ struct MarchPlan {
     int has_low, has_high;        // a halo plane below the first / above the last owned plane (row-block shards)
     long long low_src, high_src;  // its first element in the vectors
     int nruns;
+    int grid;            // blocks the runs were dealt to: the launch grid
 };
 struct MarchRun {
-    int strip, z0, len, pad;
+    int strip, z0, len;
+    int next;            // index of the same block's next run, -1: none (block b starts with runs[b])
 };
 
 // The sequence of pieces a block loads: for each of its runs the planes z0 - 1 .. z0 + len.
 struct MarchWalk {
     const MarchRun *runs;
-    int nruns, k, j;
+    int j;
     MarchRun run, nxt;
     bool have_nxt;
     __device__ __forceinline__ bool start(const MarchRun *r, int n) {
         runs = r;
-        nruns = n;
-        k = 0;
         j = -1;
-        if ((int)blockIdx.x >= nruns) return false;
+        if ((int)blockIdx.x >= n) return false;
         run = runs[blockIdx.x];
-        have_nxt = (int)blockIdx.x + (int)gridDim.x < nruns;
-        if (have_nxt) nxt = runs[blockIdx.x + gridDim.x];          // (requested a whole run ahead)
+        have_nxt = run.next >= 0;
+        if (have_nxt) nxt = runs[run.next];          // (requested a whole run ahead)
         return true;
     }
     __device__ __forceinline__ bool next() {
@@ -63,11 +63,9 @@ struct MarchWalk {
         }
         if (!have_nxt) return false;
         run = nxt;
-        k++;
         j = -1;
-        const int rr = (int)blockIdx.x + (k + 1) * (int)gridDim.x;
-        have_nxt = rr < nruns;
-        if (have_nxt) nxt = runs[rr];
+        have_nxt = run.next >= 0;
+        if (have_nxt) nxt = runs[run.next];
         return true;
     }
     __device__ __forceinline__ bool computes() const { return j >= 0 && j < run.len; }

@@ -509,30 +509,98 @@ template <typename T> struct Engine {
                 classify(off[(size_t)p * PAT_MAXLEN + j], &rel, &b);
                 (*codes)[(size_t)p * PAT_MAXLEN + j] = ((rel + 1) << 24) | (b - mp.lo0);
             }
-        // runs: every strip is cut into segments of lz planes.  A run of L planes loads L + 2 pieces, so long runs are
-        // cheap -- but the runs must spread evenly over the SMs: the cost of a choice is (rounds of runs) x (lz + what
-        // the two extra loads cost, ~0.35 of a computed piece each)
+        // runs.  A run of L planes loads L + 2 pieces (the extra two cost ~0.35 of a computed piece each), and block b
+        // starts with runs[b]; every run names the block's next one (MarchRun::next)
         const int grid = c->sm_count;
-        int best_lz = mp.nplanes;
-        double best = 1e300;
-        for (int segs = 1; segs <= mp.nplanes; segs++) {
-            const int lz = (mp.nplanes + segs - 1) / segs;
-            const long long nruns = (long long)mp.m * ((mp.nplanes + lz - 1) / lz);
-            const long long rounds = (nruns + grid - 1) / grid;
-            const double cost = (double)rounds * (lz + 0.7);
-            if (cost < best - 1e-9) {
-                best = cost;
-                best_lz = lz;
+        std::vector<MarchRun> inner;
+        auto touches_halo = [&](const MarchRun &r) {
+            return (r.z0 == 0 && mp.has_low) || (r.z0 + r.len == mp.nplanes && mp.has_high);
+        };
+        // Two ways to cut.  Vectors that stream from HBM: every strip into equal segments dealt round-robin in plane order, so
+        // that neighbouring strips are at the same planes at the same time and the margins they share hit in the L2 (the
+        // contiguous ranges below measured 270 vs 265 us on 300^3: better balanced, but every margin came from HBM again).
+        // Vectors that sit in the L2: one contiguous, cost-balanced range per block (one eighth of 300^3: 37.5 vs 40.6 us).
+        const bool streaming = (double)n * sizeof(T) >= 48e6;
+        if (c->march_lz > 0 || streaming) {
+            int best_lz = mp.nplanes;
+            double best = 1e300;
+            for (int segs = 1; segs <= mp.nplanes; segs++) {
+                const int lz = (mp.nplanes + segs - 1) / segs;
+                const long long nruns = (long long)mp.m * ((mp.nplanes + lz - 1) / lz);
+                const long long rounds = (nruns + grid - 1) / grid;
+                const double cost = (double)rounds * (lz + 0.7);
+                if (cost < best - 1e-9) {
+                    best = cost;
+                    best_lz = lz;
+                }
             }
+            // (march_lz: option, tests) the runs that read a halo plane come last
+            const int lz = std::min(c->march_lz > 0 ? c->march_lz : best_lz, mp.nplanes);
+            std::vector<MarchRun> outer;
+            for (int z0 = 0; z0 < mp.nplanes; z0 += lz) {
+                const int L = std::min(lz, mp.nplanes - z0);
+                const MarchRun probe{0, z0, L, 0};
+                for (int s = 0; s < mp.m; s++) (touches_halo(probe) ? outer : inner).push_back(MarchRun{s, z0, L, 0});
+            }
+            inner.insert(inner.end(), outer.begin(), outer.end());
+            mp.grid = (int)std::min<size_t>(grid, inner.size());
+            for (size_t i = 0; i < inner.size(); i++) inner[i].next = i + mp.grid < inner.size() ? (int)(i + mp.grid) : -1;
+        } else {
+            // One contiguous range of (strip, plane) items per block, all of the same cost: equal segments dealt
+            // round-robin left the last round half empty (300^3: 197.6 piece-times per block for 182.4 of work, one eighth
+            // of it: 27.4 for 23.1).  Within a strip the planes are taken from the middle upwards, then from the bottom
+            // to the middle, so that on a row-block shard a halo plane is the LAST piece of a run (top) or belongs to the
+            // second run of a strip (bottom) -- never the first thing a block needs, unless its range starts exactly there;
+            // a block's runs that start at the bottom halo are moved to the end of its list.
+            const long long Tn = (long long)mp.m * mp.nplanes;
+            const int G = (int)std::min<long long>(grid, Tn);
+            const int mid = (mp.has_low || mp.has_high) ? mp.nplanes / 2 : 0;
+            // item g of strip-major order -> (strip, plane): planes mid .. nplanes-1, then 0 .. mid-1
+            auto plane_of = [&](long long g) { const int i = (int)(g % mp.nplanes); return i < mp.nplanes - mid ? mid + i : i - (mp.nplanes - mid); };
+            std::vector<std::vector<MarchRun>> lists(G);
+            const double run_cost = 0.7;
+            long long g = 0;
+            // cost still to be dealt: the items + one run per strip segment (2 per strip when rotated) + one per block boundary
+            double remaining = (double)Tn + run_cost * ((double)mp.m * (mid ? 2 : 1) + G);
+            for (int b = 0; b < G && g < Tn; b++) {
+                double budget = remaining / (G - b);
+                double used = 0;
+                while (g < Tn) {
+                    // a run: from g to the end of its segment (strip end, or the wrap of the rotation), as far as the budget goes
+                    const int s = (int)(g / mp.nplanes), z0 = plane_of(g);
+                    const int seg_end = (z0 >= mid && mid) ? mp.nplanes : (mid ? mid : mp.nplanes);      // exclusive plane bound of this segment
+                    int room = (int)std::floor(budget - used - run_cost + 0.5);
+                    if (b == G - 1) room = seg_end - z0;                         // the last block takes what is left
+                    if (room < 1) {
+                        if (used > 0) break;
+                        room = 1;
+                    }
+                    const int L = std::min(room, seg_end - z0);
+                    lists[b].push_back(MarchRun{s, z0, L, 0});
+                    used += L + run_cost;
+                    g += L;
+                    if (L < seg_end - z0 && b != G - 1) break;                   // budget exhausted inside the segment
+                }
+                remaining -= used;
+                // runs whose FIRST piece is the bottom halo plane go last
+                std::stable_partition(lists[b].begin(), lists[b].end(), [&](const MarchRun &r) { return !(r.z0 == 0 && mp.has_low); });
+            }
+            // block b starts with runs[b]; every run names the block's next one
+            lists.erase(std::remove_if(lists.begin(), lists.end(), [](const std::vector<MarchRun> &l) { return l.empty(); }), lists.end());
+            mp.grid = (int)lists.size();
+            size_t rounds = 0;
+            for (auto &l : lists) rounds = std::max(rounds, l.size());
+            std::vector<int> at(lists.size(), -1);             // index of list b's latest run in `inner`
+            for (size_t k = 0; k < rounds; k++)
+                for (size_t b = 0; b < lists.size(); b++)
+                    if (lists[b].size() > k) {
+                        MarchRun r = lists[b][k];
+                        r.next = -1;
+                        if (at[b] >= 0) inner[at[b]].next = (int)inner.size();
+                        at[b] = (int)inner.size();
+                        inner.push_back(r);
+                    }
         }
-        if (c->march_lz > 0) best_lz = std::min(c->march_lz, mp.nplanes);
-        std::vector<MarchRun> inner, outer;
-        for (int z0 = 0; z0 < mp.nplanes; z0 += best_lz) {
-            const int L = std::min(best_lz, mp.nplanes - z0);
-            const bool touches = (z0 == 0 && mp.has_low) || (z0 + L == mp.nplanes && mp.has_high);
-            for (int s = 0; s < mp.m; s++) (touches ? outer : inner).push_back(MarchRun{s, z0, L, 0});
-        }
-        inner.insert(inner.end(), outer.begin(), outer.end());      // the runs that read a halo plane come last
         mp.nruns = (int)inner.size();
         if (c->d_march_runs) cudaFree(c->d_march_runs);
         c->d_march_runs = nullptr;
@@ -656,7 +724,7 @@ template <typename T> struct Engine {
                 CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
                 c->occ[key] = 1;
             }
-            const int grid = std::min(c->sm_count, c->mplan.nruns);
+            const int grid = c->mplan.grid;
             c->spmv_grid_last = grid;
             CU(launch_kernel(kern, dim3(grid), dim3(PEER ? DIR_THREADS_PEER : DIR_THREADS), smem, c->stream, (c->pdl & 1) != 0, c->n,
                              c->n + c->extra_cols, c->mplan, nstage, (const MarchRun *)c->d_march_runs, c->npat,

@@ -297,7 +297,22 @@ halo_push_kernel(PeerComm *pc, const int *__restrict__ idx, const T *__restrict_
     const int lo = pc->send_off[p], hi = pc->send_off[p + 1];
     if (hi <= lo) return;
     T *dst = reinterpret_cast<T *>(pc->d_peer[p]) + pc->remote_off[p];
-    for (int i = lo + blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += gridDim.x * blockDim.x) dst[i - lo] = d[idx[i]];
+    // four independent index -> value -> remote store chains per thread: with random columns (BASELINE config 5) nearly
+    // the whole owned block goes to every peer, and one dependent chain per thread left the NVLink idle
+    // (20 MB in ~400 us on 2 GPUs, profiles/r02_bench_c5_n2_before.json)
+    const int stride = gridDim.x * blockDim.x;
+    int i = lo + blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < hi; i += 4 * stride) {
+        int j[4];
+        T v[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) j[u] = __ldg(idx + i + u * stride);
+#pragma unroll
+        for (int u = 0; u < 4; u++) v[u] = d[j[u]];
+#pragma unroll
+        for (int u = 0; u < 4; u++) dst[i + u * stride - lo] = v[u];
+    }
+    for (; i < hi; i += stride) dst[i - lo] = d[idx[i]];
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {

@@ -116,7 +116,9 @@ template <typename T> struct ShardEngine {
             if (sh->send_total > 0) {
                 // fork: the push reads v while the SpMV (which only reads v too) already runs on the main stream;
                 // joined again before the next kernel that writes v (join_push)
-                const int nb = std::max(1, std::min(32, (sh->max_send + 2047) / 2048));
+                // a block per 2048 entries of the largest segment: 1 .. 32 for the faces of a grid partition, up to two
+                // per SM when the segment is a whole owned block (random columns)
+                const int nb = std::max(1, std::min(sh->max_send > (1 << 18) ? 2 * c->sm_count : 32, (sh->max_send + 2047) / 2048));
                 CU(cudaEventRecord(sh->ev_fork, c->stream));
                 CU(cudaStreamWaitEvent(sh->side, sh->ev_fork, 0));
                 halo_push_kernel<T><<<dim3(nb, sh->world), 256, 0, sh->side>>>(sh->d_peer, sh->d_send_idx, v, n_active);
