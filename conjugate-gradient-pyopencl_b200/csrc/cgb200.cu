@@ -519,9 +519,11 @@ template <typename T> struct Engine {
         // Two ways to cut.  Vectors that stream from HBM: every strip into equal segments dealt round-robin in plane order, so
         // that neighbouring strips are at the same planes at the same time and the margins they share hit in the L2 (the
         // contiguous ranges below measured 270 vs 265 us on 300^3: better balanced, but every margin came from HBM again).
-        // Vectors that sit in the L2: one contiguous, cost-balanced range per block (one eighth of 300^3: 37.5 vs 40.6 us).
+        // Vectors that sit in the L2: one contiguous, cost-balanced range per block (one eighth of 300^3: 37.5 vs 40.6 us) --
+        // but not on a row-block shard: there the runs that read a halo plane have to come last for every block, and ranges
+        // that meet a halo plane in their middle measured 57 vs 40.5 us on 38-plane shards (profiles/r02_trace_slab4_n2_*).
         const bool streaming = (double)n * sizeof(T) >= 48e6;
-        if (c->march_lz > 0 || streaming) {
+        if (c->march_lz > 0 || streaming || mp.has_low || mp.has_high) {
             int best_lz = mp.nplanes;
             double best = 1e300;
             for (int segs = 1; segs <= mp.nplanes; segs++) {
@@ -547,28 +549,21 @@ template <typename T> struct Engine {
             for (size_t i = 0; i < inner.size(); i++) inner[i].next = i + mp.grid < inner.size() ? (int)(i + mp.grid) : -1;
         } else {
             // One contiguous range of (strip, plane) items per block, all of the same cost: equal segments dealt
-            // round-robin left the last round half empty (300^3: 197.6 piece-times per block for 182.4 of work, one eighth
-            // of it: 27.4 for 23.1).  Within a strip the planes are taken from the middle upwards, then from the bottom
-            // to the middle, so that on a row-block shard a halo plane is the LAST piece of a run (top) or belongs to the
-            // second run of a strip (bottom) -- never the first thing a block needs, unless its range starts exactly there;
-            // a block's runs that start at the bottom halo are moved to the end of its list.
+            // round-robin leave the last round half empty (one eighth of 300^3: 27.4 piece-times per block for 23.1 of work).
             const long long Tn = (long long)mp.m * mp.nplanes;
             const int G = (int)std::min<long long>(grid, Tn);
-            const int mid = (mp.has_low || mp.has_high) ? mp.nplanes / 2 : 0;
-            // item g of strip-major order -> (strip, plane): planes mid .. nplanes-1, then 0 .. mid-1
-            auto plane_of = [&](long long g) { const int i = (int)(g % mp.nplanes); return i < mp.nplanes - mid ? mid + i : i - (mp.nplanes - mid); };
             std::vector<std::vector<MarchRun>> lists(G);
             const double run_cost = 0.7;
             long long g = 0;
-            // cost still to be dealt: the items + one run per strip segment (2 per strip when rotated) + one per block boundary
-            double remaining = (double)Tn + run_cost * ((double)mp.m * (mid ? 2 : 1) + G);
+            // cost still to be dealt: the items + one run per strip + one per block boundary
+            double remaining = (double)Tn + run_cost * ((double)mp.m + G);
             for (int b = 0; b < G && g < Tn; b++) {
                 double budget = remaining / (G - b);
                 double used = 0;
                 while (g < Tn) {
-                    // a run: from g to the end of its segment (strip end, or the wrap of the rotation), as far as the budget goes
-                    const int s = (int)(g / mp.nplanes), z0 = plane_of(g);
-                    const int seg_end = (z0 >= mid && mid) ? mp.nplanes : (mid ? mid : mp.nplanes);      // exclusive plane bound of this segment
+                    // a run: from g to the end of its strip, as far as the budget goes
+                    const int s = (int)(g / mp.nplanes), z0 = (int)(g % mp.nplanes);
+                    const int seg_end = mp.nplanes;
                     int room = (int)std::floor(budget - used - run_cost + 0.5);
                     if (b == G - 1) room = seg_end - z0;                         // the last block takes what is left
                     if (room < 1) {
@@ -582,8 +577,6 @@ template <typename T> struct Engine {
                     if (L < seg_end - z0 && b != G - 1) break;                   // budget exhausted inside the segment
                 }
                 remaining -= used;
-                // runs whose FIRST piece is the bottom halo plane go last
-                std::stable_partition(lists[b].begin(), lists[b].end(), [&](const MarchRun &r) { return !(r.z0 == 0 && mp.has_low); });
             }
             // block b starts with runs[b]; every run names the block's next one
             lists.erase(std::remove_if(lists.begin(), lists.end(), [](const std::vector<MarchRun> &l) { return l.empty(); }), lists.end());
@@ -879,7 +872,7 @@ template <typename T> struct Engine {
             CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const int grid = persistent_grid(c, kern, K::NT, smem, c->ntiles);
         c->spmv_grid_last = grid;
-        CU(launch_kernel(kern, dim3(grid), dim3(K::NT), smem, c->stream, DOT && (c->pdl & 1), c->ntiles,
+        CU(launch_kernel(kern, dim3(grid), dim3(K::NT), smem, c->stream, DOT && (c->pdl & 1), c->ntiles, c->ntiles_interior,
                          (const SpmvTile *)c->d_tiles, (const T *)c->d_vals, (const int *)c->d_rowptr,
                          (const int *)c->d_cols, x, y, (T *)c->d_chunk_sum, sc));
         c->launches++;
@@ -941,7 +934,7 @@ template <typename T> struct Engine {
         if (k == 1) {
             int variant = c->d_tiles ? c->spmv_variant : 1;
             if (variant == 0 && c->pat_ok && c->pattern) return spmv_pattern<DOT>(c, x, y, sc);
-            if (variant == 0 && c->irregular && c->auto_irregular && !sc.peer) variant = 3;
+            if (variant == 0 && c->irregular && c->auto_irregular) variant = 3;
             switch (variant) {
             case 1: return spmv1<DOT>(c, x, y, sc);
             case 3: return spmv_tma<2, DOT>(c, x, y, sc);

@@ -664,7 +664,7 @@ template <typename T, int S> struct TmaCfg {
 //      group of lpr lanes per row, and rows much longer than the rest are summed by a whole warp.
 template <typename T, int S, bool DOT>
 __global__ void __launch_bounds__(256)          // 4 blocks per SM by registers; forcing 6 (40 registers) measured 1.4x slower
-spmv_tma_kernel(int ntiles, const SpmvTile *__restrict__ tiles, const T *__restrict__ vals,
+spmv_tma_kernel(int ntiles, int ntiles_interior, const SpmvTile *__restrict__ tiles, const T *__restrict__ vals,
                 const int *__restrict__ rowptr, const int *__restrict__ cols, const T *__restrict__ x,
                 T *__restrict__ y, T *__restrict__ chunk_sum, CgScalars<T> sc) {
     using K = TmaCfg<T, S>;
@@ -723,7 +723,25 @@ spmv_tma_kernel(int ntiles, const SpmvTile *__restrict__ tiles, const T *__restr
         }
     }
 
+    int trace_it = -1;
+    if (DOT && sc.trace) {
+        trace_it = *sc.it;
+        if (blockIdx.x == 0 && t == 0) trace_mark<T>(sc, trace_it, TR_SPMV_START);
+    }
+    // row-block shards (as spmv_tma_rows_kernel): tiles [ntiles_interior, ntiles) gather entries that peers push into
+    // this GPU's vector; a block waits for them when it reaches its first such tile.  With the random columns this
+    // kernel is chosen for that is the first tile -- the matrix data of S tiles is in flight by then.
+    bool halo_ready = !(sc.peer && sc.peer->world > 1);
+
     for (int i = 0; i < count; i++) {
+        if (!halo_ready && (int)blockIdx.x + i * (int)gridDim.x >= ntiles_interior) {
+            if (t == 0) {
+                peer_wait_halo(sc.peer);
+                if ((int)blockIdx.x == ntiles_interior % (int)gridDim.x) trace_mark<T>(sc, trace_it, TR_HALO_READY);
+            }
+            __syncthreads();
+            halo_ready = true;
+        }
         const SpmvTile tl = tl_next;
         if (i + 1 < count) tl_next = tiles[blockIdx.x + (size_t)(i + 1) * gridDim.x];
         const int s = i % S;
@@ -822,10 +840,14 @@ spmv_tma_kernel(int ntiles, const SpmvTile *__restrict__ tiles, const T *__restr
     if (DOT) {
         block_col_reduce<T, 1>(dot, 1, red);
         if (publish_and_arrive<T, 1>(red, 1, 1, sc.partial, sc.ticket + TK_SPMV)) {
+            if (t == 0) trace_mark<T>(sc, trace_it, TR_SPMV_ALL_DONE);
             grid_col_reduce<T, 1>(sc.partial, 1, 1, 1, red);
+            T total = red[0];
+            if (sc.peer) total = peer_allreduce<T>(sc.peer, red[0]);    // sum over the GPUs, inside this kernel
             if (t == 0) {
-                sc.dq[0] = red[0];
+                sc.dq[0] = total;
                 sc.ticket[TK_SPMV] = 0;
+                trace_mark<T>(sc, trace_it, TR_SPMV_END);
             }
         }
     }

@@ -118,7 +118,21 @@ template <typename T> struct ShardEngine {
                 // joined again before the next kernel that writes v (join_push)
                 // a block per 2048 entries of the largest segment: 1 .. 32 for the faces of a grid partition, up to two
                 // per SM when the segment is a whole owned block (random columns)
-                const int nb = std::max(1, std::min(sh->max_send > (1 << 18) ? 2 * c->sm_count : 32, (sh->max_send + 2047) / 2048));
+                static const int env_nb = getenv("CGB200_PUSH_BLOCKS") ? atoi(getenv("CGB200_PUSH_BLOCKS")) : 0;
+                const int nb = env_nb > 0 ? env_nb
+                                          : std::max(1, std::min(sh->max_send > (1 << 18) ? 2 * c->sm_count : 32, (sh->max_send + 2047) / 2048));
+                const bool balanced_spmv = c->spmv_variant == 3 || (c->spmv_variant == 0 && c->irregular && c->auto_irregular);
+                if (sh->max_send > (1 << 18) || balanced_spmv) {
+                    // whole-block segments, or the per-non-zero SpMV: IN stream order, ahead of the SpMV.  Every tile of that SpMV needs the halo, so
+                    // there is nothing to overlap -- and its blocks (the per-non-zero kernel: 4 x 256 threads, every
+                    // register of the SM) spin for the peers' entries from their first tile on.  Forked, the push of THIS
+                    // GPU may find no room beside them while the peer's blocks wait for it and the peer's push finds no
+                    // room beside those: both GPUs spin for ever (seen: a 2-GPU run of config 5 that never returned).
+                    halo_push_kernel<T><<<dim3(nb, sh->world), 256, 0, c->stream>>>(sh->d_peer, sh->d_send_idx, v, n_active);
+                    c->launches++;
+                    sh->exchanges++;
+                    return 0;
+                }
                 CU(cudaEventRecord(sh->ev_fork, c->stream));
                 CU(cudaStreamWaitEvent(sh->side, sh->ev_fork, 0));
                 halo_push_kernel<T><<<dim3(nb, sh->world), 256, 0, sh->side>>>(sh->d_peer, sh->d_send_idx, v, n_active);
@@ -205,8 +219,8 @@ template <typename T> struct ShardEngine {
             ~PdlGuard() { c->pdl = saved; }
         } pdl_guard{c, c->pdl};
         if (!cg2 && sh->world > 1 && !getenv("CGB200_PDL")) c->pdl = 0;
-        if (sh->p2p && c->spmv_variant != 0 && c->spmv_variant != 6)
-            return fail(CGB200_ERR_UNSUPPORTED, "peer-memory collectives need the default SpMV schedule (spmv_variant 0)");
+        if (sh->p2p && c->spmv_variant != 0 && c->spmv_variant != 6 && c->spmv_variant != 3)
+            return fail(CGB200_ERR_UNSUPPORTED, "peer-memory collectives need a TMA-fed SpMV schedule (spmv_variant 0, 3 or 6)");
         const typename E::VecGeom g = E::geom(c, 1);
         const size_t bytes = (size_t)sh->n_owned * sizeof(T);
 
