@@ -148,8 +148,16 @@ __device__ __forceinline__ void dir_finish(T dot, T *red, const CgScalars<T> &sc
     }
 }
 
-// Row-block shards: ONE warp per block stores dn = r + beta d of the rows the peers reference into the halos of their
-// residual vectors, 8 entries in flight per lane, then raises the arrival flags.  It shares nothing with the rest of
+// dir_spmv is warp-specialised: DIR_CONSUMERS threads own the rows of a chunk (PAT_CHUNK / DIR_CONSUMERS rows
+// each, independent accumulation chains), one more warp does nothing but feed the ring of stages with TMA.
+constexpr int DIR_CONSUMERS = 512;
+constexpr int DIR_THREADS = DIR_CONSUMERS + 32;         // + the TMA producer warp
+constexpr int DIR_PUSH_WARPS = 3;                       // + the warps that store dn into the peers' halos (row-block shards)
+constexpr int DIR_THREADS_PEER = DIR_THREADS + 32 * DIR_PUSH_WARPS;
+constexpr int DIR_MAX_STAGES = 4;
+
+// Row-block shards: DIR_PUSH_WARPS warps per block store dn = r + beta d of the rows the peers reference into the halos of their
+// residual vectors, 16 entries in flight per lane, then raises the arrival flags.  It shares nothing with the rest of
 // the block: the consumers start on the interior chunks at once.
 template <typename T>
 __device__ __forceinline__ void dir_push_halo(const CgScalars<T> &sc, T beta, const T *__restrict__ dold, const T *__restrict__ r) {
@@ -157,20 +165,27 @@ __device__ __forceinline__ void dir_push_halo(const CgScalars<T> &sc, T beta, co
     const PeerComm *pc = sc.peer;
     if (!pc || pc->world <= 1) return;
     const int total = pc->send_off[pc->world];
-    const int lane = t & 31, nl = (int)gridDim.x * 32;
-    for (int e0 = (int)blockIdx.x * 32 + lane; e0 < total; e0 += 8 * nl) {
-        int row[8];
+    // 16 entries in flight per lane: with vectors that stream from HBM every dependent load of this warp (index, then
+    // d and r) waits behind the TMA traffic of 148 producers -- at 8 in flight (5 rounds of 2 latencies for the two faces
+    // of a 300 x 300 plane) the flags reached the neighbours ~45 us into the kernel and the blocks that start on a run
+    // above the bottom halo plane sat idle that long (4 GPUs: 114 us for the inner ranks' dir_spmv against 67 us for
+    // rank 0, profiles/r02_trace_c4_n4_before.txt)
+    constexpr int PF = 16;
+    // DIR_PUSH_WARPS warps per block share the list (they cost no registers: 17 or 20 warps, a partition holds five either way)
+    const int lane = t & 31, pt = t - (DIR_CONSUMERS + 32), nl = (int)gridDim.x * (DIR_PUSH_WARPS * 32);
+    for (int e0 = (int)blockIdx.x * (DIR_PUSH_WARPS * 32) + pt; e0 < total; e0 += PF * nl) {
+        int row[PF];
 #pragma unroll
-        for (int u = 0; u < 8; u++) {
+        for (int u = 0; u < PF; u++) {
             const int e = e0 + u * nl;
             row[u] = e < total ? pc->send_idx[e] : -1;
         }
-        T val[8];
+        T val[PF];
 #pragma unroll
-        for (int u = 0; u < 8; u++)
+        for (int u = 0; u < PF; u++)
             if (row[u] >= 0) val[u] = Sc<T>::fma(beta, dold[row[u]], r[row[u]]);
 #pragma unroll
-        for (int u = 0; u < 8; u++) {
+        for (int u = 0; u < PF; u++) {
             const int e = e0 + u * nl;
             if (row[u] >= 0) {
                 int p = 0;
@@ -184,7 +199,7 @@ __device__ __forceinline__ void dir_push_halo(const CgScalars<T> &sc, T beta, co
     if (lane == 0) {
         // the last warp to get here (over all blocks) tells every peer that receives from this rank
         const unsigned prev = atomicAdd(&sc.peer->push_ticket[0], 1u);
-        if (prev == gridDim.x - 1) {
+        if (prev == gridDim.x * DIR_PUSH_WARPS - 1) {
             sc.peer->push_ticket[0] = 0;
             __threadfence_system();
             for (int p = 0; p < pc->world; p++)
@@ -192,13 +207,6 @@ __device__ __forceinline__ void dir_push_halo(const CgScalars<T> &sc, T beta, co
         }
     }
 }
-
-// dir_spmv is warp-specialised: DIR_CONSUMERS threads own the rows of a chunk (PAT_CHUNK / DIR_CONSUMERS rows
-// each, independent accumulation chains), one more warp does nothing but feed the ring of stages with TMA.
-constexpr int DIR_CONSUMERS = 512;
-constexpr int DIR_THREADS = DIR_CONSUMERS + 32;         // + the TMA producer warp
-constexpr int DIR_THREADS_PEER = DIR_THREADS + 32;      // + the warp that stores dn into the peers' halos (row-block shards)
-constexpr int DIR_MAX_STAGES = 4;
 
 __device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");

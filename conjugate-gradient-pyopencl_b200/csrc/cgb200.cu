@@ -537,14 +537,18 @@ template <typename T> struct Engine {
                 }
             }
             // (march_lz: option, tests) the runs that read a halo plane come last
+            // Order: the runs that read no halo plane, then the ones that END below the top halo plane (they need it as
+            // their last piece), and last the ones that START above the bottom halo plane (they need it first).
             const int lz = std::min(c->march_lz > 0 ? c->march_lz : best_lz, mp.nplanes);
-            std::vector<MarchRun> outer;
+            std::vector<MarchRun> top, bottom;
             for (int z0 = 0; z0 < mp.nplanes; z0 += lz) {
                 const int L = std::min(lz, mp.nplanes - z0);
                 const MarchRun probe{0, z0, L, 0};
-                for (int s = 0; s < mp.m; s++) (touches_halo(probe) ? outer : inner).push_back(MarchRun{s, z0, L, 0});
+                const bool low = z0 == 0 && mp.has_low;
+                for (int s = 0; s < mp.m; s++) (low ? bottom : (touches_halo(probe) ? top : inner)).push_back(MarchRun{s, z0, L, 0});
             }
-            inner.insert(inner.end(), outer.begin(), outer.end());
+            inner.insert(inner.end(), top.begin(), top.end());
+            inner.insert(inner.end(), bottom.begin(), bottom.end());
             mp.grid = (int)std::min<size_t>(grid, inner.size());
             for (size_t i = 0; i < inner.size(); i++) inner[i].next = i + mp.grid < inner.size() ? (int)(i + mp.grid) : -1;
         } else {
