@@ -40,7 +40,7 @@
 // in kernels.cuh) tells the peer's TMA producer when its boundary chunks -- scheduled last -- may be loaded.
 // No push kernel, no side stream, one exchange per iteration.  (First version, in git: r in two buffers as well and
 // the boundary entries of r' pushed by update_r, flag-free; on one eighth of the 300^3 system the six vectors then
-// no longer fit the 126 MB L2 and both kernels ran 30 % slower than alone, profiles/r02_trace_n8_pingpong.txt.)
+// no longer fit the 126 MB L2 and both kernels ran 30 % slower than alone, profiles/r02_notes.md.)
 #pragma once
 
 namespace cgb {
@@ -333,7 +333,7 @@ cg2_dir_spmv_kernel(int n, int ncols, int nchunks, int nchunks_interior, const i
         // The pattern number and x of a thread's rows are requested one chunk ahead.  The loads are unconditional
         // (clamped row) and nothing touches their result before the next chunk, so that the wait for a stage
         // below never waits for THEM (a select on the loaded value right after the load did exactly that: 37 % of
-        // the stall samples of the first version, profiles/r02_ncu_dir_spmv_c4_v3.txt).
+        // the stall samples of the first version, profiles/r02_notes.md).
         // (Tried and reverted, in git: a thread owning the PAIR of rows 2t, 2t + 1 with 16-byte accesses for x, q, dn and
         //  every even-positioned neighbour -- 7 shared-memory loads per row instead of 18.  On a 300-wide grid 43 % of
         //  the warps hold a pair whose rows have different patterns -- the first / last node of a grid line -- and run

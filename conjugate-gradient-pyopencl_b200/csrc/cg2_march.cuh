@@ -196,7 +196,7 @@ cg2_dir_march_kernel(int n, int ncols, MarchPlan mp, int nstage, const MarchRun 
         // pattern numbers -- arrives in the stage by TMA: no global load, no register that waits for one.  (First version, in
         // git: x and the pattern number requested one chunk ahead into registers, as cg2_dir_spmv_kernel does; here the
         // compiler rotated those registers with MOVs that wait for the loads -- 46 % of the stall samples,
-        // profiles/r02_ncu_dir_march_c4_v1.txt.)  Ring positions are tracked incrementally: a division by the (run-time)
+        // profiles/r02_notes.md.)  Ring positions are tracked incrementally: a division by the (run-time)
         // number of stages costs ~100 dependent cycles, and there would be five per piece.
         const unsigned diag_b = (unsigned)(-mp.lo0) * (unsigned)sizeof(T);
         MarchWalk w;

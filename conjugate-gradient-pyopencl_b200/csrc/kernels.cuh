@@ -104,7 +104,7 @@ template <typename T> __device__ __forceinline__ T peer_allreduce(PeerComm *pc, 
         // words below: every storing thread executed a system-scope fence after its stores and before its block
         // arrived at the kernel's ticket, i.e. those stores were performed at the peer before the last block --
         // this one -- even started.  (A second system fence here, in front of the words, cost ~2 us per
-        // all-reduce: profiles/r02_trace_n2_*.txt.)
+        // all-reduce: profiles/r02_notes.md.)
         double v[2] = {0.0, 0.0};
         Sc<T>::to_double2(local, v);
         PeerSlot *dst = pc->slots[t] + (size_t)parity * pc->world + pc->rank;
@@ -620,7 +620,7 @@ __device__ __forceinline__ bool mbar_try_wait(unsigned long long *bar, unsigned 
 // try_wait with a suspend-time hint: the thread is parked by the hardware until the phase completes or the hint (in
 // nanoseconds) runs out, instead of coming back to the issue port every few hundred cycles.  (In the TMA-fed CG kernels
 // 18 % of all executed instructions were polls of this loop, taking issue slots from the warps that had work:
-// profiles/r02_ncu_dir_march_c4_v3.txt.)
+// profiles/r02_notes.md.)
 __device__ __forceinline__ bool mbar_try_wait_hint(unsigned long long *bar, unsigned parity, unsigned ns) {
     unsigned ok;
     asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.b32 %0, 1, 0, p;\n\t}"
