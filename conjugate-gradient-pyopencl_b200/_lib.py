@@ -38,6 +38,7 @@ SIGNATURES = {
     "cgb200_solve": (_i, [_vp, _vp, _vp, _i, _i, _d, _vp, _vp, _vp, _i]),
     "cgb200_solve_pcg": (_i, [_vp, _vp, _vp, _vp, _i, _i, _d, _vp, _vp, _vp]),
     "cgb200_check_guards": (_ll, [_vp]),
+    "cgb200_plan_march_runs": (_i, [_i, _i, _i, _i, _i, _i, _i, _vp, _i, ctypes.POINTER(_i)]),
     "cgb200_time_kernel": (_i, [_vp, _i, _i, _i, ctypes.POINTER(_d)]),
     "cgb200_last_timing": (_i, [_vp, ctypes.POINTER(_d)]),
     "cgb200_info": (_i, [_vp, ctypes.POINTER(_ll)]),

@@ -234,6 +234,103 @@ static int persistent_grid(cgb200_ctx *c, K kernel, int block, size_t smem, long
 // ---------------------------------------------------------------------------
 // typed engine
 // ---------------------------------------------------------------------------
+// ---- the runs of the plane-marching dir_spmv (cg2_march.cuh) ---------------------------------------------------------
+// m strips x nplanes planes of work items; `grid` blocks.  Returns the number of blocks the runs were dealt to (the launch
+// grid); block b starts with (*out)[b], every run names its block's next one.  Host logic only (exported as
+// cgb200_plan_march_runs for the CPU tests: every item exactly once, halo order, chains).
+static int plan_march_runs(int m, int nplanes, int grid, bool has_low, bool has_high, bool streaming, int march_lz,
+                           std::vector<MarchRun> *out) {
+    // A run of L planes loads L + 2 pieces (the extra two cost ~0.35 of a computed piece each).
+    std::vector<MarchRun> &inner = *out;
+    inner.clear();
+    int out_grid = 0;
+    auto touches_halo = [&](const MarchRun &r) {
+        return (r.z0 == 0 && has_low) || (r.z0 + r.len == nplanes && has_high);
+    };
+    // Two ways to cut.  Vectors that stream from HBM: every strip into equal segments dealt round-robin in plane order, so
+    // that neighbouring strips are at the same planes at the same time and the margins they share hit in the L2 (the
+    // contiguous ranges below measured 270 vs 265 us on 300^3: better balanced, but every margin came from HBM again).
+    // Vectors that sit in the L2: one contiguous, cost-balanced range per block (one eighth of 300^3: 37.5 vs 40.6 us) --
+    // but not on a row-block shard: there the runs that read a halo plane have to come last for every block, and ranges
+    // that meet a halo plane in their middle measured 57 vs 40.5 us on 38-plane shards (profiles/r02_trace_slab4_n2_*).
+    if (march_lz > 0 || streaming || has_low || has_high) {
+        int best_lz = nplanes;
+        double best = 1e300;
+        for (int segs = 1; segs <= nplanes; segs++) {
+            const int lz = (nplanes + segs - 1) / segs;
+            const long long nruns = (long long)m * ((nplanes + lz - 1) / lz);
+            const long long rounds = (nruns + grid - 1) / grid;
+            const double cost = (double)rounds * (lz + 0.7);
+            if (cost < best - 1e-9) {
+                best = cost;
+                best_lz = lz;
+            }
+        }
+        // (march_lz: option, tests) the runs that read a halo plane come last
+        // Order: the runs that read no halo plane, then the ones that END below the top halo plane (they need it as
+        // their last piece), and last the ones that START above the bottom halo plane (they need it first).
+        const int lz = std::min(march_lz > 0 ? march_lz : best_lz, nplanes);
+        std::vector<MarchRun> top, bottom;
+        for (int z0 = 0; z0 < nplanes; z0 += lz) {
+            const int L = std::min(lz, nplanes - z0);
+            const MarchRun probe{0, z0, L, 0};
+            const bool low = z0 == 0 && has_low;
+            for (int s = 0; s < m; s++) (low ? bottom : (touches_halo(probe) ? top : inner)).push_back(MarchRun{s, z0, L, 0});
+        }
+        inner.insert(inner.end(), top.begin(), top.end());
+        inner.insert(inner.end(), bottom.begin(), bottom.end());
+        out_grid = (int)std::min<size_t>(grid, inner.size());
+        for (size_t i = 0; i < inner.size(); i++) inner[i].next = i + out_grid < inner.size() ? (int)(i + out_grid) : -1;
+    } else {
+        // One contiguous range of (strip, plane) items per block, all of the same cost: equal segments dealt
+        // round-robin leave the last round half empty (one eighth of 300^3: 27.4 piece-times per block for 23.1 of work).
+        const long long Tn = (long long)m * nplanes;
+        const int G = (int)std::min<long long>(grid, Tn);
+        std::vector<std::vector<MarchRun>> lists(G);
+        const double run_cost = 0.7;
+        long long g = 0;
+        // cost still to be dealt: the items + one run per strip + one per block boundary
+        double remaining = (double)Tn + run_cost * ((double)m + G);
+        for (int b = 0; b < G && g < Tn; b++) {
+            double budget = remaining / (G - b);
+            double used = 0;
+            while (g < Tn) {
+                // a run: from g to the end of its strip, as far as the budget goes
+                const int s = (int)(g / nplanes), z0 = (int)(g % nplanes);
+                const int seg_end = nplanes;
+                int room = (int)std::floor(budget - used - run_cost + 0.5);
+                if (b == G - 1) room = seg_end - z0;                         // the last block takes what is left
+                if (room < 1) {
+                    if (used > 0) break;
+                    room = 1;
+                }
+                const int L = std::min(room, seg_end - z0);
+                lists[b].push_back(MarchRun{s, z0, L, 0});
+                used += L + run_cost;
+                g += L;
+                if (L < seg_end - z0 && b != G - 1) break;                   // budget exhausted inside the segment
+            }
+            remaining -= used;
+        }
+        // block b starts with runs[b]; every run names the block's next one
+        lists.erase(std::remove_if(lists.begin(), lists.end(), [](const std::vector<MarchRun> &l) { return l.empty(); }), lists.end());
+        out_grid = (int)lists.size();
+        size_t rounds = 0;
+        for (auto &l : lists) rounds = std::max(rounds, l.size());
+        std::vector<int> at(lists.size(), -1);             // index of list b's latest run in `inner`
+        for (size_t k = 0; k < rounds; k++)
+            for (size_t b = 0; b < lists.size(); b++)
+                if (lists[b].size() > k) {
+                    MarchRun r = lists[b][k];
+                    r.next = -1;
+                    if (at[b] >= 0) inner[at[b]].next = (int)inner.size();
+                    at[b] = (int)inner.size();
+                    inner.push_back(r);
+                }
+    }
+    return out_grid;
+}
+
 template <typename T> struct Engine {
     static constexpr int VW = VecW<T>::value;
 
@@ -509,95 +606,10 @@ template <typename T> struct Engine {
                 classify(off[(size_t)p * PAT_MAXLEN + j], &rel, &b);
                 (*codes)[(size_t)p * PAT_MAXLEN + j] = ((rel + 1) << 24) | (b - mp.lo0);
             }
-        // runs.  A run of L planes loads L + 2 pieces (the extra two cost ~0.35 of a computed piece each), and block b
-        // starts with runs[b]; every run names the block's next one (MarchRun::next)
-        const int grid = c->sm_count;
+        // runs (plan_march_runs: what the blocks of the marching kernel work through, in which order)
         std::vector<MarchRun> inner;
-        auto touches_halo = [&](const MarchRun &r) {
-            return (r.z0 == 0 && mp.has_low) || (r.z0 + r.len == mp.nplanes && mp.has_high);
-        };
-        // Two ways to cut.  Vectors that stream from HBM: every strip into equal segments dealt round-robin in plane order, so
-        // that neighbouring strips are at the same planes at the same time and the margins they share hit in the L2 (the
-        // contiguous ranges below measured 270 vs 265 us on 300^3: better balanced, but every margin came from HBM again).
-        // Vectors that sit in the L2: one contiguous, cost-balanced range per block (one eighth of 300^3: 37.5 vs 40.6 us) --
-        // but not on a row-block shard: there the runs that read a halo plane have to come last for every block, and ranges
-        // that meet a halo plane in their middle measured 57 vs 40.5 us on 38-plane shards (profiles/r02_trace_slab4_n2_*).
-        const bool streaming = (double)n * sizeof(T) >= 48e6;
-        if (c->march_lz > 0 || streaming || mp.has_low || mp.has_high) {
-            int best_lz = mp.nplanes;
-            double best = 1e300;
-            for (int segs = 1; segs <= mp.nplanes; segs++) {
-                const int lz = (mp.nplanes + segs - 1) / segs;
-                const long long nruns = (long long)mp.m * ((mp.nplanes + lz - 1) / lz);
-                const long long rounds = (nruns + grid - 1) / grid;
-                const double cost = (double)rounds * (lz + 0.7);
-                if (cost < best - 1e-9) {
-                    best = cost;
-                    best_lz = lz;
-                }
-            }
-            // (march_lz: option, tests) the runs that read a halo plane come last
-            // Order: the runs that read no halo plane, then the ones that END below the top halo plane (they need it as
-            // their last piece), and last the ones that START above the bottom halo plane (they need it first).
-            const int lz = std::min(c->march_lz > 0 ? c->march_lz : best_lz, mp.nplanes);
-            std::vector<MarchRun> top, bottom;
-            for (int z0 = 0; z0 < mp.nplanes; z0 += lz) {
-                const int L = std::min(lz, mp.nplanes - z0);
-                const MarchRun probe{0, z0, L, 0};
-                const bool low = z0 == 0 && mp.has_low;
-                for (int s = 0; s < mp.m; s++) (low ? bottom : (touches_halo(probe) ? top : inner)).push_back(MarchRun{s, z0, L, 0});
-            }
-            inner.insert(inner.end(), top.begin(), top.end());
-            inner.insert(inner.end(), bottom.begin(), bottom.end());
-            mp.grid = (int)std::min<size_t>(grid, inner.size());
-            for (size_t i = 0; i < inner.size(); i++) inner[i].next = i + mp.grid < inner.size() ? (int)(i + mp.grid) : -1;
-        } else {
-            // One contiguous range of (strip, plane) items per block, all of the same cost: equal segments dealt
-            // round-robin leave the last round half empty (one eighth of 300^3: 27.4 piece-times per block for 23.1 of work).
-            const long long Tn = (long long)mp.m * mp.nplanes;
-            const int G = (int)std::min<long long>(grid, Tn);
-            std::vector<std::vector<MarchRun>> lists(G);
-            const double run_cost = 0.7;
-            long long g = 0;
-            // cost still to be dealt: the items + one run per strip + one per block boundary
-            double remaining = (double)Tn + run_cost * ((double)mp.m + G);
-            for (int b = 0; b < G && g < Tn; b++) {
-                double budget = remaining / (G - b);
-                double used = 0;
-                while (g < Tn) {
-                    // a run: from g to the end of its strip, as far as the budget goes
-                    const int s = (int)(g / mp.nplanes), z0 = (int)(g % mp.nplanes);
-                    const int seg_end = mp.nplanes;
-                    int room = (int)std::floor(budget - used - run_cost + 0.5);
-                    if (b == G - 1) room = seg_end - z0;                         // the last block takes what is left
-                    if (room < 1) {
-                        if (used > 0) break;
-                        room = 1;
-                    }
-                    const int L = std::min(room, seg_end - z0);
-                    lists[b].push_back(MarchRun{s, z0, L, 0});
-                    used += L + run_cost;
-                    g += L;
-                    if (L < seg_end - z0 && b != G - 1) break;                   // budget exhausted inside the segment
-                }
-                remaining -= used;
-            }
-            // block b starts with runs[b]; every run names the block's next one
-            lists.erase(std::remove_if(lists.begin(), lists.end(), [](const std::vector<MarchRun> &l) { return l.empty(); }), lists.end());
-            mp.grid = (int)lists.size();
-            size_t rounds = 0;
-            for (auto &l : lists) rounds = std::max(rounds, l.size());
-            std::vector<int> at(lists.size(), -1);             // index of list b's latest run in `inner`
-            for (size_t k = 0; k < rounds; k++)
-                for (size_t b = 0; b < lists.size(); b++)
-                    if (lists[b].size() > k) {
-                        MarchRun r = lists[b][k];
-                        r.next = -1;
-                        if (at[b] >= 0) inner[at[b]].next = (int)inner.size();
-                        at[b] = (int)inner.size();
-                        inner.push_back(r);
-                    }
-        }
+        mp.grid = plan_march_runs(mp.m, mp.nplanes, c->sm_count, mp.has_low != 0, mp.has_high != 0,
+                                  (double)n * sizeof(T) >= 48e6, c->march_lz, &inner);
         mp.nruns = (int)inner.size();
         if (c->d_march_runs) cudaFree(c->d_march_runs);
         c->d_march_runs = nullptr;
@@ -1763,6 +1775,22 @@ static int create_ctx(cgb200_handle *out, int n, long long nnz, const void *aVal
     if (const char *e = getenv("CGB200_PDL")) c->pdl = atoi(e);
     *out = c;
     return CGB200_OK;
+}
+
+// The run plan of the plane-marching dir_spmv without a device: host logic for the CPU tests (include/cgb200.h).
+extern "C" int cgb200_plan_march_runs(int strips, int planes, int blocks, int has_low, int has_high, int streaming, int march_lz,
+                                      int *runs4, int capacity, int *grid) {
+    if (strips < 1 || planes < 1 || blocks < 1 || !grid || capacity < 0 || (capacity > 0 && !runs4))
+        return fail(CGB200_ERR_ARG, "cgb200_plan_march_runs: bad argument");
+    std::vector<MarchRun> runs;
+    *grid = plan_march_runs(strips, planes, blocks, has_low != 0, has_high != 0, streaming != 0, march_lz, &runs);
+    for (size_t i = 0; i < runs.size() && (int)i < capacity; i++) {
+        runs4[4 * i + 0] = runs[i].strip;
+        runs4[4 * i + 1] = runs[i].z0;
+        runs4[4 * i + 2] = runs[i].len;
+        runs4[4 * i + 3] = runs[i].next;
+    }
+    return (int)runs.size();
 }
 
 extern "C" int cgb200_create(cgb200_handle *out, int n, long long nnz, const void *aValues, const int *aPointers,

@@ -172,6 +172,14 @@ CGB200_API int cgb200_debug_read_patterns(cgb200_handle h, int which, void *out,
  * the number of bytes a kernel changed there since (0 = no out-of-bounds store), or < 0 on failure. */
 CGB200_API long long cgb200_check_guards(cgb200_handle h);
 
+/* Host logic of the plane-marching dir_spmv (csrc/cg2_march.cuh), callable without a GPU: how `strips` x `planes` work
+ * items are cut into runs for `blocks` thread blocks.  has_low / has_high: a halo plane below the first / above the last
+ * owned plane (row-block shards); streaming: the vectors do not fit the L2; march_lz > 0: planes per run (option
+ * "march_lz").  Writes up to `capacity` runs as {strip, first plane, planes, index of the same block's next run or -1}
+ * to runs4, the launch grid to *grid (block b starts with run b), returns the number of runs or < 0. */
+CGB200_API int cgb200_plan_march_runs(int strips, int planes, int blocks, int has_low, int has_high, int streaming,
+                                      int march_lz, int *runs4, int capacity, int *grid);
+
 /* Facts about a handle, for benches and tests:
  * [0] n [1] nnz [2] dtype [3] lanes_per_row [4] persistent grid of the SpMV kernel
  * [5] SM count [6] kernels launched so far [7] graph launches so far
