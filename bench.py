@@ -122,25 +122,72 @@ def make_problem_uncached(name, dtype, k):
     return A, np.ascontiguousarray(B, dtype=np_t)
 
 
+def summarise_clock_rows(rows, window=None, post=None):
+    """nvidia-smi rows ("timestamp, index, clocks.sm, clocks.max.sm, power.draw, reasons.active, hw_slowdown, hw_thermal_slowdown,
+    sw_thermal_slowdown, sw_power_cap") -> the `clocks` object of the bench line.  `window` = (t0, t1) wall-clock seconds of the
+    timed region: only samples inside it count.  When it holds none (a region shorter than nvidia-smi's ~100 ms period: the
+    sharded runs at 4 and 8 GPUs), the samples inside `post` -- extra untimed steps under the same load, run right after
+    -- are used instead and the object says so."""
+    import datetime
+    names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+    parsed = []
+    for r in rows:
+        if len(r) < 10:
+            continue
+        try:
+            ts = datetime.datetime.strptime(r[0].strip(), "%Y/%m/%d %H:%M:%S.%f").timestamp()
+            parsed.append((ts, float(r[2]), float(r[3]), float(r[4]), [nm for nm, v in zip(names, r[6:10]) if v.strip().lower().startswith("active")]))
+        except ValueError:
+            continue
+
+    def inside(w):
+        return [p for p in parsed if w is None or (w[0] - 0.02 <= p[0] <= w[1] + 0.02)]
+    out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+    use, where = inside(window), "timed region"
+    if not use and post is not None:
+        use, where = inside(post), "post-roll: untimed steps under the same load right after the timed region (shorter than the sampling period)"
+    if use:
+        out.update(sm_mhz=statistics.median(p[1] for p in use), sm_max_mhz=max(p[2] for p in use),
+                   reasons=sorted(set(x for p in use for x in p[4])), samples=len(use), power_w_max=max(p[3] for p in use),
+                   sampled_in=where)
+    return out
+
+
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe).  Started early (nvidia-smi
+    needs ~0.5 s to come up); begin() / end() bracket the timed region, post_begin() / post_end() an optional post-roll."""
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.p = None
+        self.t0 = self.t1 = self.p0 = self.p1 = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-lms", "100", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "-lms", "50", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             pass
 
+    def begin(self):
+        self.t0 = time.time()
+
+    def end(self):
+        self.t1 = time.time()
+
+    def post_begin(self):
+        self.p0 = time.time()
+
+    def post_end(self):
+        self.p1 = time.time()
+
+    def timed_seconds(self):
+        return (self.t1 - self.t0) if (self.t0 is not None and self.t1 is not None) else None
+
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.p is None:
-            return out
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         self.p.terminate()
         try:
             self.p.wait(timeout=5)
@@ -149,22 +196,25 @@ class ClockSampler:
         self.f.flush()
         rows = [l.strip().split(", ") for l in open(self.f.name) if l.strip()]
         os.unlink(self.f.name)
-        sm, mx, reasons, power = [], [], set(), []
-        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
-        for r in rows:
-            if len(r) < 9:
-                continue
-            try:
-                sm.append(float(r[1])); mx.append(float(r[2])); power.append(float(r[3]))
-            except ValueError:
-                continue
-            for nm, v in zip(names, r[5:9]):
-                if v.strip().lower().startswith("active"):
-                    reasons.add(nm)
-        if sm:
-            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons),
-                       samples=len(sm), power_w_max=max(power))
-        return out
+        window = (self.t0, self.t1) if self.t0 is not None and self.t1 is not None else None
+        post = (self.p0, self.p1) if self.p0 is not None and self.p1 is not None else None
+        return summarise_clock_rows(rows, window, post)
+
+
+def post_roll(sampler, step, seconds_per_step, min_seconds=0.6):
+    """Extra untimed steps under the same load when the timed region was too short for a clock sample.  Every rank calls it
+    with the same (max-reduced) seconds_per_step, so all run the same number of collective steps."""
+    timed = sampler.timed_seconds()
+    if timed is None or timed >= min_seconds or seconds_per_step <= 0:
+        return 0
+    n = max(1, min(200, int(min_seconds / seconds_per_step) + 1))
+    sampler.post_begin()
+    for _ in range(n):
+        step()
+    import torch
+    torch.cuda.synchronize()
+    sampler.post_end()
+    return n
 
 
 def measured_peak():
@@ -447,6 +497,7 @@ def run_row_block(args, wl, dtype, rank, local_rank, world):
         b_owned = np.ascontiguousarray(B[rb:re])
         shape = (n, nnz)
         del A
+    sampler = ClockSampler(local_rank)          # (early: nvidia-smi needs ~0.5 s to come up; samples are filtered by time)
     M = sharded.ShardedMatrix(plan, device=local_rank)
     stream = torch.cuda.Stream()
     M.set_stream(stream.cuda_stream)
@@ -459,7 +510,6 @@ def run_row_block(args, wl, dtype, rank, local_rank, world):
         dist.barrier()
         torch.cuda.synchronize()
 
-    sampler = ClockSampler(local_rank)
     with torch.cuda.stream(stream):
         b_dev = torch.from_numpy(b_owned).to("cuda")
         x_dev = torch.zeros(re - rb, dtype=tdt, device="cuda")
@@ -473,18 +523,25 @@ def run_row_block(args, wl, dtype, rank, local_rank, world):
         l0 = M.info()["launches"]
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sampler.begin()
         e0.record(stream)
         for _ in range(args.steps):
             info = step()
         e1.record(stream)
         barrier()
-        clocks = sampler.stop()
+        sampler.end()
         ms = e0.elapsed_time(e1)
         launches = M.info()["launches"] - l0
         save_trace(args, M, world, rank)
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_per_step = float(t.item()) / args.steps
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_per_step = float(t.item()) / args.steps
+        # (the same decision on every rank: the wall-clock length of the region is reduced too)
+        tw = torch.tensor([sampler.timed_seconds() or 0.0], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tw, op=dist.ReduceOp.MAX)
+        sampler.t1 = sampler.t0 + float(tw.item())
+        post_roll(sampler, step, ms_per_step / 1e3)
+        clocks = sampler.stop()
     value = ITERS_PER_STEP / (ms_per_step / 1e3)
 
     # e2e: this rank's slices of b and x0 in pinned host memory, x read back, every step
@@ -645,13 +702,17 @@ def main():
         launches0 = M.info()["launches"]
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sampler.begin()
         e0.record(stream)
         for _ in range(args.steps):
             step()
         e1.record(stream)
         barrier()
-        clocks = sampler.stop()
+        sampler.end()
         ms = e0.elapsed_time(e1)
+        if world == 1:
+            post_roll(sampler, step, ms / 1e3 / max(1, args.steps))     # (tiny configs: a step is a few milliseconds)
+        clocks = sampler.stop()
         launches = M.info()["launches"] - launches0
         save_trace(args, M, world, rank)
         timing = M.solve(b_dev, x=x_dev, k=k, max_iterations=ITERS_PER_STEP)[1].timing_ms

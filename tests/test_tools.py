@@ -51,3 +51,29 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert line["value"] > 0 and line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"] == {"value": line["value"], "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert line["config"]["name"] == "c1" and line["higher_is_better"] is True
+
+
+def test_clock_samples_are_taken_from_the_timed_region_or_the_post_roll():
+    """bench.summarise_clock_rows: nvidia-smi rows carry a timestamp; only samples inside the timed region count, and when
+    the region was shorter than the sampling period (sharded runs at 4 and 8 GPUs) the post-roll under the same load
+    stands in -- and the `clocks` object says so."""
+    import datetime
+    sys.path.insert(0, ROOT)
+    import bench
+    base = datetime.datetime(2026, 10, 18, 22, 30, 15, 0)
+
+    def row(ms, sm, power, cap="Not Active"):
+        ts = (base + datetime.timedelta(milliseconds=ms)).strftime("%Y/%m/%d %H:%M:%S.%f")[:-3]
+        return [ts, "0", str(sm), "1965", f"{power:.2f}", "0x0000000000000004", "Not Active", "Not Active", "Not Active", cap]
+    t = base.timestamp()
+    rows = [row(0, 345, 140.0), row(100, 1965, 700.0), row(200, 1800, 735.0, "Active"), row(300, 1800, 736.0, "Active"),
+            row(400, 1965, 400.0), ["garbage"], row(500, 1950, 690.0)]
+    c = bench.summarise_clock_rows(rows, window=(t + 0.15, t + 0.35))
+    assert c["samples"] == 2 and c["sm_mhz"] == 1800 and c["sm_max_mhz"] == 1965 and c["reasons"] == ["sw_power_cap"]
+    assert c["power_w_max"] == 736.0 and c["sampled_in"] == "timed region"
+    # a 40 ms region between two samples: nothing inside -> the post-roll
+    c = bench.summarise_clock_rows(rows, window=(t + 0.13, t + 0.17), post=(t + 0.45, t + 0.55))
+    assert c["samples"] == 1 and c["sm_mhz"] == 1950 and c["sampled_in"].startswith("post-roll")
+    # no window at all (older callers): every row; no rows: the empty object
+    assert bench.summarise_clock_rows(rows)["samples"] == 6
+    assert bench.summarise_clock_rows([], window=(t, t + 1)) == {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
