@@ -710,11 +710,11 @@ def main():
         barrier()
         sampler.end()
         ms = e0.elapsed_time(e1)
+        launches = M.info()["launches"] - launches0
+        save_trace(args, M, world, rank)
         if world == 1:
             post_roll(sampler, step, ms / 1e3 / max(1, args.steps))     # (tiny configs: a step is a few milliseconds)
         clocks = sampler.stop()
-        launches = M.info()["launches"] - launches0
-        save_trace(args, M, world, rank)
         timing = M.solve(b_dev, x=x_dev, k=k, max_iterations=ITERS_PER_STEP)[1].timing_ms
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
     if world > 1:
