@@ -201,13 +201,13 @@ class ClockSampler:
         return summarise_clock_rows(rows, window, post)
 
 
-def post_roll(sampler, step, seconds_per_step, min_seconds=0.6):
-    """Extra untimed steps under the same load when the timed region was too short for a clock sample.  Every rank calls it
-    with the same (max-reduced) seconds_per_step, so all run the same number of collective steps."""
+def post_roll(sampler, step, seconds_per_step, need=0.3, length=0.6):
+    """Extra untimed steps under the same load when the timed region (< `need` seconds) was too short for clock samples.
+    Every rank calls it with the same (max-reduced) numbers, so all run the same number of collective steps."""
     timed = sampler.timed_seconds()
-    if timed is None or timed >= min_seconds or seconds_per_step <= 0:
+    if timed is None or timed >= need or seconds_per_step <= 0:
         return 0
-    n = max(1, min(200, int(min_seconds / seconds_per_step) + 1))
+    n = max(1, min(200, int(length / seconds_per_step) + 1))
     sampler.post_begin()
     for _ in range(n):
         step()
