@@ -118,9 +118,7 @@ template <typename T> struct ShardEngine {
                 // joined again before the next kernel that writes v (join_push)
                 // a block per 2048 entries of the largest segment: 1 .. 32 for the faces of a grid partition, up to two
                 // per SM when the segment is a whole owned block (random columns)
-                static const int env_nb = getenv("CGB200_PUSH_BLOCKS") ? atoi(getenv("CGB200_PUSH_BLOCKS")) : 0;
-                const int nb = env_nb > 0 ? env_nb
-                                          : std::max(1, std::min(sh->max_send > (1 << 18) ? 2 * c->sm_count : 32, (sh->max_send + 2047) / 2048));
+                const int nb = std::max(1, std::min(sh->max_send > (1 << 18) ? 2 * c->sm_count : 32, (sh->max_send + 2047) / 2048));
                 const bool balanced_spmv = c->spmv_variant == 3 || (c->spmv_variant == 0 && c->irregular && c->auto_irregular);
                 if (sh->max_send > (1 << 18) || balanced_spmv) {
                     // whole-block segments, or the per-non-zero SpMV: IN stream order, ahead of the SpMV.  Every tile of that SpMV needs the halo, so
