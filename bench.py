@@ -146,6 +146,11 @@ def summarise_clock_rows(rows, window=None, post=None):
     use, where = inside(window), "timed region"
     if not use and post is not None:
         use, where = inside(post), "post-roll: untimed steps under the same load right after the timed region (shorter than the sampling period)"
+    if not use and parsed and window is not None:
+        # nvidia-smi's clock and the host's did not line up (time zone of the tool's output): the sampler is stopped right
+        # after the measured steps, so the LAST samples are the ones taken under load
+        span = (post[1] - post[0]) if post is not None else (window[1] - window[0])
+        use, where = parsed[-max(1, min(len(parsed), int(span / 0.05))):], "last samples before the sampler was stopped (timestamps did not match the host clock)"
     if use:
         out.update(sm_mhz=statistics.median(p[1] for p in use), sm_max_mhz=max(p[2] for p in use),
                    reasons=sorted(set(x for p in use for x in p[4])), samples=len(use), power_w_max=max(p[3] for p in use),
