@@ -150,7 +150,7 @@ def summarise_clock_rows(rows, window=None, post=None):
         # nvidia-smi's clock and the host's did not line up (time zone of the tool's output): the sampler is stopped right
         # after the measured steps, so the LAST samples are the ones taken under load
         span = (post[1] - post[0]) if post is not None else (window[1] - window[0])
-        use, where = parsed[-max(1, min(len(parsed), int(span / 0.05))):], "last samples before the sampler was stopped (timestamps did not match the host clock)"
+        use, where = parsed[-max(1, min(len(parsed), int(span / 0.1))):], "last samples before the sampler was stopped (timestamps did not match the host clock)"
     if use:
         out.update(sm_mhz=statistics.median(p[1] for p in use), sm_max_mhz=max(p[2] for p in use),
                    reasons=sorted(set(x for p in use for x in p[4])), samples=len(use), power_w_max=max(p[3] for p in use),
@@ -171,7 +171,7 @@ class ClockSampler:
         self.t0 = self.t1 = self.p0 = self.p1 = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-lms", "50", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "-lms", "100", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             pass
 
