@@ -34,7 +34,7 @@
 //
 // Row-block shards.  The direction has two buffers (the SpMV reads the old one everywhere while the owners write the
 // new one), so dir_spmv is read-only on its inputs and the entries of dn a peer needs can be recomputed and stored
-// straight into the peer's memory (NVLink) by a dedicated warp of the SAME kernel, ahead of everything else: they go
+// straight into the peer's memory (NVLink) by dedicated warps of the SAME kernel, ahead of everything else: they go
 // into the halo of the peer's RESIDUAL vector while the halos of both direction buffers stay zero, so that the
 // peer's gather r[j] + beta d[j] yields exactly dn[j] there.  An arrival flag (numbered by the all-reduce count, as
 // in kernels.cuh) tells the peer's TMA producer when its boundary chunks -- scheduled last -- may be loaded.
